@@ -1,0 +1,136 @@
+"""The C oracle against the committed known answers (tests/golden/oracle_kat.json, produced by the
+independent Python transliteration oracle/pyref.py) and against SURVEY.md 8(c)'s hand-evaluated values.
+Parity is unpinned by the reference itself: it ships no vectors and cannot be compiled here."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import pyref
+
+
+def test_ran2_known_answers(golden):
+    for rank, kat in golden["ran2"].items():
+        o = orc.Oracle(4, 4, 4, 1.0, 1.0, 1.0)
+        o.seed_ran2(int(rank))
+        got = [o.ran2() for _ in range(8)]
+        assert got == kat["first8"]                       # bit-exact
+        assert o.ran2_state() == (kat["idum"], kat["idum2"], kat["iy"])
+
+
+def test_ran2_survey_values():
+    # hand evaluation of ran2.f, seed -95648324 (rank 0)
+    o = orc.Oracle(4, 4, 4, 1.0, 1.0, 1.0)
+    o.seed_ran2(0)
+    assert [o.ran2() for _ in range(3)] == [0.46431189704058284, 0.13783885804764132, 0.3965865484019074]
+    o.seed_ran2(1)
+    assert [o.ran2() for _ in range(2)] == [0.623781193523389, 0.6663942391255453]
+
+
+def test_ran2_range_and_mean():
+    o = orc.Oracle(4, 4, 4, 1.0, 1.0, 1.0)
+    o.seed_ran2(2)
+    x = np.array([o.ran2() for _ in range(200000)])
+    assert x.min() > 0.0 and x.max() <= 1.0 - 1.2e-7
+    assert abs(x.mean() - 0.5) < 4 * (1 / np.sqrt(12 * x.size))
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    assert orc.philox4x32_10((0, 0), (0, 0, 0, 0)) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = 0xFFFFFFFF
+    assert orc.philox4x32_10((f, f), (f, f, f, f)) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert orc.philox4x32_10((0xA4093822, 0x299F31D0), (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+@pytest.mark.parametrize("n,vmax", [(80, 0.03), (200, 0.5), (7, 1.0)])
+def test_find_matches_bisection_semantics(n, vmax):
+    faces = np.array(pyref.make_faces(n, vmax))
+    rng = np.random.default_rng(n)
+    vals = list(rng.uniform(-0.1 * vmax, 2.1 * vmax, 300))
+    vals += list(faces) + [np.nextafter(f, np.inf) for f in faces] + [np.nextafter(f, -np.inf) for f in faces]
+    for v in vals:
+        assert orc.find(v, faces) == pyref.find(float(v), list(faces))
+    assert orc.find(faces[0], faces) == 1
+    assert orc.find(faces[-1], faces) == n                  # val == a(n) -> n-1 with n = nfaces
+    assert orc.find(np.nextafter(faces[-1], np.inf), faces) == -1
+    assert orc.find(-1e-300, faces) == -1
+
+
+def _check_packets(rec, draws_off, pk):
+    assert len(rec) == len(pk)
+    for r, p in zip(rec, pk):
+        assert [r["xp"], r["yp"], r["zp"]] == p["pos"]
+        assert [r["nxp"], r["nyp"], r["nzp"]] == p["dir"]
+        assert [r["xcell"], r["ycell"], r["zcell"]] == p["cell"]
+        assert (r["steps"], r["nscatt"], r["ndraws"], r["fate"]) == (p["steps"], p["nscatt"], p["ndraws"], p["fate"])
+        assert r["deposit"] == p["deposit"]
+    assert list(np.diff(draws_off)) == [p["ndraws"] for p in pk]
+
+
+def _check_tally(jmean, tally):
+    nz = {(i + 1, j + 1, k + 1): jmean[i, j, k] for i, j, k in zip(*np.nonzero(jmean))}
+    want = {tuple(k): v for k, v in tally if v != 0.0}   # rhokap == 0 voxels are visited with zero deposit
+    assert nz == want                                        # bit-exact, same summation order
+
+
+def test_shipped_regime_first_packets(golden):
+    o = orc.Oracle(80, 80, 80, 0.03, 0.03, 0.06)
+    o.gridset_uniform(o.init_opt1())
+    o.seed_ran2(0)
+    out = o.run(16, records=True, draws_cap=64)
+    _check_packets(out["records"], out["offsets"], golden["shipped_first16"])
+    _check_tally(o.jmean, golden["shipped_first16_tally"])
+    # SURVEY.md 8(c)(2)
+    r = out["records"][0]
+    # (xp went through "+ xmax ... - xmax" in tauint1, hence approx on the last bits)
+    assert (r["xp"], r["yp"]) == pytest.approx((0.005517907060891863, 0.006488561903839001), rel=1e-13)
+    assert r["deposit"] == pytest.approx(1.5746906053985468, rel=1e-15)
+    assert (r["xcell"], r["ycell"], r["steps"]) == (48, 49, 2)
+    r = out["records"][1]
+    assert (r["xp"], r["yp"]) == pytest.approx((0.000608783529361103, -0.007412552078470491), rel=1e-13)
+    assert (r["xcell"], r["ycell"], r["steps"]) == (41, 31, 2)
+
+
+def test_turbid_scatter_loop(golden):
+    o = orc.Oracle(20, 20, 20, 0.05, 0.05, 0.05)
+    rk = np.zeros((22, 22, 22), order="F")
+    rk[1:21, 1:21, 1:21] = 101.0
+    rk[1:21, 1:21, 1:5] = 55.0
+    o.set_rhokap(rk)
+    o.set_optics(100.0 / 101.0, 0.9)
+    o.set_flags(orc.FLAG_SCATTER)
+    o.seed_ran2(3)
+    out = o.run(12, records=True, draws_cap=4096)
+    _check_packets(out["records"], out["offsets"], golden["turbid_first12"])
+    _check_tally(o.jmean, golden["turbid_first12_tally"])
+
+
+def test_isotropic_branch(golden):
+    o = orc.Oracle(16, 16, 16, 0.04, 0.04, 0.04)
+    o.gridset_uniform(60.0)
+    o.set_optics(0.9, 0.0)
+    o.set_flags(orc.FLAG_SCATTER)
+    o.seed_ran2(5)
+    out = o.run(8, records=True, draws_cap=4096)
+    _check_packets(out["records"], out["offsets"], golden["isotropic_first8"])
+    _check_tally(o.jmean, golden["isotropic_first8_tally"])
+
+
+def test_pyref_live_agrees_on_fresh_case():
+    """Not only the frozen vectors: a fresh configuration, both transliterations run now."""
+    nx, ny, nz = 12, 10, 14
+    o = orc.Oracle(nx, ny, nz, 0.02, 0.025, 0.03)
+    rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+    ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    rk[1:-1, 1:-1, 1:-1] = 40.0 + 5.0 * ((ii + 2 * jj + 3 * kk) % 7)
+    rk[5:8, 4:7, nz - 2:nz + 1] = 0.0                      # an ablated crater under the beam
+    o.set_rhokap(rk)
+    o.set_optics(0.8, 0.7)
+    o.set_flags(orc.FLAG_SCATTER)
+    o.seed_ran2(11)
+    out = o.run(40, records=True, draws_cap=1 << 16)
+    tally, pk = pyref.photon_loop(40, nx, ny, nz, 0.02, 0.025, 0.03, lambda i, j, k: float(rk[i, j, k]),
+                                  pyref.Ran2(11), albedo=0.8, hgg=0.7, scatter=True)
+    _check_packets(out["records"], out["offsets"], pk)
+    _check_tally(o.jmean, [[list(k), v] for k, v in tally.items()])

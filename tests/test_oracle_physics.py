@@ -1,0 +1,104 @@
+"""Analytic invariants the shipped regime admits -- an oracle check that does not
+depend on another transliteration."""
+import numpy as np
+
+from oracle import oracle as orc
+
+
+def _shipped(n):
+    o = orc.Oracle(80, 80, 80, 0.03, 0.03, 0.06)
+    o.gridset_uniform(o.init_opt1())
+    o.seed_ran2(0)
+    return o, o.run(n, records=True)
+
+
+def test_shipped_regime_invariants():
+    n = 200000
+    o, out = _shipped(n)
+    st, rec, jm = out["stats"], out["records"], o.jmean
+    # 81.6 optical depths: nothing is transmitted, every packet deposits exactly its sampled tau
+    assert st["absorbed"] == n and sum(st["exits"]) == 0
+    assert st["draws"] == 4 * n
+    assert jm.sum() == np.float64(st["deposit_sum"]) or abs(jm.sum() - st["deposit_sum"]) < 1e-9 * n
+    # E[tau] = 1, Var = 1
+    assert abs(rec["deposit"].mean() - 1.0) < 4.0 / np.sqrt(n)
+    # mean voxel-steps per packet = 1 / (1 - exp(-kappa dz)) = 1.56395
+    tc = 680.0 * 0.0015
+    assert abs(st["voxel_steps"] / n - 1.0 / (1.0 - np.exp(-tc))) < 4 * 0.94 / np.sqrt(n)
+    # all deposits lie under the 0.025 cm disk: columns within 16.67 voxels of the axis (+1 for the edge)
+    ii, jj, kk = np.nonzero(jm)
+    r = np.hypot(ii + 0.5 - 40.0, jj + 0.5 - 40.0)
+    assert r.max() < 0.0125 / (0.06 / 80) + 0.7072
+    assert 870 <= len(set(zip(ii, jj))) <= 960          # pi*16.67^2 = 873 full columns + the rim
+    # per-layer expectation: e^{-(k-1) tc} - e^{-k tc} per packet (k counted from the top)
+    layer = jm.sum(axis=(0, 1))[::-1]
+    for k in range(1, 6):
+        # P(reach layer k) * E[min(tau', tc)] (memoryless), E[min(tau', tc)] = 1 - e^{-tc}
+        want = n * np.exp(-(k - 1) * tc) * (1.0 - np.exp(-tc))
+        assert abs(layer[k - 1] - want) < 5 * np.sqrt(n) * np.exp(-(k - 1) * tc / 2) + 1e-6 * n
+    # direction is never changed by the stub loop
+    assert np.all(rec["nzp"] == -1.0) and np.all(rec["nscatt"] == 0)
+
+
+def test_ablated_voxels_take_no_deposit():
+    o = orc.Oracle(40, 40, 40, 0.03, 0.03, 0.06)
+    o.gridset_uniform(680.0)
+    o.rhokap[1:41, 1:41, 36:41] = 0.0            # 5 ablated layers on top
+    o.seed_ran2(0)
+    out = o.run(20000, records=True)
+    assert o.jmean[:, :, 35:].sum() == 0.0
+    assert o.jmean[:, :, 34].sum() > 0.0
+    assert np.all(out["records"]["steps"] >= 6)
+
+
+def test_thin_slab_transmits():
+    # kappa*2zmax = 2.0 -> exp(-2) of the packets leave through the bottom face (-z, fate 5)
+    n = 100000
+    o = orc.Oracle(10, 10, 10, 0.05, 0.05, 0.05)
+    o.gridset_uniform(20.0)
+    o.seed_ran2(4)
+    out = o.run(n, records=True)
+    st = out["stats"]
+    p = np.exp(-2.0)
+    assert st["exits"][4] + st["absorbed"] == n
+    assert abs(st["exits"][4] / n - p) < 4 * np.sqrt(p * (1 - p) / n)
+    gone = out["records"]["fate"] == 5
+    assert np.all(out["records"]["zcell"][gone] == -1)
+    assert np.allclose(out["records"]["deposit"][gone], 2.0, rtol=1e-6)
+
+
+def test_scatter_energy_balance_and_hg_mean():
+    n = 20000
+    o = orc.Oracle(30, 30, 30, 0.5, 0.5, 0.5)
+    o.gridset_uniform(20.0)
+    o.set_optics(0.9, 0.9)
+    o.set_flags(orc.FLAG_SCATTER)
+    o.seed_ran2(6)
+    out = o.run(n, records=True)
+    st = out["stats"]
+    assert st["absorbed"] + sum(st["exits"]) == n
+    assert st["draws"] == out["records"]["ndraws"].sum()
+    # analog absorption: expected scatters per absorbed packet in an infinite medium = a/(1-a) = 9;
+    # escapes shorten it, so 0 < mean < 9
+    assert 1.0 < st["scatters"] / n < 9.0
+    d = out["records"]
+    norm = d["nxp"] ** 2 + d["nyp"] ** 2 + d["nzp"] ** 2
+    assert np.allclose(norm, 1.0, atol=1e-9)
+
+
+def test_run_ranks_equals_sum_of_single_ranks():
+    nx = 24
+    rk = np.zeros((nx + 2,) * 3, order="F")
+    rk[1:-1, 1:-1, 1:-1] = 300.0
+    res = orc.run_ranks(3, nx, nx, nx, 0.03, 0.03, 0.06, rk, 0.0, 0.9, 5000)
+    tot = np.zeros((nx,) * 3, order="F")
+    steps = 0
+    for r in range(3):
+        o = orc.Oracle(nx, nx, nx, 0.03, 0.03, 0.06)
+        o.set_rhokap(rk)
+        o.seed_ran2(r)
+        steps += o.run(5000)["stats"]["voxel_steps"]
+        tot += o.jmean
+    assert np.array_equal(res["jmean"], tot)
+    assert res["stats"]["packets"] == 15000 and res["stats"]["voxel_steps"] == steps
+    assert res["seconds"] > 0 and res["threads"] >= 1
