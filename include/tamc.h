@@ -1,0 +1,160 @@
+/*
+ * tamc.h -- C ABI of libtamc.so: the B200-native photon Monte-Carlo transport that replaces the
+ * per-rank photon loop and the jmean reduction of lewisfish/Tissue-Ablation-MC
+ * (/root/reference/src/mcpolar.f90:151-173) behind the reference's own call sites.
+ *
+ * The reference has no plugin/FFI layer: its boundary is a source-level cut in the main program.
+ * State crosses it through module globals -- iarray::rhokap, xface/yface/zface (iarray.f90:8-9),
+ * opt_prop::albedo,hgg,g2,n1,n2 (opt_prop.f90:5), constants::nxg,nyg,nzg (constants.f90:12), the
+ * locals nphotons,xmax,ymax,zmax,delta,iseed,id,numproc -- and comes back as iarray::jmeanGLOBAL.
+ * Each entry point below names the reference lines it stands in for.  The Fortran binding
+ * (iso_c_binding) and the patched call site are in tissue-ablation-mc_b200/fortran/ and
+ * INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a TAMC_E*
+ * code (message via tamc_last_error()); nothing throws or exits across the ABI; arrays are
+ * Fortran column-major fp64 exactly as the reference allocates them (subs.f90:62-68); the library
+ * never keeps a host pointer past the call that received it; there is no CPU fallback -- without a
+ * CUDA device every compute entry point fails with TAMC_ENODEVICE.
+ */
+#ifndef TAMC_H
+#define TAMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAMC_VERSION 100
+
+enum {
+    TAMC_OK = 0,
+    TAMC_EINVAL = 1,     /* bad argument */
+    TAMC_ENODEVICE = 2,  /* no CUDA device / device ordinal out of range */
+    TAMC_ECUDA = 3,      /* CUDA runtime error (see tamc_last_error) */
+    TAMC_ENCCL = 4,      /* NCCL missing or failed */
+    TAMC_ESTATE = 5,     /* call order: optics not set, communicator not initialised, ... */
+    TAMC_EREPLAY = 6     /* a replayed packet ran out of draws */
+};
+
+/* tamc_set_optics flags */
+enum {
+    TAMC_SCATTER = 1     /* run the albedo test + stokes() loop the driver's shell implies
+                            (mcpolar.f90:165-169, stokes.f90:6-153) instead of the shipped stub */
+};
+
+typedef struct tamc_context *tamc_handle;
+
+/* One record per packet (replay / validation).  88 bytes, no padding surprises. */
+typedef struct {
+    double xp, yp, zp;            /* final position, grid-centred (photon_vars.f90:11) */
+    double nxp, nyp, nzp;         /* final direction cosines */
+    double deposit;               /* sum of the packet's jmean increments (inttau2.f90:46,53) */
+    int32_t xcell, ycell, zcell;  /* final voxel, 1-based; -1 = outside (inttau2.f90:208-239) */
+    int32_t steps;                /* voxel-steps: passes of the loop body inttau2.f90:37-63 */
+    int32_t nscatt;               /* scattering events (mcpolar.f90:28 nscatt) */
+    int32_t ndraws;               /* uniform draws consumed */
+    int32_t fate;                 /* 0 absorbed/interaction; 1..6 left through -x,+x,-y,+y,-z,+z */
+    int32_t flags;                /* bit0: draw list exhausted */
+} tamc_packet_record;
+
+/* Counters and device timings of the most recent MC call on this handle (this rank only). */
+typedef struct {
+    int64_t packets;
+    int64_t voxel_steps;
+    int64_t scatters;
+    int64_t absorbed;             /* ended by interaction (stub) or analog absorption */
+    int64_t exits[6];             /* -x,+x,-y,+y,-z(bottom: transmitted),+z(top: reflected) */
+    double zero_ms;               /* tally clear */
+    double kernel_ms;             /* transport kernel, CUDA events on the library's stream */
+    double allreduce_ms;          /* ncclAllReduce of the tally (0 without a communicator) */
+    double h2d_ms, d2h_ms;        /* rhokap upload / jmean download inside the last calls */
+    int64_t gpu_launches;         /* kernels launched by the library for this call */
+} tamc_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+
+/* Device-side twin of alloc_array + gridset's face arrays (subs.f90:44-77, gridset.f90:23-31) and
+ * of the scalars the loop reads (mcpolar.f90:86-88 xmax..zmax, :112 delta).  `device` is the CUDA
+ * ordinal this handle (one MPI rank / one process) drives. */
+int tamc_init(int device, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax, double delta,
+              tamc_handle *out);
+/* Releases device buffers, streams, events and the communicator. */
+int tamc_finalize(tamc_handle h);
+
+/* sourceph.f90:23 spotSize (cm).  Default 250d-4. */
+int tamc_set_source_co2(tamc_handle h, double spot_diameter_cm);
+
+/* Uploads iarray::rhokap exactly as Fortran holds it -- (0:nxg+1,0:nyg+1,0:nzg+1), column-major,
+ * halo included, i.e. pass rhokap(0,0,0) -- plus opt_prop's scalars.  Called once after gridset
+ * (gridset.f90:33-45, ch_opt.f90:15-23) and again after every setupThermalCoeff (3dFD.f90:312-361).
+ * rhokap == NULL keeps the resident grid and only updates the scalars.  n1/n2 are accepted and
+ * stored (the reference reads them, mcpolar.f90:84-85, and never uses them). */
+int tamc_set_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2,
+                    int flags);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* Replaces mcpolar.f90:151-173: runs `nphotons` packets ON THIS RANK (the reference's per-rank
+ * `do j = 1, nphotons`), sums the tally over all ranks of the communicator (the MPI_allREDUCE) and
+ * writes the UNSCALED sum to jmean_global (nxg*nyg*nzg, column-major); line :174's scaling stays
+ * in the driver.  Packets draw from Philox4x32-10 keyed by `seed` with the global packet id as
+ * counter; ids are taken from the handle's cursor, which advances by nranks*nphotons per call so
+ * repeated calls (the ablation loop) never reuse a stream.  Blocking.  stats may be NULL. */
+int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats);
+
+/* Same work, split so a driver can overlap it or keep the tally on the device:
+ * enqueue tally clear + transport + all-reduce on the handle's stream; first_packet_id < 0 takes
+ * (and advances) the cursor, otherwise this rank runs ids [first_packet_id, first_packet_id+n). */
+int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id);
+int tamc_sync(tamc_handle h);
+int tamc_get_jmean(tamc_handle h, double *jmean_global);
+int tamc_get_stats(tamc_handle h, tamc_stats *stats);
+int tamc_seek(tamc_handle h, int64_t next_packet_id);
+
+/* Trace replay (validation): packet p consumes draws[draw_offsets[p] .. draw_offsets[p+1]) in the
+ * order the reference would call ran2 (sourceph.f90:28,29,34; inttau2.f90:36; scatter loop: albedo
+ * test, stokes.f90:48, :64).  fp64, no FMA contraction.  records and jmean are host arrays
+ * (npackets records; nxg*nyg*nzg doubles, overwritten); either may be NULL.  No all-reduce. */
+int tamc_run_replay(tamc_handle h, int64_t npackets, const int64_t *draw_offsets, const double *draws,
+                    tamc_packet_record *records, double *jmean);
+
+/* Production kernel with per-packet records (validation of the Philox path against the oracle
+ * running the same counter-based stream).  records: nphotons host entries. */
+int tamc_run_records(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id,
+                     tamc_packet_record *records, double *jmean);
+
+/* ---- multi-GPU: one process (MPI rank) per GPU ------------------------------------------------- */
+
+/* Rank 0 fills a 128-byte id, the driver broadcasts it (MPI_Bcast / torch.distributed), every
+ * rank calls tamc_comm_init.  After that tamc_run's reduction is one ncclAllReduce(ncclDouble,
+ * ncclSum) of the tally over NVLink on the handle's stream -- mcpolar.f90:173. */
+int tamc_comm_unique_id(void *id128);
+int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *id128);
+
+/* ---- device residency, tuning, measurement ----------------------------------------------------- */
+
+void *tamc_stream(tamc_handle h);          /* cudaStream_t the library launches on */
+double *tamc_jmean_device(tamc_handle h);  /* device tally, nxg*nyg*nzg fp64 */
+double *tamc_rhokap_device(tamc_handle h); /* device opacity grid with halo */
+/* Page-lock a caller-owned host array once so uploads/downloads run at PCIe speed. */
+int tamc_pin_host(void *ptr, uint64_t bytes);
+int tamc_unpin_host(void *ptr);
+/* Tuning knobs: "variant" (transport kernel), "block", "ctas_per_sm", "reduce" (0 = skip). */
+int tamc_set_option(tamc_handle h, const char *name, int64_t value);
+int64_t tamc_get_option(tamc_handle h, const char *name);
+/* Access-pattern-only kernel: the tally/grid address stream of `nphotons` straight-down packets
+ * with no transport arithmetic; ms receives its device time, steps the voxel-steps issued. */
+int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *ms, int64_t *steps);
+/* Writes >= bytes of device memory to evict L2 between timed steps. */
+int tamc_flush_l2(tamc_handle h, uint64_t bytes);
+
+const char *tamc_last_error(void);
+int tamc_version(void);
+int tamc_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,228 @@
+"""Production (Philox) kernels through the C ABI.
+
+ (1) exact: the oracle run on the same counter-based stream must give the same packets and grid;
+ (2) statistical: against the oracle on the reference's own ran2 stream, per-voxel z-scores from
+     batch means and chi-square over the grid (north_star: 3 sigma per voxel);
+ (3) properties that hold at BASELINE.json's full sizes.
+"""
+import numpy as np
+import pytest
+
+from tests.util import compare_grids, compare_records, make_oracle, make_transport
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261017
+
+
+def _philox_exact(cfg, n, first=0, rhokap=None):
+    rk = rhokap if rhokap is not None else cfg["rhokap"]()
+    o = make_oracle(cfg, rk)
+    o.seed_philox(SEED, first)
+    want = o.run(n, records=True)
+    t = make_transport(cfg, rk)
+    rec, jm = t.run_records(n, SEED, first)
+    scale = {"xp": cfg["xmax"], "yp": cfg["ymax"], "zp": cfg["zmax"], "nxp": 1.0, "nyp": 1.0, "nzp": 1.0}
+    compare_records(rec, want["records"], rtol=1e-9, scale=scale)
+    compare_grids(jm, o.jmean, rtol=1e-10)
+    # both kernel shapes and both tally policies give the same grid and counters
+    for variant in (0, 1):
+        for merge in (0, 1):
+            for thr in ((1, 1), (8, 8), (32, 32)):
+                if variant == 0 and thr != (1, 1):
+                    continue
+                t.set_option("variant", variant)
+                t.set_option("merge", merge)
+                t.set_option("refill_min", thr[0])
+                t.set_option("scatter_min", thr[1])
+                t.run_async(n, SEED, first)
+                jm2 = t.get_jmean()
+                st = t.get_stats()
+                compare_grids(jm2, o.jmean, rtol=1e-10)
+                assert st["packets"] == n
+                assert st["voxel_steps"] == want["stats"]["voxel_steps"]
+                assert st["scatters"] == want["stats"]["scatters"]
+                assert st["absorbed"] == want["stats"]["absorbed"]
+                assert st["exits"] == want["stats"]["exits"]
+    t.close()
+
+
+def test_philox_exact_shipped():
+    import tamc
+
+    _philox_exact(tamc.configs.CONFIGS["shipped80"], 125000)
+
+
+def test_philox_exact_offset_ids_cross_2_32():
+    import tamc
+
+    _philox_exact(tamc.configs.CONFIGS["shipped80"], 30000, first=(1 << 32) - 10000)
+
+
+def test_philox_exact_turbid():
+    import tamc
+
+    _philox_exact(tamc.configs.scaled("turbid200", 60), 6000)
+
+
+def test_philox_exact_skin_and_crater():
+    import tamc
+
+    _philox_exact(tamc.configs.scaled("skin200", 100), 6000)
+    rk = list(tamc.configs.crater_sequence(80, 5))[4]
+    _philox_exact(tamc.configs.CONFIGS["shipped80"], 40000, rhokap=rk)
+
+
+def test_partition_invariance_and_cursor():
+    """Packets keyed by global id: any split over calls / GPUs sums to the same grid."""
+    import tamc
+
+    cfg = tamc.configs.scaled("skin200", 64)
+    t = make_transport(cfg)
+    n = 40000
+    t.run_async(n, SEED, 0)
+    whole = t.get_jmean()
+    parts = np.zeros_like(whole)
+    for lo, hi in ((0, 10000), (10000, 10001), (10001, 40000)):
+        t.run_async(hi - lo, SEED, lo)
+        parts += t.get_jmean()
+    compare_grids(parts, whole, rtol=1e-10)
+    # tamc_run advances the cursor: two calls of n/2 == one call of n from id 0
+    t.seek(0)
+    a, sa = t.run(n // 2, SEED)
+    b, sb = t.run(n // 2, SEED)
+    assert not np.array_equal(a, b)
+    compare_grids(a + b, whole, rtol=1e-10)
+    assert sa["packets"] == sb["packets"] == n // 2
+    assert sa["gpu_launches"] >= 1 and sa["kernel_ms"] > 0
+    t.close()
+
+
+def _batch_grids_gpu(cfg, batches, per_batch):
+    t = make_transport(cfg)
+    out = []
+    for b in range(batches):
+        t.run_async(per_batch, SEED, b * per_batch)
+        out.append(t.get_jmean().copy())
+    t.close()
+    return np.stack(out)
+
+
+def _batch_grids_oracle(cfg, batches, per_batch):
+    out = []
+    for b in range(batches):
+        o = make_oracle(cfg)
+        o.seed_ran2(b)                    # one emulated MPI rank per batch (mcpolar.f90:97-98)
+        o.run(per_batch)
+        out.append(o.jmean.copy())
+    return np.stack(out)
+
+
+def _chi_square(a, b, min_mean):
+    """Two sets of batch grids -> per-voxel z from batch means, chi2/dof over well-populated voxels."""
+    ma, mb = a.mean(0), b.mean(0)
+    va, vb = a.var(0, ddof=1) / a.shape[0], b.var(0, ddof=1) / b.shape[0]
+    sel = (ma > min_mean) & (mb > min_mean) & (va + vb > 0)
+    z = (ma[sel] - mb[sel]) / np.sqrt(va[sel] + vb[sel])
+    return z, float((z ** 2).mean())
+
+
+@pytest.mark.parametrize("name,n,per_batch,min_mean", [("shipped80", 80, 60000, 20.0), ("skin200", 50, 12000, 15.0)])
+def test_chi_square_against_ran2_oracle(name, n, per_batch, min_mean):
+    import tamc
+
+    cfg = tamc.configs.scaled(name, n)
+    K = 16
+    g = _batch_grids_gpu(cfg, K, per_batch)
+    c = _batch_grids_oracle(cfg, K, per_batch)
+    z, chi2 = _chi_square(g, c, min_mean)
+    assert z.size > 200
+    # z follows Student-t with ~2(K-1)=30 dof: var = 30/28 = 1.07; chi2/dof within 5 sigma of that
+    assert abs(chi2 - 1.07) < 5 * np.sqrt(2.5 / z.size) + 0.05, (chi2, z.size)
+    # 3-sigma criterion: the fraction beyond 3 sigma stays near the expected 0.5 % (t_30), never a bulk shift
+    assert (np.abs(z) > 3).mean() < 0.012
+    assert abs(z.mean()) < 5 / np.sqrt(z.size)
+    # total absorbed energy per packet agrees within 4 sigma
+    ta, tb = g.sum(axis=(1, 2, 3)), c.sum(axis=(1, 2, 3))
+    assert abs(ta.mean() - tb.mean()) < 4 * np.sqrt(ta.var(ddof=1) / K + tb.var(ddof=1) / K)
+
+
+def test_fractions_reflected_absorbed_transmitted():
+    """Totals by fate (north_star: reflected/absorbed/transmitted fractions) vs the ran2 oracle."""
+    import tamc
+
+    cfg = tamc.configs.scaled("skin200", 40)
+    n = 200000
+    t = make_transport(cfg)
+    t.run_async(n, SEED, 0)
+    st = t.get_stats()
+    t.close()
+    o = make_oracle(cfg)
+    o.seed_ran2(0)
+    ref = o.run(n)["stats"]
+    assert st["absorbed"] + sum(st["exits"]) == n
+    for got, want in [(st["absorbed"], ref["absorbed"])] + list(zip(st["exits"], ref["exits"])):
+        p = max(want, 1) / n
+        assert abs(got - want) < 5 * np.sqrt(2 * n * p * (1 - p)) + 5
+    assert abs(st["voxel_steps"] / ref["voxel_steps"] - 1) < 0.02
+    assert abs(st["scatters"] / ref["scatters"] - 1) < 0.02
+
+
+def test_full_size_homog200_properties():
+    """BASELINE config 2 at full grid size, 2e7 packets: properties that need no oracle run."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["homog200"]
+    n = 20_000_000
+    t = make_transport(cfg)
+    jm, st = t.run(n, SEED)
+    t.close()
+    tc = 680.0 * (0.12 / 200)
+    assert st["packets"] == n and st["absorbed"] == n and sum(st["exits"]) == 0
+    assert abs(jm.sum() / n - 1.0) < 5 / np.sqrt(n)                       # E[tau] = 1
+    assert abs(st["voxel_steps"] / n - 1 / (1 - np.exp(-tc))) < 5 * 2.5 / np.sqrt(n)
+    ii, jj, kk = np.nonzero(jm)
+    r = np.hypot(ii + 0.5 - 100.0, jj + 0.5 - 100.0)
+    assert r.max() < 0.0125 / (0.06 / 200) + 0.7072                      # under the 0.025 cm disk
+    layer = jm.sum(axis=(0, 1))[::-1]
+    for k in range(1, 8):
+        want = n * np.exp(-(k - 1) * tc) * (1 - np.exp(-tc))
+        assert abs(layer[k - 1] / want - 1) < 6 / np.sqrt(want)
+    # linearity in packet count: a second, disjoint id range gives a statistically identical grid
+    t = make_transport(cfg)
+    t.seek(n)
+    jm2, _ = t.run(n, SEED)
+    t.close()
+    top = (jm[:, :, -1] > 0) & (jm2[:, :, -1] > 0)
+    z = (jm[:, :, -1][top] - jm2[:, :, -1][top]) / np.sqrt(jm[:, :, -1][top] + jm2[:, :, -1][top])
+    assert 0.2 < (z ** 2).mean() < 1.2          # deposit per hit <= tc < 1 -> variance below Poisson
+
+
+def test_error_behaviour():
+    import tamc
+
+    t = tamc.MCTransport(8, 8, 8, 0.1, 0.1, 0.1)
+    with pytest.raises(tamc.TamcError) as e:
+        t.run(10, 1)
+    assert e.value.code == 5                     # TAMC_ESTATE: optics not set
+    rk = np.zeros((10, 10, 10), order="F")
+    with pytest.raises(tamc.TamcError) as e:
+        t.set_optics(rk, 1.5, 0.9)
+    assert e.value.code == 1
+    with pytest.raises(ValueError):
+        t.set_optics(np.zeros((8, 8, 8)), 0.0, 0.9)
+    with pytest.raises(tamc.TamcError):
+        t.set_source_co2(1.0)                    # spot wider than the face
+    t.set_optics(rk, 0.0, 0.9)
+    jm, st = t.run(0, 1)
+    assert st["packets"] == 0 and not jm.any()
+    # rhokap == 0 everywhere: every packet crosses the grid with zero deposit and leaves through -z
+    jm, st = t.run(1000, 1)
+    assert not jm.any() and st["exits"][4] == 1000 and st["voxel_steps"] == 8000
+    t.close()
+    with pytest.raises(tamc.TamcError) as e:
+        tamc.MCTransport(8, 8, 8, 0.1, 0.1, 0.1, delta=1e-30)
+    assert e.value.code == 1
+    with pytest.raises(tamc.TamcError) as e:
+        tamc.MCTransport(8, 8, 8, 0.1, 0.1, 0.1, device=99)
+    assert e.value.code == 2

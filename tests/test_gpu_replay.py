@@ -1,0 +1,117 @@
+"""Trace replay: the CUDA path fed the reference's ran2 sequence packet by packet must reproduce the
+oracle's photon paths and deposits (north_star: 1e-6 relative, fp64).  Calls go through the C ABI."""
+import numpy as np
+import pytest
+
+from tests.util import compare_grids, compare_records, make_oracle, make_transport
+
+pytestmark = pytest.mark.gpu
+
+
+def _replay_case(cfg, npackets, rank=0, cap_per_packet=4, rhokap=None):
+    import tamc  # noqa: F401
+
+    rk = rhokap if rhokap is not None else cfg["rhokap"]()
+    o = make_oracle(cfg, rk)
+    o.seed_ran2(rank)
+    out = o.run(npackets, records=True, draws_cap=npackets * cap_per_packet)
+    t = make_transport(cfg, rk)
+    rec, jm = t.run_replay(out["offsets"], out["draws"])
+    st = t.get_stats()
+    scale = {"xp": cfg["xmax"], "yp": cfg["ymax"], "zp": cfg["zmax"], "nxp": 1.0, "nyp": 1.0, "nzp": 1.0}
+    worst = compare_records(rec, out["records"], scale=scale)
+    gerr = compare_grids(jm, o.jmean)
+    assert st["packets"] == npackets
+    assert st["voxel_steps"] == out["stats"]["voxel_steps"]
+    assert st["scatters"] == out["stats"]["scatters"]
+    assert st["absorbed"] == out["stats"]["absorbed"]
+    assert st["exits"] == out["stats"]["exits"]
+    t.close()
+    return worst, gerr
+
+
+def test_replay_shipped_regime_80():
+    import tamc
+
+    worst, gerr = _replay_case(tamc.configs.CONFIGS["shipped80"], 125000)
+    assert worst < 1e-9 and gerr < 1e-11
+
+
+def test_replay_other_rank_seed():
+    import tamc
+
+    _replay_case(tamc.configs.CONFIGS["shipped80"], 20000, rank=5)
+
+
+def test_replay_homogeneous_200_full_grid():
+    import tamc
+
+    _replay_case(tamc.configs.CONFIGS["homog200"], 400000)
+
+
+def test_replay_turbid_scatter_loop():
+    import tamc
+
+    cfg = tamc.configs.scaled("turbid200", 60)
+    _replay_case(cfg, 4000, rank=2, cap_per_packet=4000)
+
+
+def test_replay_turbid_200_subset():
+    import tamc
+
+    _replay_case(tamc.configs.CONFIGS["turbid200"], 3000, cap_per_packet=6000)
+
+
+def test_replay_layered_skin():
+    import tamc
+
+    cfg = tamc.configs.scaled("skin200", 100)
+    _replay_case(cfg, 5000, rank=1, cap_per_packet=4000)
+
+
+def test_replay_isotropic_branch():
+    cfg = dict(n=24, xmax=0.04, ymax=0.04, zmax=0.04, albedo=0.9, hgg=0.0, flags=1)
+    rk = np.zeros((26, 26, 26), order="F")
+    rk[1:-1, 1:-1, 1:-1] = 60.0
+    _replay_case(cfg, 20000, rank=5, cap_per_packet=400, rhokap=rk)
+
+
+def test_replay_ablated_crater_and_varying_grid():
+    import tamc
+
+    rk = next(iter(list(tamc.configs.crater_sequence(80, 6))[5:]))
+    cfg = dict(tamc.configs.CONFIGS["shipped80"])
+    _replay_case(cfg, 50000, rank=3, rhokap=rk)
+    # non-cubic voxels, anisotropic extents, heterogeneous opacity, scatter on
+    n = 30
+    cfg = dict(n=n, xmax=0.02, ymax=0.035, zmax=0.05, albedo=0.85, hgg=0.7, flags=1)
+    ii, jj, kk = np.meshgrid(*[np.arange(1, n + 1)] * 3, indexing="ij")
+    rk = np.zeros((n + 2,) * 3, order="F")
+    rk[1:-1, 1:-1, 1:-1] = 40.0 + 5.0 * ((ii + 2 * jj + 3 * kk) % 7)
+    rk[12:18, 12:18, n - 3:n + 1] = 0.0
+    _replay_case(cfg, 20000, rank=7, cap_per_packet=600, rhokap=rk)
+
+
+def test_replay_thin_slab_exits():
+    cfg = dict(n=10, xmax=0.05, ymax=0.05, zmax=0.05, albedo=0.0, hgg=0.9, flags=0)
+    rk = np.zeros((12, 12, 12), order="F")
+    rk[1:-1, 1:-1, 1:-1] = 20.0
+    _replay_case(cfg, 30000, rank=4, rhokap=rk)
+
+
+def test_replay_empty_and_short_draw_lists():
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["shipped80"]
+    t = make_transport(cfg)
+    rec, jm = t.run_replay(np.zeros(1, dtype=np.int64), np.zeros(0))
+    assert rec.size == 0 and not jm.any()
+    o = make_oracle(cfg)
+    o.seed_ran2(0)
+    out = o.run(100, records=True, draws_cap=400)
+    off = out["offsets"].copy()
+    off[50:] -= 1                                   # packet 49 gets 3 draws instead of 4
+    with pytest.raises(tamc.TamcError) as e:
+        t.run_replay(off, out["draws"][:-1])
+    assert e.value.code == 6                        # TAMC_EREPLAY
+    t.close()

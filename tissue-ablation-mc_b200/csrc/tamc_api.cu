@@ -1,0 +1,598 @@
+// tamc_api.cu -- the C ABI of libtamc.so (include/tamc.h): device residency of the grids, launch of
+// the transport kernels, the tally all-reduce over NCCL, and the host<->device copies at the
+// boundary with the reference's driver (/root/reference/src/mcpolar.f90:151-173).
+//
+// NCCL is bound at run time (dlopen) so a single-GPU caller needs no NCCL at all and a process
+// that already loaded an NCCL (e.g. through torch) shares that copy.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tamc_internal.h"
+
+using namespace tamc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(TAMC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound lazily
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *so = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.so ? &api : nullptr;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        api.so = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.so) break;
+    }
+    if (!api.so) return nullptr;
+#define BIND(f) api.f = reinterpret_cast<decltype(api.f)>(dlsym(api.so, "nccl" #f))
+    BIND(GetUniqueId); BIND(CommInitRank); BIND(AllReduce); BIND(CommDestroy); BIND(GetErrorString); BIND(GetVersion);
+#undef BIND
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+        dlclose(api.so);
+        api.so = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess)                                                                           \
+            return fail(TAMC_ENCCL, std::string(#call) + ": " +                                           \
+                                        (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "nccl error")); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum { EV_ZERO0 = 0, EV_K0, EV_K1, EV_AR1, EV_H0, EV_H1, EV_D0, EV_D1, EV_N };
+
+struct tamc_context {
+    int device = 0;
+    int num_sms = 148;
+    int nxg = 0, nyg = 0, nzg = 0;
+    double xmax = 0, ymax = 0, zmax = 0, delta = 0;
+    double spot = 250e-4;               // sourceph.f90:23
+    double albedo = 0, hgg = 0.9, n1 = 1, n2 = 1;
+    int flags = 0;
+    bool optics_set = false;
+
+    size_t n_rhokap = 0, n_jmean = 0;
+    double *d_rhokap = nullptr, *d_jmean = nullptr, *d_faces = nullptr, *d_flush = nullptr;
+    size_t flush_elems = 0;
+    unsigned long long *d_cnt = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_N] = {};
+
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    int64_t cursor = 0;
+
+    LaunchCfg cfg{1, 256, 0, 148, 1, 1, -1};
+    int reduce = 1;
+
+    // bookkeeping of the last call
+    int64_t last_launches = 0;
+    bool timed_reduce = false, timed_h2d = false, timed_d2h = false, ran = false;
+};
+
+static int check(tamc_handle h)
+{
+    if (!h) return fail(TAMC_EINVAL, "null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(TAMC_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return TAMC_OK;
+}
+
+static DevGrid make_grid(const tamc_context *c)
+{
+    DevGrid g;
+    g.nxg = c->nxg; g.nyg = c->nyg; g.nzg = c->nzg;
+    g.sx = c->nxg + 2;
+    g.sxy = (long long)(c->nxg + 2) * (c->nyg + 2);
+    g.xmax = c->xmax; g.ymax = c->ymax; g.zmax = c->zmax; g.delta = c->delta;
+    g.spot_r2 = (c->spot / 2.) * (c->spot / 2.);                       // sourceph.f90:28
+    g.zp0 = c->zmax - (1.e-8 * (2. * c->zmax / (double)c->nzg));       // sourceph.f90:32
+    g.inv_dx = (double)c->nxg / (2. * c->xmax);
+    g.inv_dy = (double)c->nyg / (2. * c->ymax);
+    g.inv_dz = (double)c->nzg / (2. * c->zmax);
+    g.albedo = c->albedo; g.hgg = c->hgg; g.g2 = c->hgg * c->hgg;      // ch_opt.f90:16
+    g.flags = c->flags;
+    g.rhokap = c->d_rhokap; g.jmean = c->d_jmean; g.faces = c->d_faces;
+    return g;
+}
+
+static bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *tamc_last_error(void) { return g_err.c_str(); }
+extern "C" int tamc_version(void) { return TAMC_VERSION; }
+
+extern "C" int tamc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int tamc_init(int device, int nxg, int nyg, int nzg, double xmax, double ymax, double zmax, double delta,
+                         tamc_handle *out)
+{
+    if (!out) return fail(TAMC_EINVAL, "tamc_init: out is null");
+    *out = nullptr;
+    if (nxg < 1 || nyg < 1 || nzg < 1 || nxg > 4096 || nyg > 4096 || nzg > 4096)
+        return fail(TAMC_EINVAL, "tamc_init: grid dimensions must be in [1,4096]");
+    if (!(xmax > 0) || !(ymax > 0) || !(zmax > 0) || !(delta > 0))
+        return fail(TAMC_EINVAL, "tamc_init: xmax, ymax, zmax and delta must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(TAMC_ENODEVICE, "tamc_init: no CUDA device (libtamc has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(TAMC_ENODEVICE, "tamc_init: device ordinal out of range");
+    // the snap `face -+ delta` must move the position off the face (inttau2.f90:142-166)
+    if (2. * zmax + delta == 2. * zmax || 2. * xmax + delta == 2. * xmax || 2. * ymax + delta == 2. * ymax)
+        return fail(TAMC_EINVAL, "tamc_init: delta is below the fp64 resolution of the face coordinates");
+
+    CU(cudaSetDevice(device));
+    tamc_context *c = new tamc_context();
+    c->device = device;
+    c->nxg = nxg; c->nyg = nyg; c->nzg = nzg;
+    c->xmax = xmax; c->ymax = ymax; c->zmax = zmax; c->delta = delta;
+    c->n_rhokap = (size_t)(nxg + 2) * (nyg + 2) * (nzg + 2);
+    c->n_jmean = (size_t)nxg * nyg * nzg;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->cfg.num_sms = c->num_sms;
+
+    // gridset.f90:23-31: face(i) = (i-1) * 2. * max/n, left to right
+    std::vector<double> faces;
+    faces.reserve((size_t)nxg + nyg + nzg + 3);
+    for (int i = 1; i <= nxg + 1; ++i) faces.push_back((double)(i - 1) * 2. * xmax / (double)nxg);
+    for (int i = 1; i <= nyg + 1; ++i) faces.push_back((double)(i - 1) * 2. * ymax / (double)nyg);
+    for (int i = 1; i <= nzg + 1; ++i) faces.push_back((double)(i - 1) * 2. * zmax / (double)nzg);
+
+    auto cleanup = [&](int code) { tamc_finalize(c); return code; };
+#define CUI(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            fail(TAMC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                        \
+            return cleanup(TAMC_ECUDA);                                                                  \
+        }                                                                                                \
+    } while (0)
+    CUI(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_N; ++i) CUI(cudaEventCreate(&c->ev[i]));
+    CUI(cudaMalloc(&c->d_rhokap, c->n_rhokap * sizeof(double)));
+    CUI(cudaMalloc(&c->d_jmean, c->n_jmean * sizeof(double)));
+    CUI(cudaMalloc(&c->d_faces, faces.size() * sizeof(double)));
+    CUI(cudaMalloc(&c->d_cnt, CNT_N * sizeof(unsigned long long)));
+    CUI(cudaMemcpy(c->d_faces, faces.data(), faces.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUI(cudaMemset(c->d_rhokap, 0, c->n_rhokap * sizeof(double)));
+    CUI(cudaMemset(c->d_jmean, 0, c->n_jmean * sizeof(double)));
+    CUI(cudaMemset(c->d_cnt, 0, CNT_N * sizeof(unsigned long long)));
+#undef CUI
+    *out = c;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_finalize(tamc_handle h)
+{
+    if (!h) return TAMC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
+    cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_cnt); cudaFree(h->d_flush);
+    for (int i = 0; i < EV_N; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_set_source_co2(tamc_handle h, double spot_diameter_cm)
+{
+    if (int rc = check(h)) return rc;
+    if (!(spot_diameter_cm >= 0)) return fail(TAMC_EINVAL, "tamc_set_source_co2: negative spot diameter");
+    // the launch formula (sourceph.f90:45-46) indexes outside the grid if the spot overhangs it
+    if (spot_diameter_cm / 2. >= h->xmax || spot_diameter_cm / 2. >= h->ymax)
+        return fail(TAMC_EINVAL, "tamc_set_source_co2: spot does not fit on the top face");
+    h->spot = spot_diameter_cm;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_set_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2,
+                               int flags)
+{
+    if (int rc = check(h)) return rc;
+    if (!(albedo >= 0. && albedo <= 1.)) return fail(TAMC_EINVAL, "tamc_set_optics: albedo must be in [0,1]");
+    if (!(hgg > -1. && hgg < 1.)) return fail(TAMC_EINVAL, "tamc_set_optics: hgg must be in (-1,1)");
+    if (flags & ~TAMC_SCATTER) return fail(TAMC_EINVAL, "tamc_set_optics: unknown flag bits");
+    if (!rhokap && !h->optics_set) return fail(TAMC_ESTATE, "tamc_set_optics: first call needs the rhokap grid");
+    h->timed_h2d = false;
+    if (rhokap) {
+        CU(cudaEventRecord(h->ev[EV_H0], h->stream));
+        if (host_is_pinned(rhokap))
+            CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        else {
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpy(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        CU(cudaEventRecord(h->ev[EV_H1], h->stream));
+        h->timed_h2d = true;
+    }
+    h->albedo = albedo; h->hgg = hgg; h->n1 = n1; h->n2 = n2; h->flags = flags;
+    h->optics_set = true;
+    return TAMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU
+// ------------------------------------------------------------------------------------------------
+extern "C" int tamc_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(TAMC_EINVAL, "tamc_comm_unique_id: null buffer");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(TAMC_ENCCL, "libnccl.so.2 not found");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(n->GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return TAMC_OK;
+}
+
+extern "C" int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *id128)
+{
+    if (int rc = check(h)) return rc;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(TAMC_EINVAL, "tamc_comm_init: bad rank/size/id");
+    if (h->comm) return fail(TAMC_ESTATE, "tamc_comm_init: communicator already initialised");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(TAMC_ENCCL, "libnccl.so.2 not found");
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NC(n->CommInitRank(&h->comm, nranks, id, rank));
+    h->nranks = nranks;
+    h->rank = rank;
+    return TAMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot path
+// ------------------------------------------------------------------------------------------------
+static int enqueue_reduce(tamc_handle h)
+{
+    h->timed_reduce = false;
+    if (h->comm && h->reduce && h->nranks > 1) {
+        // mcpolar.f90:173: MPI_allREDUCE(jmean, jmeanGLOBAL, nxg*nyg*nzg, MPI_DOUBLE_PRECISION, MPI_SUM)
+        NC(nccl_api()->AllReduce(h->d_jmean, h->d_jmean, h->n_jmean, ncclDouble, ncclSum, h->comm, h->stream));
+        h->timed_reduce = true;
+    }
+    CU(cudaEventRecord(h->ev[EV_AR1], h->stream));
+    return TAMC_OK;
+}
+
+extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id)
+{
+    if (int rc = check(h)) return rc;
+    if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run: tamc_set_optics has not been called");
+    if (nphotons < 0 || nphotons > ((int64_t)1 << 46)) return fail(TAMC_EINVAL, "tamc_run: nphotons out of range");
+    int64_t first = first_packet_id;
+    if (first < 0) {
+        first = h->cursor + (int64_t)h->rank * nphotons;     // rank r runs its own nphotons (mcpolar.f90:151)
+        h->cursor += (int64_t)h->nranks * nphotons;
+    }
+    const DevGrid g = make_grid(h);
+    int launches = 0;
+    CU(cudaEventRecord(h->ev[EV_ZERO0], h->stream));
+    CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));   // zarray / jmean = 0. (mcpolar.f90:185)
+    CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev[EV_K0], h->stream));
+    CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches));
+    CU(cudaEventRecord(h->ev[EV_K1], h->stream));
+    if (int rc = enqueue_reduce(h)) return rc;
+    h->last_launches = launches;
+    h->timed_d2h = false;
+    h->ran = true;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_sync(tamc_handle h)
+{
+    if (int rc = check(h)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return TAMC_OK;
+}
+
+extern "C" int tamc_get_jmean(tamc_handle h, double *jmean_global)
+{
+    if (int rc = check(h)) return rc;
+    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_get_jmean: null destination");
+    CU(cudaEventRecord(h->ev[EV_D0], h->stream));
+    if (host_is_pinned(jmean_global))
+        CU(cudaMemcpyAsync(jmean_global, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else {
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(jmean_global, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    CU(cudaEventRecord(h->ev[EV_D1], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->timed_d2h = true;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_get_stats(tamc_handle h, tamc_stats *st)
+{
+    if (int rc = check(h)) return rc;
+    if (!st) return fail(TAMC_EINVAL, "tamc_get_stats: null destination");
+    memset(st, 0, sizeof(*st));
+    if (!h->ran) return TAMC_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    unsigned long long cnt[CNT_N];
+    CU(cudaMemcpy(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    st->packets = (int64_t)cnt[CNT_PACKETS];
+    st->voxel_steps = (int64_t)cnt[CNT_STEPS];
+    st->scatters = (int64_t)cnt[CNT_SCATTERS];
+    st->absorbed = (int64_t)cnt[CNT_ABSORBED];
+    for (int f = 0; f < 6; ++f) st->exits[f] = (int64_t)cnt[CNT_EXIT0 + f];
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev[EV_ZERO0], h->ev[EV_K0])); st->zero_ms = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[EV_K0], h->ev[EV_K1])); st->kernel_ms = ms;
+    if (h->timed_reduce) { CU(cudaEventElapsedTime(&ms, h->ev[EV_K1], h->ev[EV_AR1])); st->allreduce_ms = ms; }
+    if (h->timed_h2d) { CU(cudaEventElapsedTime(&ms, h->ev[EV_H0], h->ev[EV_H1])); st->h2d_ms = ms; }
+    if (h->timed_d2h) { CU(cudaEventElapsedTime(&ms, h->ev[EV_D0], h->ev[EV_D1])); st->d2h_ms = ms; }
+    st->gpu_launches = h->last_launches;
+    if (cnt[CNT_ERRORS])
+        return fail(TAMC_EINVAL, "transport: " + std::to_string(cnt[CNT_ERRORS]) + " packet(s) exceeded the voxel-step cap");
+    return TAMC_OK;
+}
+
+extern "C" int tamc_seek(tamc_handle h, int64_t next_packet_id)
+{
+    if (!h || next_packet_id < 0) return fail(TAMC_EINVAL, "tamc_seek: bad argument");
+    h->cursor = next_packet_id;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
+{
+    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_run: jmean_global is null");
+    if (int rc = tamc_run_async(h, nphotons, seed, -1)) return rc;
+    if (int rc = tamc_get_jmean(h, jmean_global)) return rc;
+    if (stats) return tamc_get_stats(h, stats);
+    tamc_stats tmp;
+    return tamc_get_stats(h, &tmp);   // surfaces transport errors even when the caller wants no stats
+}
+
+// ------------------------------------------------------------------------------------------------
+// validation paths
+// ------------------------------------------------------------------------------------------------
+extern "C" int tamc_run_replay(tamc_handle h, int64_t npackets, const int64_t *draw_offsets, const double *draws,
+                               tamc_packet_record *records, double *jmean)
+{
+    if (int rc = check(h)) return rc;
+    if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run_replay: tamc_set_optics has not been called");
+    if (npackets < 0 || (npackets > 0 && (!draw_offsets || !draws))) return fail(TAMC_EINVAL, "tamc_run_replay: bad arguments");
+    const DevGrid g = make_grid(h);
+    CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev[EV_ZERO0], h->stream));
+    CU(cudaEventRecord(h->ev[EV_K0], h->stream));
+
+    // chunks bounded in packets and in draws so the staging buffers stay modest
+    const int64_t max_pk = 1 << 22, max_dr = (int64_t)1 << 27;
+    long long *d_off = nullptr;
+    double *d_draws = nullptr;
+    tamc_packet_record *d_rec = nullptr;
+    int64_t cap_dr = 0, cap_pk = 0;
+    std::vector<long long> rebased;
+    int rc = TAMC_OK;
+    int launches = 0;
+    for (int64_t p0 = 0; p0 < npackets && rc == TAMC_OK;) {
+        int64_t p1 = p0;
+        while (p1 < npackets && p1 - p0 < max_pk && (p1 == p0 || draw_offsets[p1 + 1] - draw_offsets[p0] <= max_dr)) ++p1;
+        const int64_t npk = p1 - p0, ndr = draw_offsets[p1] - draw_offsets[p0];
+        if (ndr < 0) { rc = fail(TAMC_EINVAL, "tamc_run_replay: draw_offsets must be non-decreasing"); break; }
+        auto cu = [&](cudaError_t e, const char *what) {
+            if (e != cudaSuccess && rc == TAMC_OK) rc = fail(TAMC_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        };
+        if (npk > cap_pk) {
+            cudaFree(d_off); cudaFree(d_rec);
+            cap_pk = npk;
+            cu(cudaMalloc(&d_off, (size_t)(cap_pk + 1) * sizeof(long long)), "cudaMalloc offsets");
+            cu(cudaMalloc(&d_rec, (size_t)cap_pk * sizeof(tamc_packet_record)), "cudaMalloc records");
+        }
+        if (ndr > cap_dr) {
+            cudaFree(d_draws);
+            cap_dr = ndr;
+            cu(cudaMalloc(&d_draws, (size_t)(cap_dr > 0 ? cap_dr : 1) * sizeof(double)), "cudaMalloc draws");
+        }
+        if (rc != TAMC_OK) break;
+        rebased.resize((size_t)npk + 1);
+        for (int64_t i = 0; i <= npk; ++i) rebased[(size_t)i] = draw_offsets[p0 + i] - draw_offsets[p0];
+        cu(cudaMemcpyAsync(d_off, rebased.data(), (size_t)(npk + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream), "H2D offsets");
+        cu(cudaMemcpyAsync(d_draws, draws + draw_offsets[p0], (size_t)ndr * sizeof(double), cudaMemcpyHostToDevice, h->stream), "H2D draws");
+        cu(launch_replay(g, npk, d_off, d_draws, h->d_cnt, d_rec, h->stream), "replay launch");
+        ++launches;
+        if (records)
+            cu(cudaMemcpyAsync(records + p0, d_rec, (size_t)npk * sizeof(tamc_packet_record), cudaMemcpyDeviceToHost, h->stream), "D2H records");
+        cu(cudaStreamSynchronize(h->stream), "replay sync");
+        p0 = p1;
+    }
+    cudaFree(d_off); cudaFree(d_draws); cudaFree(d_rec);
+    if (rc != TAMC_OK) return rc;
+    CU(cudaEventRecord(h->ev[EV_K1], h->stream));
+    CU(cudaEventRecord(h->ev[EV_AR1], h->stream));
+    h->timed_reduce = false; h->timed_d2h = false; h->ran = true; h->last_launches = launches;
+    if (jmean) CU(cudaMemcpy(jmean, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost));
+    unsigned long long cnt[CNT_N];
+    CU(cudaMemcpy(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (cnt[CNT_OVERFLOW]) return fail(TAMC_EREPLAY, std::to_string(cnt[CNT_OVERFLOW]) + " packet(s) ran out of replay draws");
+    return TAMC_OK;
+}
+
+extern "C" int tamc_run_records(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id,
+                                tamc_packet_record *records, double *jmean)
+{
+    if (int rc = check(h)) return rc;
+    if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run_records: tamc_set_optics has not been called");
+    if (nphotons < 0 || first_packet_id < 0 || !records) return fail(TAMC_EINVAL, "tamc_run_records: bad arguments");
+    const DevGrid g = make_grid(h);
+    CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev[EV_ZERO0], h->stream));
+    CU(cudaEventRecord(h->ev[EV_K0], h->stream));
+    const int64_t chunk = 1 << 22;
+    tamc_packet_record *d_rec = nullptr;
+    CU(cudaMalloc(&d_rec, (size_t)(nphotons < chunk ? (nphotons > 0 ? nphotons : 1) : chunk) * sizeof(tamc_packet_record)));
+    int launches = 0;
+    int rc = TAMC_OK;
+    for (int64_t p0 = 0; p0 < nphotons && rc == TAMC_OK; p0 += chunk) {
+        const int64_t npk = nphotons - p0 < chunk ? nphotons - p0 : chunk;
+        cudaError_t e = launch_transport(g, h->cfg, npk, (uint64_t)seed, (uint64_t)(first_packet_id + p0), h->d_cnt, d_rec, h->stream, &launches);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(records + p0, d_rec, (size_t)npk * sizeof(tamc_packet_record), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(TAMC_ECUDA, std::string("tamc_run_records: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_rec);
+    if (rc != TAMC_OK) return rc;
+    CU(cudaEventRecord(h->ev[EV_K1], h->stream));
+    CU(cudaEventRecord(h->ev[EV_AR1], h->stream));
+    h->timed_reduce = false; h->timed_d2h = false; h->ran = true; h->last_launches = launches;
+    if (jmean) CU(cudaMemcpy(jmean, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost));
+    return TAMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// residency, tuning, measurement
+// ------------------------------------------------------------------------------------------------
+extern "C" void *tamc_stream(tamc_handle h) { return h ? (void *)h->stream : nullptr; }
+extern "C" double *tamc_jmean_device(tamc_handle h) { return h ? h->d_jmean : nullptr; }
+extern "C" double *tamc_rhokap_device(tamc_handle h) { return h ? h->d_rhokap : nullptr; }
+
+extern "C" int tamc_pin_host(void *ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return fail(TAMC_EINVAL, "tamc_pin_host: bad argument");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return TAMC_OK;
+}
+
+extern "C" int tamc_unpin_host(void *ptr)
+{
+    if (!ptr) return fail(TAMC_EINVAL, "tamc_unpin_host: null pointer");
+    CU(cudaHostUnregister(ptr));
+    return TAMC_OK;
+}
+
+static int *option_slot(tamc_handle h, const char *name)
+{
+    if (!h || !name) return nullptr;
+    if (!strcmp(name, "variant")) return &h->cfg.variant;
+    if (!strcmp(name, "block")) return &h->cfg.block;
+    if (!strcmp(name, "ctas_per_sm")) return &h->cfg.ctas_per_sm;
+    if (!strcmp(name, "refill_min")) return &h->cfg.refill_min;
+    if (!strcmp(name, "scatter_min")) return &h->cfg.scatter_min;
+    if (!strcmp(name, "merge")) return &h->cfg.merge;
+    if (!strcmp(name, "reduce")) return &h->reduce;
+    return nullptr;
+}
+
+extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
+{
+    int *slot = option_slot(h, name);
+    if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
+    if (slot == &h->cfg.block && (value < 32 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be a multiple of 32 in [32,256]");
+    if (slot == &h->cfg.variant && (value < 0 || value > 1)) return fail(TAMC_EINVAL, "variant must be 0 or 1");
+    if ((slot == &h->cfg.refill_min || slot == &h->cfg.scatter_min) && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "threshold must be in [1,32]");
+    if (slot == &h->cfg.ctas_per_sm && (value < 0 || value > 32)) return fail(TAMC_EINVAL, "ctas_per_sm must be in [0,32]");
+    *slot = (int)value;
+    return TAMC_OK;
+}
+
+extern "C" int64_t tamc_get_option(tamc_handle h, const char *name)
+{
+    int *slot = option_slot(h, name);
+    return slot ? *slot : -1;
+}
+
+extern "C" int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *ms, int64_t *steps)
+{
+    if (int rc = check(h)) return rc;
+    if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_roofline_probe: tamc_set_optics has not been called");
+    const DevGrid g = make_grid(h);
+    CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev[EV_K0], h->stream));
+    CU(launch_probe(g, h->cfg, nphotons, (uint64_t)seed, h->d_cnt, h->stream));
+    CU(cudaEventRecord(h->ev[EV_K1], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, h->ev[EV_K0], h->ev[EV_K1]));
+    unsigned long long cnt[CNT_N];
+    CU(cudaMemcpy(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (ms) *ms = t;
+    if (steps) *steps = (int64_t)cnt[CNT_STEPS];
+    h->ran = false;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_flush_l2(tamc_handle h, uint64_t bytes)
+{
+    if (int rc = check(h)) return rc;
+    const size_t n = (size_t)(bytes + 7) / 8;
+    if (n > h->flush_elems) {
+        cudaFree(h->d_flush);
+        h->d_flush = nullptr;
+        h->flush_elems = 0;
+        CU(cudaMalloc(&h->d_flush, n * sizeof(double)));
+        h->flush_elems = n;
+    }
+    CU(launch_fill(h->d_flush, n, 0., h->num_sms, h->stream));
+    return TAMC_OK;
+}

@@ -1,0 +1,34 @@
+// tamc_internal.h -- launcher prototypes shared by the C-ABI layer and the kernel translation units.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tamc_transport.cuh"
+
+namespace tamc {
+
+struct LaunchCfg {
+    int variant;        // 0 = thread-per-packet grid-stride, 1 = persistent warp-refill state machine
+    int block;          // threads per CTA
+    int ctas_per_sm;    // resident CTAs per SM the grid is sized for
+    int num_sms;
+    int refill_min;     // persistent: refill a warp once this many lanes are idle
+    int scatter_min;    // persistent: run the scattering phase once this many lanes wait for it
+    int merge;          // merge consecutive same-voxel deposits in registers (-1 = auto: on with TAMC_SCATTER)
+};
+
+// production transport (Philox).  d_rec may be null; when non-null variant 0 is used.
+cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
+                             unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches);
+
+// trace replay (tamc_replay.cu, compiled with -fmad=false)
+cudaError_t launch_replay(const DevGrid &g, long long n, const long long *d_off, const double *d_draws,
+                          unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s);
+
+// access-pattern-only probe and utilities
+cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,
+                         cudaStream_t s);
+cudaError_t launch_fill(double *p, size_t n, double v, int num_sms, cudaStream_t s);
+
+}  // namespace tamc

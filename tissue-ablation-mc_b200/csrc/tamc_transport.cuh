@@ -1,0 +1,420 @@
+// tamc_transport.cuh -- device-side photon transport for sm_100a.
+//
+// One packet = one GPU thread.  The arithmetic is the reference's, statement for statement, in
+// fp64 (the reference is fp64 throughout: src/Makefile:3 -freal-4-real-8); what is new is the
+// execution model: counter-based Philox instead of the sequential ran2, face tables in shared
+// memory, position->voxel by multiply+fix-up instead of three bisections, fp64 RED atomics into
+// the per-GPU tally.  Included by two translation units: tamc_kernels.cu (production, FMA
+// contraction allowed) and tamc_replay.cu (trace replay, compiled -fmad=false).
+//
+// Reference lines restated here (all under /root/reference/src):
+//   sourceph.f90:28-47  launch()          inttau2.f90:75-121  wall distance in voxel_step()
+//   inttau2.f90:36-63   voxel_step()      inttau2.f90:124-187 position update in voxel_step()
+//   inttau2.f90:208-239 find_cell()       stokes.f90:6-153    stokes()
+//   mcpolar.f90:151-170 transport_packet() / the persistent kernel in tamc_kernels.cu
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/tamc.h"
+
+namespace tamc {
+
+// constants.f90:13 -- 7-digit truncations held in doubles; replay parity needs exactly these.
+constexpr double kPI = 3.141592;
+constexpr double kTWOPI = 6.283185;
+
+// A packet that takes more voxel-steps than this is killed and counted as an error: guards the GPU
+// against a caller-supplied delta below the ulp of a face coordinate (the reference would spin).
+constexpr int kMaxStepsPerPacket = 1 << 26;
+
+enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_N = 16 };
+
+struct DevGrid {
+    int nxg, nyg, nzg;
+    int sx;               // rhokap stride in j: nxg+2
+    long long sxy;        // rhokap stride in k: (nxg+2)*(nyg+2)
+    double xmax, ymax, zmax, delta;
+    double spot_r2;       // (spotSize/2.)**2, sourceph.f90:28
+    double zp0;           // zmax-(1.e-8*(2.*zmax/nzg)), sourceph.f90:32
+    double inv_dx, inv_dy, inv_dz;  // nxg/(2 xmax) ...: first guess of the voxel index only
+    double albedo, hgg, g2;
+    int flags;
+    const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
+    double *jmean;        // (nxg,nyg,nzg) column-major
+    const double *faces;  // xface(1:nxg+1) | yface(1:nyg+1) | zface(1:nzg+1)
+};
+
+// ---------------------------------------------------------------------------------------------
+// RNG: Philox4x32-10, key = run seed, counter = (packet id lo, hi, draw block, 0).
+// One block = 4 uniforms = exactly what one event consumes (launch: r, theta, phi, tau;
+// interaction: albedo test, HG cosine, azimuth, tau).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// (x + 0.5) * 2^-32: exact in fp64, strictly inside (0,1) like ran2's output (ran2.f:31).
+__device__ __forceinline__ double u32_to_unit(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+struct PhiloxRng {
+    uint2 key;
+    uint32_t id_lo, id_hi, blk;
+    __device__ __forceinline__ void seed(uint64_t s, uint64_t packet)
+    {
+        key = make_uint2((uint32_t)s, (uint32_t)(s >> 32));
+        id_lo = (uint32_t)packet;
+        id_hi = (uint32_t)(packet >> 32);
+        blk = 0;
+    }
+    __device__ __forceinline__ void block(double u[4])
+    {
+        const uint4 r = philox4x32_10(key, make_uint4(id_lo, id_hi, blk++, 0u));
+        u[0] = u32_to_unit(r.x); u[1] = u32_to_unit(r.y); u[2] = u32_to_unit(r.z); u[3] = u32_to_unit(r.w);
+    }
+};
+
+// Replay: the packet's slice of the reference ran2 sequence, consumed in the reference's order.
+struct ReplayRng {
+    const double *p;
+    long long pos, end;
+    __device__ __forceinline__ void block(double u[4])
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = (pos + i < end) ? p[pos + i] : 0.5;
+        pos += 4;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Tally policies.  fp64 atomicAdd with the result unused compiles to RED.E.ADD.F64 (fire and
+// forget, resolved in L2).  A zero deposit (ablated voxel, rhokap == 0) is skipped: jmean += 0.
+// ---------------------------------------------------------------------------------------------
+struct DirectTally {
+    double *jm;
+    double packet_sum;
+    __device__ __forceinline__ void begin() { packet_sum = 0.; }
+    __device__ __forceinline__ void add(long long idx, double v)
+    {
+        packet_sum += v;
+        if (v != 0.) atomicAdd(jm + idx, v);
+    }
+    __device__ __forceinline__ void flush() {}
+};
+
+// Consecutive deposits into the same voxel (the partial step that ends at a scattering site and the
+// first step after it) are merged in registers and written once.
+struct MergeTally {
+    double *jm;
+    double packet_sum;
+    long long pidx;
+    double pval;
+    __device__ __forceinline__ void begin() { packet_sum = 0.; pidx = -1; pval = 0.; }
+    __device__ __forceinline__ void add(long long idx, double v)
+    {
+        packet_sum += v;
+        if (idx == pidx) { pval += v; return; }
+        if (pval != 0.) atomicAdd(jm + pidx, pval);
+        pidx = idx;
+        pval = v;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (pval != 0.) atomicAdd(jm + pidx, pval);
+        pidx = -1;
+        pval = 0.;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Packet state: photon_vars.f90:11 (xp.. are kept in the shifted frame of inttau2.f90:24-26).
+// ---------------------------------------------------------------------------------------------
+struct Photon {
+    double xcur, ycur, zcur;
+    double nxp, nyp, nzp;
+    double cost, sint, phi;
+    double tau, taurun;
+    int celli, cellj, cellk;
+};
+
+enum { STEP_WALL = 0, STEP_INTERACT = 1, STEP_EXIT = 2 };
+
+// inttau2.f90:208-239 `find`: same result as the bisection over a(1:n) -- 1 when val == a(1), n-1
+// when val == a(n), -1 outside, otherwise the largest lo with a(lo) <= val -- reached from an
+// arithmetic first guess plus a fix-up against the very same face values.  `a` is 0-based here.
+__device__ __forceinline__ int find_cell(double val, const double *a, int n, double inv_w)
+{
+    if (val < a[0] || val > a[n - 1]) return -1;
+    if (val == a[n - 1]) return n - 1;
+    int lo = (int)(val * inv_w);
+    lo = max(0, min(lo, n - 2));
+    while (a[lo] > val) --lo;
+    while (a[lo + 1] <= val) ++lo;
+    return lo + 1;
+}
+
+// sourceph.f90:28-47.  u[0..2] = the three ran2 draws in call order, u[3] = tauint1's draw
+// (inttau2.f90:36).  sint = 0, so nxp = sint*cosp and nyp = sint*sinp are (signed) zeros and
+// cos(phi)/sin(phi) are not needed; phi itself is kept for the first scattering.
+__device__ __forceinline__ void launch(const DevGrid &g, Photon &p, const double u[4])
+{
+    const double r = u[0] * g.spot_r2;
+    const double theta = u[1] * kTWOPI;
+    double s, c;
+    sincos(theta, &s, &c);
+    const double sr = sqrt(r);
+    const double xp = sr * c;
+    const double yp = sr * s;
+    const double zp = g.zp0;
+    p.phi = kTWOPI * u[2];
+    p.sint = 0.;
+    p.cost = -1.;
+    p.nxp = 0.;
+    p.nyp = 0.;
+    p.nzp = -1.;
+    p.celli = (int)((double)g.nxg * (xp + g.xmax) / (2. * g.xmax)) + 1;
+    p.cellj = (int)((double)g.nyg * (yp + g.ymax) / (2. * g.ymax)) + 1;
+    p.cellk = (int)((double)g.nzg * (zp + g.zmax) / (2. * g.zmax)) + 1;
+    // inttau2.f90:24-26,36
+    p.xcur = xp + g.xmax;
+    p.ycur = yp + g.ymax;
+    p.zcur = zp + g.zmax;
+    p.taurun = 0.;
+    p.tau = -log(u[3]);
+}
+
+// tauint1 returns the centred position and the next call shifts it again (inttau2.f90:65-67 then
+// :24-26): (cur - max) + max is not always cur in fp64, so the round trip is replayed.
+__device__ __forceinline__ void recentre(const DevGrid &g, Photon &p)
+{
+    p.xcur = (p.xcur - g.xmax) + g.xmax;
+    p.ycur = (p.ycur - g.ymax) + g.ymax;
+    p.zcur = (p.zcur - g.zmax) + g.zmax;
+}
+
+// One pass of the loop body inttau2.f90:37-63 = one voxel-step.
+template <class Tally>
+__device__ __forceinline__ int voxel_step(const DevGrid &g, const double *xf, const double *yf, const double *zf,
+                                          Photon &p, Tally &tally)
+{
+    // wall_dist, inttau2.f90:75-121 (face(c+1) is xf[c], face(c) is xf[c-1])
+    double dx, dy, dz;
+    if (p.nxp > 0.) dx = (xf[p.celli] - p.xcur) / p.nxp;
+    else if (p.nxp < 0.) dx = (xf[p.celli - 1] - p.xcur) / p.nxp;
+    else dx = 100000.;
+    if (p.nyp > 0.) dy = (yf[p.cellj] - p.ycur) / p.nyp;
+    else if (p.nyp < 0.) dy = (yf[p.cellj - 1] - p.ycur) / p.nyp;
+    else dy = 100000.;
+    if (p.nzp > 0.) dz = (zf[p.cellk] - p.zcur) / p.nzp;
+    else if (p.nzp < 0.) dz = (zf[p.cellk - 1] - p.zcur) / p.nzp;
+    else dz = 100000.;
+    double dcell = fmin(fmin(dx, dy), dz);
+    const int dir = (dcell == dz) ? 2 : ((dcell == dy) ? 1 : 0);   // later axis wins ties, :116-118
+
+    const double rk = __ldg(g.rhokap + ((long long)p.celli + (long long)g.sx * p.cellj + g.sxy * p.cellk));
+    const double taucell = dcell * rk;
+    const long long jidx = (long long)(p.celli - 1) + (long long)g.nxg * ((long long)(p.cellj - 1) + (long long)g.nyg * (p.cellk - 1));
+
+    if (p.taurun + taucell < p.tau) {
+        p.taurun = p.taurun + taucell;
+        tally.add(jidx, taucell);                                  // dcell*rhokap, inttau2.f90:46
+        // update_pos(wall_flag=.TRUE.), inttau2.f90:140-170
+        if (dir == 0) {
+            p.xcur = (p.nxp > 0.) ? xf[p.celli] + g.delta : xf[p.celli - 1] - g.delta;
+            p.ycur = p.ycur + p.nyp * dcell;
+            p.zcur = p.zcur + p.nzp * dcell;
+        } else if (dir == 1) {
+            p.xcur = p.xcur + p.nxp * dcell;
+            p.ycur = (p.nyp > 0.) ? yf[p.cellj] + g.delta : yf[p.cellj - 1] - g.delta;
+            p.zcur = p.zcur + p.nzp * dcell;
+        } else {
+            p.xcur = p.xcur + p.nxp * dcell;
+            p.ycur = p.ycur + p.nyp * dcell;
+            p.zcur = (p.nzp > 0.) ? zf[p.cellk] + g.delta : zf[p.cellk - 1] - g.delta;
+        }
+        // update_voxels, inttau2.f90:201-203
+        p.celli = find_cell(p.xcur, xf, g.nxg + 1, g.inv_dx);
+        p.cellj = find_cell(p.ycur, yf, g.nyg + 1, g.inv_dy);
+        p.cellk = find_cell(p.zcur, zf, g.nzg + 1, g.inv_dz);
+        return (p.celli == -1 || p.cellj == -1 || p.cellk == -1) ? STEP_EXIT : STEP_WALL;   // :58-61
+    }
+    // inttau2.f90:51-55
+    dcell = (p.tau - p.taurun) / rk;
+    tally.add(jidx, dcell * rk);
+    p.xcur = p.xcur + p.nxp * dcell;
+    p.ycur = p.ycur + p.nyp * dcell;
+    p.zcur = p.zcur + p.nzp * dcell;
+    return STEP_INTERACT;
+}
+
+// stokes.f90:6-153: new direction after a scattering event (no polarisation state exists).
+// u1 feeds stokes.f90:24 / :48, u2 feeds :32 / :64.
+__device__ __forceinline__ void stokes(const DevGrid &g, Photon &p, double u1, double u2)
+{
+    double sinp, cosp;
+    if (g.hgg == 0.0) {
+        p.cost = 2. * u1 - 1.;
+        double s2 = 1. - p.cost * p.cost;
+        p.sint = (s2 <= 0.) ? 0. : sqrt(s2);
+        p.phi = kTWOPI * u2;
+        sincos(p.phi, &sinp, &cosp);
+        p.nxp = p.sint * cosp;
+        p.nyp = p.sint * sinp;
+        p.nzp = p.cost;
+        return;
+    }
+    const double costp = p.cost, sintp = p.sint, phip = p.phi;
+    const double q = (1. - g.g2) / (1. - g.hgg + 2. * g.hgg * u1);
+    double bmu = ((1. + g.g2) - q * q) / (2. * g.hgg);
+    double cosb2 = bmu * bmu;
+    if (fabs(bmu) > 1.) {
+        bmu = (bmu > 1.) ? 1. : -1.;
+        cosb2 = 1.;
+    }
+    const double sinbt = sqrt(1. - cosb2);
+    const double ri1 = kTWOPI * u2;
+    const bool upper = ri1 > kPI;
+    const double ri = upper ? kTWOPI - ri1 : ri1;     // ri3 (:67) or ri1 (:107)
+    double sini, cosi;
+    sincos(ri, &sini, &cosi);
+    if (bmu == 1. || bmu == -1.) return;              // goto 100: direction left untouched (:71-77)
+
+    p.cost = costp * bmu + sintp * sinbt * cosi;
+    double sini2, cosi2 = 0.;
+    if (fabs(p.cost) < 1.) {
+        p.sint = fabs(sqrt(1. - p.cost * p.cost));
+        sini2 = sini * sintp / p.sint;
+        const double bott = p.sint * sinbt;
+        cosi2 = costp / bott - p.cost * bmu / bott;
+    } else {
+        p.sint = 0.;
+        sini2 = 0.;
+        if (p.cost >= 1.) cosi2 = -1.;
+        if (p.cost <= -1.) cosi2 = 1.;
+    }
+    double cosdph = -(cosi2 * cosi) + sini2 * sini * bmu;
+    if (fabs(cosdph) > 1.) cosdph = (cosdph > 1.) ? 1. : -1.;
+    p.phi = upper ? phip + acos(cosdph) : phip - acos(cosdph);
+    if (p.phi > kTWOPI) p.phi = p.phi - kTWOPI;
+    if (p.phi < 0.) p.phi = p.phi + kTWOPI;
+    sincos(p.phi, &sinp, &cosp);
+    p.nxp = p.sint * cosp;
+    p.nyp = p.sint * sinp;
+    p.nzp = p.cost;
+}
+
+__device__ __forceinline__ int exit_face(const Photon &p)
+{
+    if (p.celli == -1) return p.nxp > 0. ? 2 : 1;
+    if (p.cellj == -1) return p.nyp > 0. ? 4 : 3;
+    if (p.cellk == -1) return p.nzp > 0. ? 6 : 5;
+    return 0;
+}
+
+// Per-thread counters, folded into the global counters once per warp at kernel end.
+struct Counters {
+    unsigned long long steps, scatters;
+    unsigned int packets, absorbed, errors, overflow;
+    unsigned int exits[6];
+    __device__ __forceinline__ void clear()
+    {
+        steps = scatters = 0ull;
+        packets = absorbed = errors = overflow = 0u;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) exits[f] = 0u;
+    }
+    __device__ __forceinline__ void fate(int f)
+    {
+        packets++;
+        absorbed += (f == 0);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) exits[i] += (f == i + 1);
+    }
+    __device__ __forceinline__ void commit(unsigned long long *g) const
+    {
+        unsigned long long v[12] = {packets, steps, scatters, absorbed, exits[0], exits[1], exits[2],
+                                    exits[3], exits[4], exits[5], errors, overflow};
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            unsigned long long x = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0 && x) atomicAdd(g + i, x);
+        }
+    }
+};
+
+// mcpolar.f90:153-169 for one packet: launch, tauint1, then either the shipped stub (:166-169:
+// the packet ends at its first interaction) or, with TAMC_SCATTER, the albedo test + stokes loop.
+template <class Rng, class Tally, bool kRecord>
+__device__ __forceinline__ void transport_packet(const DevGrid &g, const double *xf, const double *yf, const double *zf,
+                                                 Rng &rng, Tally &tally, Counters &cnt, tamc_packet_record *rec,
+                                                 long long draws_available)
+{
+    double u[4];
+    Photon p;
+    rng.block(u);
+    launch(g, p, u);
+    tally.begin();
+    int ndraws = 4, steps = 0, nscatt = 0, fate = 0;
+    for (;;) {
+        const int r = voxel_step(g, xf, yf, zf, p, tally);
+        ++steps;
+        if (r == STEP_WALL) {
+            if (steps >= kMaxStepsPerPacket) { cnt.errors++; break; }
+            continue;
+        }
+        if (r == STEP_EXIT) { fate = exit_face(p); break; }
+        if (!(g.flags & TAMC_SCATTER)) break;                      // stub: tflag = .true.; exit
+        rng.block(u);
+        if (u[0] < g.albedo) {
+            stokes(g, p, u[1], u[2]);
+            ++nscatt;
+            ndraws += 4;
+            recentre(g, p);
+            p.taurun = 0.;
+            p.tau = -log(u[3]);
+        } else {
+            ndraws += 1;
+            break;                                                 // absorbed
+        }
+    }
+    tally.flush();
+    cnt.steps += (unsigned long long)steps;
+    cnt.scatters += (unsigned long long)nscatt;
+    cnt.fate(fate);
+    if (kRecord) {
+        const bool over = ndraws > draws_available;
+        cnt.overflow += over;
+        rec->xp = p.xcur - g.xmax; rec->yp = p.ycur - g.ymax; rec->zp = p.zcur - g.zmax;
+        rec->nxp = p.nxp; rec->nyp = p.nyp; rec->nzp = p.nzp;
+        rec->deposit = tally.packet_sum;
+        rec->xcell = p.celli; rec->ycell = p.cellj; rec->zcell = p.cellk;
+        rec->steps = steps; rec->nscatt = nscatt; rec->ndraws = ndraws;
+        rec->fate = fate; rec->flags = over ? 1 : 0;
+    }
+}
+
+// Copies the three face tables into shared memory; returns pointers to each.
+__device__ __forceinline__ void stage_faces(const DevGrid &g, double *smem, const double *&xf, const double *&yf,
+                                            const double *&zf)
+{
+    const int n = g.nxg + g.nyg + g.nzg + 3;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = g.faces[i];
+    __syncthreads();
+    xf = smem;
+    yf = smem + (g.nxg + 1);
+    zf = yf + (g.nyg + 1);
+}
+
+}  // namespace tamc
