@@ -8,7 +8,7 @@
 import numpy as np
 import pytest
 
-from tests.util import compare_grids, compare_records, make_oracle, make_transport
+from tests.util import compare_grids, compare_records, make_oracle, make_transport, voxel_tau
 
 pytestmark = pytest.mark.gpu
 
@@ -23,8 +23,9 @@ def _philox_exact(cfg, n, first=0, rhokap=None):
     t = make_transport(cfg, rk)
     rec, jm = t.run_records(n, SEED, first)
     scale = {"xp": cfg["xmax"], "yp": cfg["ymax"], "zp": cfg["zmax"], "nxp": 1.0, "nyp": 1.0, "nzp": 1.0}
-    compare_records(rec, want["records"], rtol=1e-9, scale=scale)
-    compare_grids(jm, o.jmean, rtol=1e-10)
+    compare_records(rec, want["records"], rtol=1e-6, scale=scale)
+    gk = dict(rtol=1e-6, dep_scale=voxel_tau(cfg, rk)) if cfg["flags"] & 1 else dict(rtol=1e-10)
+    compare_grids(jm, o.jmean, **gk)
     # both kernel shapes and both tally policies give the same grid and counters
     for variant in (0, 1):
         for merge in (0, 1):
@@ -38,7 +39,8 @@ def _philox_exact(cfg, n, first=0, rhokap=None):
                 t.run_async(n, SEED, first)
                 jm2 = t.get_jmean()
                 st = t.get_stats()
-                compare_grids(jm2, o.jmean, rtol=1e-10)
+                compare_grids(jm2, o.jmean, **gk)
+                compare_grids(jm2, jm, **gk)                # device vs device: summation order, FMA placement
                 assert st["packets"] == n
                 assert st["voxel_steps"] == want["stats"]["voxel_steps"]
                 assert st["scatters"] == want["stats"]["scatters"]
