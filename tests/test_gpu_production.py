@@ -21,28 +21,44 @@ def _philox_exact(cfg, n, first=0, rhokap=None):
     o.seed_philox(SEED, first)
     want = o.run(n, records=True)
     t = make_transport(cfg, rk)
-    rec, jm = t.run_records(n, SEED, first)
     scale = {"xp": cfg["xmax"], "yp": cfg["ymax"], "zp": cfg["zmax"], "nxp": 1.0, "nyp": 1.0, "nzp": 1.0}
-    compare_records(rec, want["records"], rtol=1e-6, scale=scale)
-    gk = dict(rtol=1e-6, dep_scale=voxel_tau(cfg, rk)) if cfg["flags"] & 1 else dict(rtol=1e-10)
-    compare_grids(jm, o.jmean, **gk)
+    scat = bool(cfg["flags"] & 1)
+    # Tolerances.  Exact arithmetic (variant 2): the north_star's 1e-6.  Production arithmetic
+    # (tamc_fast.cuh) rotates the direction vector instead of tracking phi, so it does not reproduce one
+    # artefact of the reference: `phi -+ TWOPI` with the truncated TWOPI = 6.283185 turns the azimuth by
+    # 3.07e-7 rad at every wrap (stokes.f90:102-103).  After tens of scatterings that is ~1e-7..1e-5 of
+    # the box size per packet: bounded here at 1e-4 (max) and 5e-6 (99th percentile), with rare edge flips.
+    gk_exact = dict(rtol=1e-6, dep_scale=voxel_tau(cfg, rk)) if scat else dict(rtol=1e-10)
+    # (a packet displaced by 1e-5 of the box changes its chord in a voxel by ~1e-3 of that voxel's optical depth)
+    gk_fast = dict(rtol=2e-2, dep_scale=voxel_tau(cfg, rk), sum_rtol=1e-5) if scat else dict(rtol=1e-10)
+    for variant in (2, 1):
+        t.set_option("variant", variant)
+        rec, jm = t.run_records(n, SEED, first)
+        if variant == 2 or not scat:
+            compare_records(rec, want["records"], rtol=1e-6, scale=scale)
+            compare_grids(jm, o.jmean, **gk_exact)
+        else:
+            compare_records(rec, want["records"], rtol=1e-4, scale=scale, flip_fraction=1e-3, p99_rtol=5e-6)
+            compare_grids(jm, o.jmean, **gk_fast)
     # both kernel shapes and both tally policies give the same grid and counters
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         for merge in (0, 1):
-            for thr in ((1, 1), (8, 8), (32, 32)):
-                if variant == 0 and thr != (1, 1):
+            for thr in ((32, 1), (0, 16), (64, 32)):
+                if variant != 1 and thr != (32, 1):
                     continue
                 t.set_option("variant", variant)
                 t.set_option("merge", merge)
-                t.set_option("refill_min", thr[0])
+                t.set_option("chunk", thr[0])
                 t.set_option("scatter_min", thr[1])
                 t.run_async(n, SEED, first)
                 jm2 = t.get_jmean()
                 st = t.get_stats()
-                compare_grids(jm2, o.jmean, **gk)
-                compare_grids(jm2, jm, **gk)                # device vs device: summation order, FMA placement
+                compare_grids(jm2, o.jmean, **(gk_exact if variant == 2 else gk_fast))
+                if variant != 2:
+                    compare_grids(jm2, jm, **gk_exact)      # device vs device, same arithmetic: summation order only
                 assert st["packets"] == n
-                assert st["voxel_steps"] == want["stats"]["voxel_steps"]
+                slack = 0 if (variant == 2 or not scat) else 2 * max(2, int(1e-3 * n))   # edge flips, see compare_records
+                assert abs(st["voxel_steps"] - want["stats"]["voxel_steps"]) <= slack
                 assert st["scatters"] == want["stats"]["scatters"]
                 assert st["absorbed"] == want["stats"]["absorbed"]
                 assert st["exits"] == want["stats"]["exits"]

@@ -32,13 +32,28 @@ def make_transport(cfg, rhokap=None, device=0):
     return t
 
 
-def compare_records(got, want, rtol=REPLAY_RTOL, scale=None):
+def compare_records(got, want, rtol=REPLAY_RTOL, scale=None, flip_fraction=0.0, p99_rtol=None):
     """Integer fields bit-exact; floating fields within rtol of the oracle (relative to the field's
-    natural scale for coordinates that may sit near zero)."""
+    natural scale for coordinates that may sit near zero).
+
+    flip_fraction > 0 (production arithmetic only): a path that differs from the oracle's in the 9th
+    digit can pass on the other side of a voxel edge, which changes the visited-voxel sequence (steps,
+    final cell by one) without moving the packet by more than rtol.  At most that fraction of packets
+    (and never fewer than 2 allowed) may show such a flip -- by at most one voxel / two steps, with the
+    same fate, draws and scatter count -- and they still have to meet the floating-point tolerance."""
     assert got.shape == want.shape
+    flipped = np.zeros(got.shape, dtype=bool)
     for f in INT_FIELDS:
-        bad = np.nonzero(got[f] != want[f])[0]
-        assert bad.size == 0, f"{f}: {bad.size} packets differ, first {bad[:5]}: {got[f][bad[:5]]} vs {want[f][bad[:5]]}"
+        bad = got[f] != want[f]
+        if flip_fraction == 0.0 or f in ("nscatt", "ndraws", "fate"):
+            idx = np.nonzero(bad)[0]
+            assert idx.size == 0, f"{f}: {idx.size} packets differ, first {idx[:5]}: {got[f][idx[:5]]} vs {want[f][idx[:5]]}"
+        else:
+            lim = 2 if f == "steps" else 1
+            assert np.all(np.abs(got[f][bad].astype(np.int64) - want[f][bad]) <= lim), f"{f}: flip larger than {lim}"
+            flipped |= bad
+    allowed = max(2, int(flip_fraction * got.size))
+    assert flipped.sum() <= allowed, f"{flipped.sum()} packets changed their voxel sequence (allowed {allowed})"
     worst = 0.0
     for f in FP_FIELDS:
         s = np.abs(want[f])
@@ -48,6 +63,8 @@ def compare_records(got, want, rtol=REPLAY_RTOL, scale=None):
         err[(got[f] == want[f])] = 0.0
         worst = max(worst, float(err.max(initial=0.0)))
         assert err.max(initial=0.0) <= rtol, f"{f}: max rel err {err.max():.3e} at packet {err.argmax()}"
+        if p99_rtol is not None and err.size:
+            assert np.quantile(err, 0.99) <= p99_rtol, f"{f}: p99 rel err {np.quantile(err, 0.99):.3e}"
     return worst
 
 
@@ -57,7 +74,7 @@ def voxel_tau(cfg, rhokap):
     return float(np.max(rhokap)) * 2.0 * min(cfg["xmax"], cfg["ymax"], cfg["zmax"]) / n
 
 
-def compare_grids(got, want, rtol=1e-11, dep_scale=None):
+def compare_grids(got, want, rtol=1e-11, dep_scale=None, sum_rtol=1e-8):
     """Tally grids against the oracle.
 
     Without scattering every chord is a full voxel edge or the final partial step, the two sides sum the
@@ -77,5 +94,5 @@ def compare_grids(got, want, rtol=1e-11, dep_scale=None):
         err = np.abs(got - want) / np.maximum(np.abs(want), dep_scale)
     assert err.max() <= rtol, f"tally max rel err {err.max():.3e}"
     # the grid totals agree much more tightly than any single voxel
-    assert abs(got.sum() - want.sum()) <= 1e-8 * abs(want.sum()) + 1e-300
+    assert abs(got.sum() - want.sum()) <= sum_rtol * abs(want.sum()) + 1e-300
     return float(err.max())

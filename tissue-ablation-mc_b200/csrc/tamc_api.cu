@@ -106,7 +106,7 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    LaunchCfg cfg{1, 256, 0, 148, 1, 1, -1};
+    LaunchCfg cfg{1, 256, 0, 148, 0, 16, -1};
     int reduce = 1;
 
     // bookkeeping of the last call
@@ -135,6 +135,8 @@ static DevGrid make_grid(const tamc_context *c)
     g.inv_dy = (double)c->nyg / (2. * c->ymax);
     g.inv_dz = (double)c->nzg / (2. * c->zmax);
     g.albedo = c->albedo; g.hgg = c->hgg; g.g2 = c->hgg * c->hgg;      // ch_opt.f90:16
+    g.zcur0 = g.zp0 + c->zmax;
+    g.cellk0 = (int)((double)c->nzg * (g.zp0 + c->zmax) / (2. * c->zmax)) + 1;
     g.flags = c->flags;
     g.rhokap = c->d_rhokap; g.jmean = c->d_jmean; g.faces = c->d_faces;
     return g;
@@ -167,6 +169,8 @@ extern "C" int tamc_init(int device, int nxg, int nyg, int nzg, double xmax, dou
     *out = nullptr;
     if (nxg < 1 || nyg < 1 || nzg < 1 || nxg > 4096 || nyg > 4096 || nzg > 4096)
         return fail(TAMC_EINVAL, "tamc_init: grid dimensions must be in [1,4096]");
+    if ((double)(nxg + 2) * (nyg + 2) * (nzg + 2) >= 2147483648.)
+        return fail(TAMC_EINVAL, "tamc_init: grid too large, (nxg+2)(nyg+2)(nzg+2) must stay below 2^31 voxels");
     if (!(xmax > 0) || !(ymax > 0) || !(zmax > 0) || !(delta > 0))
         return fail(TAMC_EINVAL, "tamc_init: xmax, ymax, zmax and delta must be positive");
     int ndev = 0;
@@ -536,7 +540,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "variant")) return &h->cfg.variant;
     if (!strcmp(name, "block")) return &h->cfg.block;
     if (!strcmp(name, "ctas_per_sm")) return &h->cfg.ctas_per_sm;
-    if (!strcmp(name, "refill_min")) return &h->cfg.refill_min;
+    if (!strcmp(name, "chunk")) return &h->cfg.chunk;
     if (!strcmp(name, "scatter_min")) return &h->cfg.scatter_min;
     if (!strcmp(name, "merge")) return &h->cfg.merge;
     if (!strcmp(name, "reduce")) return &h->reduce;
@@ -548,8 +552,9 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     int *slot = option_slot(h, name);
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
     if (slot == &h->cfg.block && (value < 32 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be a multiple of 32 in [32,256]");
-    if (slot == &h->cfg.variant && (value < 0 || value > 1)) return fail(TAMC_EINVAL, "variant must be 0 or 1");
-    if ((slot == &h->cfg.refill_min || slot == &h->cfg.scatter_min) && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "threshold must be in [1,32]");
+    if (slot == &h->cfg.variant && (value < 0 || value > 2)) return fail(TAMC_EINVAL, "variant must be 0, 1 or 2");
+    if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
+    if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");
     if (slot == &h->cfg.ctas_per_sm && (value < 0 || value > 32)) return fail(TAMC_EINVAL, "ctas_per_sm must be in [0,32]");
     *slot = (int)value;
     return TAMC_OK;

@@ -1,0 +1,251 @@
+// tamc_fast.cuh -- production arithmetic of the transport (fp64), used by every Philox kernel.
+//
+// Same physics and the same mapping from draws to paths as tamc_transport.cuh (the statement-by-
+// statement restatement that the trace-replay kernel uses), reorganised so the per-voxel-step and
+// per-event instruction counts are small:
+//   * wall distances multiply by per-event reciprocals of the direction cosines instead of three
+//     fp64 divisions per step (inttau2.f90:75-121);
+//   * after a wall crossing only the crossed axis is re-indexed (cell +- 1, exit = index leaves
+//     1..n) instead of re-deriving all three indices from the position (inttau2.f90:190-239);
+//     the snapped coordinate `face +- delta` lies in that neighbour by construction;
+//   * the new direction after a scattering is the same rotation as stokes.f90:40-148 written on the
+//     direction vector: u' = cos(T) u - sin(T) (cos(i1) e_theta + sin(i1) e_phi), where T is the
+//     scattering angle and i1 = TWOPI*xi; this is what the spherical-triangle formulas evaluate
+//     (cost' = costp*bmu + sintp*sinbt*cos(i1); phi' = phip -+ acos(cosdph)), without the acos, the
+//     second sincos and four of the divisions.  The bmu == +-1 "goto 100" no-op is kept.
+// Results differ from the exact path by fp64 rounding only; tests/test_gpu_production.py checks the
+// kernels built on this header packet by packet (1e-6 relative) against the oracle run on the same
+// Philox stream, and statistically against the oracle on the reference's ran2 stream.
+#pragma once
+
+#include "tamc_transport.cuh"
+
+namespace tamc {
+
+struct FastPhoton {
+    double xcur, ycur, zcur;      // shifted frame, inttau2.f90:24-26
+    double nxp, nyp, nzp;         // direction cosines (nzp = cost)
+    double inx, iny, inz;         // reciprocals (0 where the cosine is 0)
+    double sint, cosp, sinp;      // photon_vars sint, cos(phi), sin(phi)
+    double tau, taurun;
+    int celli, cellj, cellk;      // 1-based voxel
+    int ridx, jidx;               // linear indices into rhokap (halo layout) and jmean
+    int dflags;                   // bit0-2: cosine < 0 (x,y,z); bit3-5: cosine == 0
+};
+
+__device__ __forceinline__ void set_direction(FastPhoton &p)
+{
+    int f = 0;
+    f |= (p.nxp < 0.) ? 1 : 0;
+    f |= (p.nyp < 0.) ? 2 : 0;
+    f |= (p.nzp < 0.) ? 4 : 0;
+    f |= (p.nxp == 0.) ? 8 : 0;
+    f |= (p.nyp == 0.) ? 16 : 0;
+    f |= (p.nzp == 0.) ? 32 : 0;
+    p.dflags = f;
+    p.inx = (f & 8) ? 0. : 1. / p.nxp;
+    p.iny = (f & 16) ? 0. : 1. / p.nyp;
+    p.inz = (f & 32) ? 0. : 1. / p.nzp;
+}
+
+struct LaunchConsts {
+    double zcur0;     // zp0 + zmax
+    int cellk0;       // int(nzg*(zp0+zmax)/(2.*zmax))+1, sourceph.f90:47
+};
+
+// What a launch produces; small enough to park in shared memory until a lane is free.
+struct Launched {
+    double xcur, ycur, tau, cosp, sinp;
+    int celli, cellj;
+};
+
+// sourceph.f90:28-47 + inttau2.f90:36.  u = (r, theta, phi, tau) draws in the reference's order.
+__device__ __forceinline__ Launched launch_fast(const DevGrid &g, const double u[4], bool need_azimuth)
+{
+    Launched L;
+    const double r = u[0] * g.spot_r2;
+    const double theta = u[1] * kTWOPI;
+    double s, c;
+    sincos(theta, &s, &c);
+    const double sr = sqrt(r);
+    L.xcur = sr * c + g.xmax;
+    L.ycur = sr * s + g.ymax;
+    L.celli = (int)(L.xcur * g.inv_dx) + 1;
+    L.cellj = (int)(L.ycur * g.inv_dy) + 1;
+    L.cosp = 1.;
+    L.sinp = 0.;
+    if (need_azimuth) sincos(kTWOPI * u[2], &L.sinp, &L.cosp);   // phi is first used by the first scattering
+    L.tau = -log(u[3]);
+    return L;
+}
+
+__device__ __forceinline__ void adopt(const DevGrid &g, const LaunchConsts &lc, FastPhoton &p, const Launched &L)
+{
+    p.xcur = L.xcur; p.ycur = L.ycur; p.zcur = lc.zcur0;
+    p.nxp = 0.; p.nyp = 0.; p.nzp = -1.;          // sint = 0, cost = -1 (sourceph.f90:37-42)
+    p.inx = 0.; p.iny = 0.; p.inz = -1.;
+    p.dflags = 4 | 8 | 16;
+    p.sint = 0.; p.cosp = L.cosp; p.sinp = L.sinp;
+    p.tau = L.tau; p.taurun = 0.;
+    p.celli = L.celli; p.cellj = L.cellj; p.cellk = lc.cellk0;
+    p.ridx = p.celli + g.sx * (p.cellj + (g.nyg + 2) * p.cellk);
+    p.jidx = (p.celli - 1) + g.nxg * ((p.cellj - 1) + g.nyg * (p.cellk - 1));
+}
+
+// One voxel-step, inttau2.f90:37-63.
+template <class Tally>
+__device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *xf, const double *yf, const double *zf,
+                                               FastPhoton &p, Tally &tally)
+{
+    const int f = p.dflags;
+    const int negx = f & 1, negy = (f >> 1) & 1, negz = (f >> 2) & 1;
+    const double fx = xf[p.celli - negx], fy = yf[p.cellj - negy], fz = zf[p.cellk - negz];
+    const double dx = (f & 8) ? 100000. : (fx - p.xcur) * p.inx;
+    const double dy = (f & 16) ? 100000. : (fy - p.ycur) * p.iny;
+    const double dz = (f & 32) ? 100000. : (fz - p.zcur) * p.inz;
+    double dcell = fmin(fmin(dx, dy), dz);
+    const double rk = __ldg(g.rhokap + p.ridx);
+    const double taucell = dcell * rk;
+
+    if (p.taurun + taucell < p.tau) {
+        p.taurun += taucell;
+        tally.add(p.jidx, taucell);
+        bool out;
+        if (dcell == dz) {                               // later axis wins ties, inttau2.f90:116-118
+            p.xcur += p.nxp * dcell;
+            p.ycur += p.nyp * dcell;
+            p.zcur = negz ? fz - g.delta : fz + g.delta;
+            const int s = negz ? -1 : 1;
+            p.cellk += s;
+            p.ridx += s * (int)g.sxy;
+            p.jidx += s * g.nxg * g.nyg;
+            out = (p.cellk < 1) | (p.cellk > g.nzg);
+        } else if (dcell == dy) {
+            p.xcur += p.nxp * dcell;
+            p.ycur = negy ? fy - g.delta : fy + g.delta;
+            p.zcur += p.nzp * dcell;
+            const int s = negy ? -1 : 1;
+            p.cellj += s;
+            p.ridx += s * g.sx;
+            p.jidx += s * g.nxg;
+            out = (p.cellj < 1) | (p.cellj > g.nyg);
+        } else {
+            p.xcur = negx ? fx - g.delta : fx + g.delta;
+            p.ycur += p.nyp * dcell;
+            p.zcur += p.nzp * dcell;
+            const int s = negx ? -1 : 1;
+            p.celli += s;
+            p.ridx += s;
+            p.jidx += s;
+            out = (p.celli < 1) | (p.celli > g.nxg);
+        }
+        return out ? STEP_EXIT : STEP_WALL;
+    }
+    dcell = (p.tau - p.taurun) / rk;                      // inttau2.f90:51-55
+    tally.add(p.jidx, dcell * rk);
+    p.xcur += p.nxp * dcell;
+    p.ycur += p.nyp * dcell;
+    p.zcur += p.nzp * dcell;
+    return STEP_INTERACT;
+}
+
+struct ScatterConsts {
+    double one_m_g2, one_p_g2, one_m_g, two_g, inv_two_g;
+};
+
+// stokes.f90:6-153 as a rotation of the direction vector (see the header comment).
+// u1 -> stokes.f90:24/:48, u2 -> :32/:64, u3 -> the next tauint1 draw (inttau2.f90:36).
+__device__ __forceinline__ void scatter_fast(const DevGrid &g, const ScatterConsts &sc, FastPhoton &p, double u1, double u2,
+                                             double u3)
+{
+    p.taurun = 0.;
+    p.tau = -log(u3);
+    // the centred position round trip of inttau2.f90:65-67 / :24-26
+    p.xcur = (p.xcur - g.xmax) + g.xmax;
+    p.ycur = (p.ycur - g.ymax) + g.ymax;
+    p.zcur = (p.zcur - g.zmax) + g.zmax;
+
+    if (g.hgg == 0.0) {                                   // isotropic, stokes.f90:23-38
+        const double cost = 2. * u1 - 1.;
+        const double s2 = 1. - cost * cost;
+        p.sint = (s2 <= 0.) ? 0. : sqrt(s2);
+        sincos(kTWOPI * u2, &p.sinp, &p.cosp);
+        p.nxp = p.sint * p.cosp;
+        p.nyp = p.sint * p.sinp;
+        p.nzp = cost;
+        set_direction(p);
+        return;
+    }
+    const double q = sc.one_m_g2 / (sc.one_m_g + sc.two_g * u1);      // stokes.f90:48
+    double bmu = (sc.one_p_g2 - q * q) * sc.inv_two_g;
+    bmu = fmin(1., fmax(-1., bmu));
+    if (bmu == 1. || bmu == -1.) return;                               // goto 100, stokes.f90:71-77
+    const double sinbt = sqrt(1. - bmu * bmu);
+    // i1 = TWOPI*xi; beyond PI the reference works with i3 = TWOPI - i1 and adds instead of subtracts
+    // (stokes.f90:66-68,101).  With the truncated constants i3 is not exactly -i1 (mod 2 pi), so the
+    // same i3 is formed here and only the sign of its sine is flipped.
+    const double ri1 = kTWOPI * u2;
+    const bool upper = ri1 > kPI;
+    double si, ci;
+    sincos(upper ? kTWOPI - ri1 : ri1, &si, &ci);
+    si = upper ? -si : si;
+
+    const double costp = p.nzp, sintp = p.sint;
+    const double a = sinbt * ci * costp, b = sinbt * si;
+    double uz = costp * bmu + sintp * sinbt * ci;                      // stokes.f90:79 / :117
+    const double ux = bmu * p.nxp - (a * p.cosp - b * p.sinp);
+    const double uy = bmu * p.nyp - (a * p.sinp + b * p.cosp);
+    uz = fmin(1., fmax(-1., uz));
+    const double h2 = ux * ux + uy * uy;
+    if (h2 > 0.) {
+        const double ih = 1. / sqrt(h2);
+        p.cosp = ux * ih;
+        p.sinp = uy * ih;
+    }
+    p.sint = sqrt(1. - uz * uz);                                        // stokes.f90:81 / :119
+    p.nxp = p.sint * p.cosp;                                            // stokes.f90:143-148
+    p.nyp = p.sint * p.sinp;
+    p.nzp = uz;
+    set_direction(p);
+}
+
+__device__ __forceinline__ int exit_face_fast(const FastPhoton &p, const DevGrid &g)
+{
+    if (p.celli < 1 || p.celli > g.nxg) return p.nxp > 0. ? 2 : 1;
+    if (p.cellj < 1 || p.cellj > g.nyg) return p.nyp > 0. ? 4 : 3;
+    if (p.cellk < 1 || p.cellk > g.nzg) return p.nzp > 0. ? 6 : 5;
+    return 0;
+}
+
+// Tally policies on 32-bit voxel indices (tamc_init bounds the grid so they fit).
+struct DirectTally32 {
+    double *jm;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void add(int idx, double v)
+    {
+        if (v != 0.) atomicAdd(jm + idx, v);              // RED.E.ADD.F64
+    }
+    __device__ __forceinline__ void flush() {}
+};
+
+struct MergeTally32 {
+    double *jm;
+    int pidx;
+    double pval;
+    __device__ __forceinline__ void begin() { pidx = -1; pval = 0.; }
+    __device__ __forceinline__ void add(int idx, double v)
+    {
+        if (idx == pidx) { pval += v; return; }
+        if (pval != 0.) atomicAdd(jm + pidx, pval);
+        pidx = idx;
+        pval = v;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (pval != 0.) atomicAdd(jm + pidx, pval);
+        pidx = -1;
+        pval = 0.;
+    }
+};
+
+}  // namespace tamc

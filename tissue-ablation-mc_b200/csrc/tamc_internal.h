@@ -9,11 +9,11 @@
 namespace tamc {
 
 struct LaunchCfg {
-    int variant;        // 0 = thread-per-packet grid-stride, 1 = persistent warp-refill state machine
+    int variant;        // 0 = thread-per-packet grid-stride, 1 = persistent warps (default), 2 = variant 0 on the exact arithmetic
     int block;          // threads per CTA
     int ctas_per_sm;    // resident CTAs per SM the grid is sized for
     int num_sms;
-    int refill_min;     // persistent: refill a warp once this many lanes are idle
+    int chunk;          // persistent: packet ids a warp claims per atomic (0 = auto)
     int scatter_min;    // persistent: run the scattering phase once this many lanes wait for it
     int merge;          // merge consecutive same-voxel deposits in registers (-1 = auto: on with TAMC_SCATTER)
 };

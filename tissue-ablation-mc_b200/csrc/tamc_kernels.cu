@@ -1,20 +1,44 @@
 // tamc_kernels.cu -- production transport kernels (Philox streams) for sm_100a.
 //
-// Replaces the per-rank `do j = 1, nphotons` of /root/reference/src/mcpolar.f90:151-170.  Two
-// execution shapes over the same transport code (tamc_transport.cuh):
-//   variant 0  one packet per thread, grid-stride over packet ids (also the records path);
-//   variant 1  persistent warps: each warp owns a contiguous id range and refills idle lanes in
-//              place, so lanes whose packet died early do not wait for the longest walk in the warp;
-//              walking and scattering are phased so the divergent scattering code runs for many
-//              lanes at once.
+// Replaces the per-rank `do j = 1, nphotons` of /root/reference/src/mcpolar.f90:151-170.
+//   variant 1 (default)  persistent warps.  A warp claims chunks of packet ids from one global
+//              counter, launches 32 packets at a time with all lanes active into a small shared-
+//              memory reservoir, and every lane whose packet has ended adopts the next one from
+//              the reservoir in place -- so neither the launch code nor the walk runs with a
+//              mostly-empty warp.  Walking and scattering are phased: lanes that reached an
+//              interaction site wait until `scatter_min` of them can run the scattering code
+//              together.
+//   variant 0  one packet per thread, grid-stride (also the per-packet records path).
+//   variant 2  variant 0 on the statement-by-statement arithmetic of tamc_transport.cuh
+//              (device-side cross-check of the production arithmetic in tamc_fast.cuh).
 // The path is a random walk over an fp64 grid with fp64 atomics: no dense contraction, no tensor
 // cores.
+#include "tamc_fast.cuh"
 #include "tamc_internal.h"
 
 namespace tamc {
 
+__device__ __forceinline__ ScatterConsts scatter_consts(const DevGrid &g)
+{
+    ScatterConsts sc;
+    sc.one_m_g2 = 1. - g.g2;
+    sc.one_p_g2 = 1. + g.g2;
+    sc.one_m_g = 1. - g.hgg;
+    sc.two_g = 2. * g.hgg;
+    sc.inv_two_g = (g.hgg != 0.) ? 1. / (2. * g.hgg) : 0.;
+    return sc;
+}
+
+// Adds the packet's deposit sum for the records path.
+template <class Base>
+struct SumTally : Base {
+    double packet_sum;
+    __device__ __forceinline__ void begin() { packet_sum = 0.; Base::begin(); }
+    __device__ __forceinline__ void add(int idx, double v) { packet_sum += v; Base::add(idx, v); }
+};
+
 // ---------------------------------------------------------------------------------------------
-// variant 0
+// variant 0: one packet per thread (production arithmetic), optional per-packet records
 // ---------------------------------------------------------------------------------------------
 template <class Tally, bool kRecord>
 __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
@@ -24,7 +48,72 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
     extern __shared__ double s_faces[];
     const double *xf, *yf, *zf;
     stage_faces(g, s_faces, xf, yf, zf);
+    const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
+    const ScatterConsts sc = scatter_consts(g);
+    const LaunchConsts lc{g.zcur0, g.cellk0};
 
+    Counters c;
+    c.clear();
+    SumTally<Tally> tally;
+    tally.jm = g.jmean;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        PhiloxRng rng;
+        rng.seed(seed, first_id + (uint64_t)i);
+        double u[4];
+        rng.block(u);
+        FastPhoton p;
+        adopt(g, lc, p, launch_fast(g, u, scatter_on));
+        tally.begin();
+        int steps = 0, nscatt = 0, fate = 0, ndraws = 4;
+        for (;;) {
+            const int r = voxel_step_fast(g, xf, yf, zf, p, tally);
+            ++steps;
+            if (r == STEP_WALL) {
+                if (steps >= kMaxStepsPerPacket) { c.errors++; break; }
+                continue;
+            }
+            if (r == STEP_EXIT) { fate = exit_face_fast(p, g); break; }
+            if (!scatter_on) break;                               // mcpolar.f90:166-169 stub
+            rng.block(u);
+            if (u[0] < g.albedo) {
+                scatter_fast(g, sc, p, u[1], u[2], u[3]);
+                ++nscatt;
+                ndraws += 4;
+            } else {
+                ndraws += 1;
+                break;
+            }
+        }
+        tally.flush();
+        c.steps += (unsigned long long)steps;
+        c.scatters += (unsigned long long)nscatt;
+        c.fate(fate);
+        if (kRecord) {
+            tamc_packet_record *r = rec + i;
+            r->xp = p.xcur - g.xmax; r->yp = p.ycur - g.ymax; r->zp = p.zcur - g.zmax;
+            r->nxp = p.nxp; r->nyp = p.nyp; r->nzp = p.nzp;
+            r->deposit = tally.packet_sum;
+            r->xcell = (p.celli < 1 || p.celli > g.nxg) ? -1 : p.celli;
+            r->ycell = (p.cellj < 1 || p.cellj > g.nyg) ? -1 : p.cellj;
+            r->zcell = (p.cellk < 1 || p.cellk > g.nzg) ? -1 : p.cellk;
+            r->steps = steps; r->nscatt = nscatt; r->ndraws = ndraws; r->fate = fate; r->flags = 0;
+        }
+    }
+    c.commit(cnt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 2: one packet per thread on the exact (replay) arithmetic
+// ---------------------------------------------------------------------------------------------
+template <class Tally, bool kRecord>
+__global__ void __launch_bounds__(256) k_transport_exact(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
+                                                         unsigned long long *__restrict__ cnt,
+                                                         tamc_packet_record *__restrict__ rec)
+{
+    extern __shared__ double s_faces[];
+    const double *xf, *yf, *zf;
+    stage_faces(g, s_faces, xf, yf, zf);
     Counters c;
     c.clear();
     Tally tally;
@@ -40,56 +129,97 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
 }
 
 // ---------------------------------------------------------------------------------------------
-// variant 1: persistent warps with in-place refill
+// variant 1: persistent warps, chunked ids, launch reservoir, phased scattering
 // ---------------------------------------------------------------------------------------------
 enum { LANE_IDLE = 0, LANE_WALK = 1, LANE_INTERACT = 2 };
+constexpr int kResv = 64;   // reservoir slots per warp: < 32 left over + one generation of 32
+
+struct WarpReservoir {
+    double xcur[kResv], ycur[kResv], tau[kResv], cosp[kResv], sinp[kResv];
+    unsigned int id_lo[kResv], id_hi[kResv];
+    int celli[kResv], cellj[kResv];
+};
 
 template <class Tally>
 __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
-                                                              int refill_min, int scatter_min,
+                                                              int chunk, int scatter_min,
                                                               unsigned long long *__restrict__ cnt)
 {
     extern __shared__ double s_faces[];
     const double *xf, *yf, *zf;
     stage_faces(g, s_faces, xf, yf, zf);
+    const int nfaces = g.nxg + g.nyg + g.nzg + 3;
+    WarpReservoir &R = reinterpret_cast<WarpReservoir *>(s_faces + nfaces)[threadIdx.x >> 5];
 
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    // contiguous id range of this warp (n < 2^47, nwarps < 2^16: no overflow)
-    long long next = (n / nwarps) * warp + min(n % nwarps, warp);
-    const long long end = next + n / nwarps + (warp < n % nwarps ? 1 : 0);
     const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
+    const ScatterConsts sc = scatter_consts(g);
+    const LaunchConsts lc{g.zcur0, g.cellk0};
 
     Counters c;
     c.clear();
     Tally tally;
     tally.jm = g.jmean;
     tally.begin();
-    Photon p;
+    FastPhoton p;
     PhiloxRng rng;
+    rng.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     int mode = LANE_IDLE, steps = 0, nscatt = 0;
+    int count = 0;                       // launched packets parked in the reservoir (warp-uniform)
+    long long next = 0, end = 0;         // ids of the chunk this warp currently owns
+    bool exhausted = false;
     double u[4];
 
     for (;;) {
         const unsigned idle = __ballot_sync(full, mode == LANE_IDLE);
         const int nidle = __popc(idle);
-        // ---- refill idle lanes from the warp's id range
-        if (next < end && (nidle >= refill_min || nidle == 32)) {
-            const long long avail = end - next;
+        // ---- more idle lanes than parked packets: launch another 32 with every lane active
+        if (nidle > count && !exhausted) {
+            if (next >= end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(cnt + CNT_WORK, (unsigned long long)chunk);
+                base = __shfl_sync(full, base, 0);
+                if ((long long)base >= n) exhausted = true;
+                else { next = (long long)base; end = min(next + chunk, n); }
+            }
+            if (!exhausted) {
+                const long long id = next + lane;
+                if (id < end) {
+                    const uint64_t gid = first_id + (uint64_t)id;
+                    PhiloxRng lr;
+                    lr.seed(seed, gid);
+                    lr.block(u);
+                    const Launched L = launch_fast(g, u, scatter_on);
+                    const int s = count + (int)lane;
+                    R.xcur[s] = L.xcur; R.ycur[s] = L.ycur; R.tau[s] = L.tau; R.cosp[s] = L.cosp; R.sinp[s] = L.sinp;
+                    R.id_lo[s] = (uint32_t)gid; R.id_hi[s] = (uint32_t)(gid >> 32);
+                    R.celli[s] = L.celli; R.cellj[s] = L.cellj;
+                }
+                const int ngen = (int)min((long long)32, end - next);
+                count += ngen;
+                next += ngen;
+                __syncwarp();
+            }
+        }
+        // ---- idle lanes adopt parked packets
+        if (nidle && count) {
             const int rank = __popc(idle & lt_mask);
-            if (mode == LANE_IDLE && rank < avail) {
-                rng.seed(seed, first_id + (uint64_t)(next + rank));
-                rng.block(u);
-                launch(g, p, u);
+            if (mode == LANE_IDLE && rank < count) {
+                const int s = count - 1 - rank;
+                Launched L;
+                L.xcur = R.xcur[s]; L.ycur = R.ycur[s]; L.tau = R.tau[s]; L.cosp = R.cosp[s]; L.sinp = R.sinp[s];
+                L.celli = R.celli[s]; L.cellj = R.cellj[s];
+                rng.id_lo = R.id_lo[s]; rng.id_hi = R.id_hi[s]; rng.blk = 1;   // block 0 went into the launch
+                adopt(g, lc, p, L);
                 tally.begin();
                 steps = 0;
                 nscatt = 0;
                 mode = LANE_WALK;
             }
-            next += min((long long)nidle, avail);
+            count -= min(nidle, count);
+            __syncwarp();
         }
         // ---- scattering phase for the lanes waiting at an interaction site
         const unsigned waiting = __ballot_sync(full, mode == LANE_INTERACT);
@@ -97,12 +227,9 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
         if (waiting && (__popc(waiting) >= scatter_min || walking == 0u)) {
             if (mode == LANE_INTERACT) {
                 rng.block(u);
-                if (u[0] < g.albedo) {
-                    stokes(g, p, u[1], u[2]);
+                if (u[0] < g.albedo) {                    // draw < albedo ? stokes : absorbed
+                    scatter_fast(g, sc, p, u[1], u[2], u[3]);
                     ++nscatt;
-                    recentre(g, p);
-                    p.taurun = 0.;
-                    p.tau = -log(u[3]);
                     mode = LANE_WALK;
                 } else {
                     tally.flush();
@@ -112,12 +239,12 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
                     mode = LANE_IDLE;
                 }
             }
-        } else if (walking == 0u && waiting == 0u && next >= end) {
-            break;   // nothing in flight and the id range is exhausted
+        } else if (walking == 0u && waiting == 0u && count == 0 && exhausted) {
+            break;
         }
         // ---- one voxel-step for every walking lane
         if (mode == LANE_WALK) {
-            const int r = voxel_step(g, xf, yf, zf, p, tally);
+            const int r = voxel_step_fast(g, xf, yf, zf, p, tally);
             ++steps;
             if (r == STEP_INTERACT && scatter_on) {
                 mode = LANE_INTERACT;
@@ -126,7 +253,7 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
                 c.steps += (unsigned long long)steps;
                 c.scatters += (unsigned long long)nscatt;
                 c.errors += (r == STEP_WALL);
-                c.fate(r == STEP_EXIT ? exit_face(p) : 0);
+                c.fate(r == STEP_EXIT ? exit_face_fast(p, g) : 0);
                 mode = LANE_IDLE;
             }
         }
@@ -136,9 +263,9 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
 
 // ---------------------------------------------------------------------------------------------
 // roofline probe: the tally / grid address stream of straight-down packets and nothing else.
-// Per packet: a column under the beam disk (fp32 rejection sampling), then voxel after voxel from
-// the top face, one fp64 load of rhokap and one fp64 RED into jmean per voxel, continuing with
-// probability exp(-rhokap*dz) decided by comparing raw Philox words against a threshold.
+// Per packet: a column under the beam disk (fp32), then voxel after voxel from the top face, one
+// fp64 load of rhokap and one fp64 RED into jmean per voxel, continuing with probability
+// exp(-rhokap*dz) decided by comparing raw Philox words against a threshold.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_probe(const DevGrid g, long long n, uint64_t seed, float disk_r_vox,
                                                unsigned long long *__restrict__ cnt)
@@ -162,7 +289,6 @@ __global__ void __launch_bounds__(256) k_probe(const DevGrid g, long long n, uin
             const long long jidx = (long long)(ci - 1) + (long long)g.nxg * ((long long)(cj - 1) + (long long)g.nyg * (ck - 1));
             atomicAdd(g.jmean + jidx, rk);
             ++steps;
-            // continue with probability exp(-rk*dz); dz = 2 zmax / nzg
             const float pc = __expf(-(float)rk * (float)(2. * g.zmax / g.nzg));
             if (w * 2.3283064e-10f >= pc || --ck < 1) break;
             if (used == 3) { w = r.w; used = 4; }
@@ -198,10 +324,14 @@ static long long resident_ctas(K kernel, const LaunchCfg &cfg, size_t smem)
     return (long long)per_sm * cfg.num_sms;
 }
 
+// grid = min(CTAs resident on the whole chip, CTAs needed to give every thread one packet)
 template <class K, class... Args>
 static cudaError_t launch_sized(K kernel, const LaunchCfg &cfg, size_t smem, long long n, cudaStream_t s, Args... args)
 {
-    // grid = min(resident CTAs on the whole chip, CTAs needed to give every thread one packet)
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     const long long resident = resident_ctas(kernel, cfg, smem);
     const long long want = (n + cfg.block - 1) / cfg.block;
     const int grid = (int)(want < resident ? want : resident);
@@ -216,19 +346,36 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n
     const bool merge = cfg.merge < 0 ? (g.flags & TAMC_SCATTER) != 0 : cfg.merge != 0;
     const size_t smem = faces_bytes(g);
     if (launches) *launches += 1;
+    tamc_packet_record *none = nullptr;
 
+    if (cfg.variant == 2) {
+        if (d_rec) {
+            if (merge) return launch_sized(k_transport_exact<MergeTally, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
+            return launch_sized(k_transport_exact<DirectTally, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
+        }
+        if (merge) return launch_sized(k_transport_exact<MergeTally, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
+        return launch_sized(k_transport_exact<DirectTally, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
+    }
     if (d_rec) {
-        if (merge) return launch_sized(k_transport_simple<MergeTally, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
-        return launch_sized(k_transport_simple<DirectTally, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
+        if (merge) return launch_sized(k_transport_simple<MergeTally32, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
+        return launch_sized(k_transport_simple<DirectTally32, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
     }
     if (cfg.variant == 0) {
-        tamc_packet_record *none = nullptr;
-        if (merge) return launch_sized(k_transport_simple<MergeTally, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
-        return launch_sized(k_transport_simple<DirectTally, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
+        if (merge) return launch_sized(k_transport_simple<MergeTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
+        return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
-    if (merge)
-        return launch_sized(k_transport_persistent<MergeTally>, cfg, smem, n, s, g, n, seed, first_id, cfg.refill_min, cfg.scatter_min, d_cnt);
-    return launch_sized(k_transport_persistent<DirectTally>, cfg, smem, n, s, g, n, seed, first_id, cfg.refill_min, cfg.scatter_min, d_cnt);
+    // persistent warps: faces + one reservoir per warp in shared memory
+    const size_t psmem = smem + (size_t)(cfg.block / 32) * sizeof(WarpReservoir);
+    int chunk = cfg.chunk;
+    if (chunk <= 0) {
+        // aim for >= 8 chunks per resident warp so the tail is short, within [32, 1024] ids per claim
+        const long long warps = (long long)cfg.num_sms * 24;
+        long long c = n / (warps * 8);
+        c = c < 32 ? 32 : (c > 1024 ? 1024 : c);
+        chunk = (int)(c / 32 * 32);
+    }
+    if (merge) return launch_sized(k_transport_persistent<MergeTally32>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    return launch_sized(k_transport_persistent<DirectTally32>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
 }
 
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,

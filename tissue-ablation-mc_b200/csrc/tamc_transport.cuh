@@ -29,7 +29,7 @@ constexpr double kTWOPI = 6.283185;
 // against a caller-supplied delta below the ulp of a face coordinate (the reference would spin).
 constexpr int kMaxStepsPerPacket = 1 << 26;
 
-enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_N = 16 };
+enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_WORK = 12, CNT_N = 16 };
 
 struct DevGrid {
     int nxg, nyg, nzg;
@@ -40,6 +40,8 @@ struct DevGrid {
     double zp0;           // zmax-(1.e-8*(2.*zmax/nzg)), sourceph.f90:32
     double inv_dx, inv_dy, inv_dz;  // nxg/(2 xmax) ...: first guess of the voxel index only
     double albedo, hgg, g2;
+    double zcur0;         // zp0 + zmax: every packet starts at this height (inttau2.f90:26)
+    int cellk0;           // int(nzg*(zp0+zmax)/(2.*zmax))+1, sourceph.f90:47
     int flags;
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
