@@ -43,9 +43,20 @@ __device__ __forceinline__ void set_direction(FastPhoton &p)
     f |= (p.nyp == 0.) ? 16 : 0;
     f |= (p.nzp == 0.) ? 32 : 0;
     p.dflags = f;
-    p.inx = (f & 8) ? 0. : 1. / p.nxp;
-    p.iny = (f & 16) ? 0. : 1. / p.nyp;
-    p.inz = (f & 32) ? 0. : 1. / p.nzp;
+    if ((f & 56) == 0) {
+        // one division for the three reciprocals (the products cannot under/overflow for unit vectors
+        // whose smallest component is far above 1e-100)
+        const double xy = p.nxp * p.nyp;
+        const double r = 1. / (xy * p.nzp);
+        p.inz = xy * r;
+        const double rz = r * p.nzp;
+        p.inx = p.nyp * rz;
+        p.iny = p.nxp * rz;
+    } else {
+        p.inx = (f & 8) ? 0. : 1. / p.nxp;
+        p.iny = (f & 16) ? 0. : 1. / p.nyp;
+        p.inz = (f & 32) ? 0. : 1. / p.nzp;
+    }
 }
 
 struct LaunchConsts {
@@ -56,7 +67,8 @@ struct LaunchConsts {
 // What a launch produces; small enough to park in shared memory until a lane is free.
 struct Launched {
     double xcur, ycur, tau, cosp, sinp;
-    int celli, cellj;
+    int cells;        // celli | cellj << 16 (tamc_init bounds the grid at 4096 per axis)
+    int ridx, jidx;   // linear indices of the launch voxel in rhokap / jmean
 };
 
 // sourceph.f90:28-47 + inttau2.f90:36.  u = (r, theta, phi, tau) draws in the reference's order.
@@ -70,8 +82,11 @@ __device__ __forceinline__ Launched launch_fast(const DevGrid &g, const double u
     const double sr = sqrt(r);
     L.xcur = sr * c + g.xmax;
     L.ycur = sr * s + g.ymax;
-    L.celli = (int)(L.xcur * g.inv_dx) + 1;
-    L.cellj = (int)(L.ycur * g.inv_dy) + 1;
+    const int celli = (int)(L.xcur * g.inv_dx) + 1;
+    const int cellj = (int)(L.ycur * g.inv_dy) + 1;
+    L.cells = celli | (cellj << 16);
+    L.ridx = celli + g.sx * (cellj + (g.nyg + 2) * g.cellk0);
+    L.jidx = (celli - 1) + g.nxg * ((cellj - 1) + g.nyg * (g.cellk0 - 1));
     L.cosp = 1.;
     L.sinp = 0.;
     if (need_azimuth) sincos(kTWOPI * u[2], &L.sinp, &L.cosp);   // phi is first used by the first scattering
@@ -87,13 +102,19 @@ __device__ __forceinline__ void adopt(const DevGrid &g, const LaunchConsts &lc, 
     p.dflags = 4 | 8 | 16;
     p.sint = 0.; p.cosp = L.cosp; p.sinp = L.sinp;
     p.tau = L.tau; p.taurun = 0.;
-    p.celli = L.celli; p.cellj = L.cellj; p.cellk = lc.cellk0;
-    p.ridx = p.celli + g.sx * (p.cellj + (g.nyg + 2) * p.cellk);
-    p.jidx = (p.celli - 1) + g.nxg * ((p.cellj - 1) + g.nyg * (p.cellk - 1));
+    p.celli = L.cells & 0xffff; p.cellj = L.cells >> 16; p.cellk = lc.cellk0;
+    p.ridx = L.ridx;
+    p.jidx = L.jidx;
 }
 
-// One voxel-step, inttau2.f90:37-63.
-template <class Tally>
+// One voxel-step, inttau2.f90:37-63, written without divergent branches: the wall-crossing step
+// (inttau2.f90:42-48) and the final partial step (:50-55) share one instruction stream and differ
+// only through selects, so a warp whose lanes cross different faces -- or end their flight -- in the
+// same iteration still issues the step once.
+// kNeedPos = false (shipped stub regime: the packet ends at its first interaction) drops the final
+// position update and its division: the last deposit dcell*rhokap = ((tau-taurun)/rhokap)*rhokap is
+// tallied as tau-taurun.
+template <bool kNeedPos, class Tally>
 __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *xf, const double *yf, const double *zf,
                                                FastPhoton &p, Tally &tally)
 {
@@ -103,50 +124,41 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     const double dx = (f & 8) ? 100000. : (fx - p.xcur) * p.inx;
     const double dy = (f & 16) ? 100000. : (fy - p.ycur) * p.iny;
     const double dz = (f & 32) ? 100000. : (fz - p.zcur) * p.inz;
-    double dcell = fmin(fmin(dx, dy), dz);
+    const double dwall = fmin(fmin(dx, dy), dz);
     const double rk = __ldg(g.rhokap + p.ridx);
-    const double taucell = dcell * rk;
+    const double taucell = dwall * rk;
+    const bool wall = p.taurun + taucell < p.tau;                    // inttau2.f90:42
+    const double rest = p.tau - p.taurun;
 
-    if (p.taurun + taucell < p.tau) {
-        p.taurun += taucell;
-        tally.add(p.jidx, taucell);
-        bool out;
-        if (dcell == dz) {                               // later axis wins ties, inttau2.f90:116-118
-            p.xcur += p.nxp * dcell;
-            p.ycur += p.nyp * dcell;
-            p.zcur = negz ? fz - g.delta : fz + g.delta;
-            const int s = negz ? -1 : 1;
-            p.cellk += s;
-            p.ridx += s * (int)g.sxy;
-            p.jidx += s * g.nxg * g.nyg;
-            out = (p.cellk < 1) | (p.cellk > g.nzg);
-        } else if (dcell == dy) {
-            p.xcur += p.nxp * dcell;
-            p.ycur = negy ? fy - g.delta : fy + g.delta;
-            p.zcur += p.nzp * dcell;
-            const int s = negy ? -1 : 1;
-            p.cellj += s;
-            p.ridx += s * g.sx;
-            p.jidx += s * g.nxg;
-            out = (p.cellj < 1) | (p.cellj > g.nyg);
-        } else {
-            p.xcur = negx ? fx - g.delta : fx + g.delta;
-            p.ycur += p.nyp * dcell;
-            p.zcur += p.nzp * dcell;
-            const int s = negx ? -1 : 1;
-            p.celli += s;
-            p.ridx += s;
-            p.jidx += s;
-            out = (p.celli < 1) | (p.celli > g.nxg);
-        }
-        return out ? STEP_EXIT : STEP_WALL;
+    if (!kNeedPos) {
+        tally.add(p.jidx, wall ? taucell : rest);
+        if (!wall) return STEP_INTERACT;
     }
-    dcell = (p.tau - p.taurun) / rk;                      // inttau2.f90:51-55
-    tally.add(p.jidx, dcell * rk);
-    p.xcur += p.nxp * dcell;
-    p.ycur += p.nyp * dcell;
-    p.zcur += p.nzp * dcell;
-    return STEP_INTERACT;
+    double dcell = dwall;
+    if (kNeedPos) {
+        const double dpart = rest / rk;                               // inttau2.f90:51 (unused when rk == 0: wall is true)
+        dcell = wall ? dwall : dpart;
+        tally.add(p.jidx, wall ? taucell : dpart * rk);
+    }
+    p.taurun += taucell;
+    // which face: the later axis wins ties (inttau2.f90:116-118); none on the final partial step
+    const bool hz = wall & (dwall == dz);
+    const bool hy = wall & !hz & (dwall == dy);
+    const bool hx = wall & !hz & !hy;
+    const double xn = p.xcur + p.nxp * dcell, yn = p.ycur + p.nyp * dcell, zn = p.zcur + p.nzp * dcell;
+    p.xcur = hx ? (negx ? fx - g.delta : fx + g.delta) : xn;          // inttau2.f90:140-170
+    p.ycur = hy ? (negy ? fy - g.delta : fy + g.delta) : yn;
+    p.zcur = hz ? (negz ? fz - g.delta : fz + g.delta) : zn;
+    const int sx = hx ? 1 - 2 * negx : 0, sy = hy ? 1 - 2 * negy : 0, sz = hz ? 1 - 2 * negz : 0;
+    p.celli += sx;
+    p.cellj += sy;
+    p.cellk += sz;
+    p.ridx += sx + sy * g.sx + sz * (int)g.sxy;
+    p.jidx += sx + sy * g.nxg + sz * (g.nxg * g.nyg);
+    if (!wall) return STEP_INTERACT;
+    const bool out = ((unsigned)(p.celli - 1) >= (unsigned)g.nxg) | ((unsigned)(p.cellj - 1) >= (unsigned)g.nyg) |
+                     ((unsigned)(p.cellk - 1) >= (unsigned)g.nzg);
+    return out ? STEP_EXIT : STEP_WALL;
 }
 
 struct ScatterConsts {
@@ -198,7 +210,7 @@ __device__ __forceinline__ void scatter_fast(const DevGrid &g, const ScatterCons
     uz = fmin(1., fmax(-1., uz));
     const double h2 = ux * ux + uy * uy;
     if (h2 > 0.) {
-        const double ih = 1. / sqrt(h2);
+        const double ih = rsqrt(h2);
         p.cosp = ux * ih;
         p.sinp = uy * ih;
     }

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
         tally.begin();
         int steps = 0, nscatt = 0, fate = 0, ndraws = 4;
         for (;;) {
-            const int r = voxel_step_fast(g, xf, yf, zf, p, tally);
+            const int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
             ++steps;
             if (r == STEP_WALL) {
                 if (steps >= kMaxStepsPerPacket) { c.errors++; break; }
@@ -137,10 +137,12 @@ constexpr int kResv = 64;   // reservoir slots per warp: < 32 left over + one ge
 struct WarpReservoir {
     double xcur[kResv], ycur[kResv], tau[kResv], cosp[kResv], sinp[kResv];
     unsigned int id_lo[kResv], id_hi[kResv];
-    int celli[kResv], cellj[kResv];
+    int cells[kResv], ridx[kResv], jidx[kResv];
 };
 
-template <class Tally>
+// kScatter = false is the shipped regime (mcpolar.f90:166-169 stub): no scattering phase, no azimuth,
+// no position after the final partial step -- the compiler drops that state and its registers.
+template <class Tally, bool kScatter>
 __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                               int chunk, int scatter_min,
                                                               unsigned long long *__restrict__ cnt)
@@ -154,7 +156,6 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
     const ScatterConsts sc = scatter_consts(g);
     const LaunchConsts lc{g.zcur0, g.cellk0};
 
@@ -191,11 +192,14 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
                     PhiloxRng lr;
                     lr.seed(seed, gid);
                     lr.block(u);
-                    const Launched L = launch_fast(g, u, scatter_on);
+                    const Launched L = launch_fast(g, u, kScatter);
                     const int s = count + (int)lane;
-                    R.xcur[s] = L.xcur; R.ycur[s] = L.ycur; R.tau[s] = L.tau; R.cosp[s] = L.cosp; R.sinp[s] = L.sinp;
-                    R.id_lo[s] = (uint32_t)gid; R.id_hi[s] = (uint32_t)(gid >> 32);
-                    R.celli[s] = L.celli; R.cellj[s] = L.cellj;
+                    R.xcur[s] = L.xcur; R.ycur[s] = L.ycur; R.tau[s] = L.tau;
+                    if (kScatter) {
+                        R.cosp[s] = L.cosp; R.sinp[s] = L.sinp;
+                        R.id_lo[s] = (uint32_t)gid; R.id_hi[s] = (uint32_t)(gid >> 32);
+                    }
+                    R.cells[s] = L.cells; R.ridx[s] = L.ridx; R.jidx[s] = L.jidx;
                 }
                 const int ngen = (int)min((long long)32, end - next);
                 count += ngen;
@@ -209,9 +213,13 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
             if (mode == LANE_IDLE && rank < count) {
                 const int s = count - 1 - rank;
                 Launched L;
-                L.xcur = R.xcur[s]; L.ycur = R.ycur[s]; L.tau = R.tau[s]; L.cosp = R.cosp[s]; L.sinp = R.sinp[s];
-                L.celli = R.celli[s]; L.cellj = R.cellj[s];
-                rng.id_lo = R.id_lo[s]; rng.id_hi = R.id_hi[s]; rng.blk = 1;   // block 0 went into the launch
+                L.xcur = R.xcur[s]; L.ycur = R.ycur[s]; L.tau = R.tau[s];
+                L.cosp = 1.; L.sinp = 0.;
+                if (kScatter) {
+                    L.cosp = R.cosp[s]; L.sinp = R.sinp[s];
+                    rng.id_lo = R.id_lo[s]; rng.id_hi = R.id_hi[s]; rng.blk = 1;   // block 0 went into the launch
+                }
+                L.cells = R.cells[s]; L.ridx = R.ridx[s]; L.jidx = R.jidx[s];
                 adopt(g, lc, p, L);
                 tally.begin();
                 steps = 0;
@@ -222,9 +230,9 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
             __syncwarp();
         }
         // ---- scattering phase for the lanes waiting at an interaction site
-        const unsigned waiting = __ballot_sync(full, mode == LANE_INTERACT);
+        const unsigned waiting = kScatter ? __ballot_sync(full, mode == LANE_INTERACT) : 0u;
         const unsigned walking = __ballot_sync(full, mode == LANE_WALK);
-        if (waiting && (__popc(waiting) >= scatter_min || walking == 0u)) {
+        if (kScatter && waiting && (__popc(waiting) >= scatter_min || walking == 0u)) {
             if (mode == LANE_INTERACT) {
                 rng.block(u);
                 if (u[0] < g.albedo) {                    // draw < albedo ? stokes : absorbed
@@ -244,9 +252,9 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
         }
         // ---- one voxel-step for every walking lane
         if (mode == LANE_WALK) {
-            const int r = voxel_step_fast(g, xf, yf, zf, p, tally);
+            const int r = voxel_step_fast<kScatter>(g, xf, yf, zf, p, tally);
             ++steps;
-            if (r == STEP_INTERACT && scatter_on) {
+            if (kScatter && r == STEP_INTERACT) {
                 mode = LANE_INTERACT;
             } else if (r != STEP_WALL || steps >= kMaxStepsPerPacket) {
                 tally.flush();
@@ -374,8 +382,12 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n
         c = c < 32 ? 32 : (c > 1024 ? 1024 : c);
         chunk = (int)(c / 32 * 32);
     }
-    if (merge) return launch_sized(k_transport_persistent<MergeTally32>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
-    return launch_sized(k_transport_persistent<DirectTally32>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    if (g.flags & TAMC_SCATTER) {
+        if (merge) return launch_sized(k_transport_persistent<MergeTally32, true>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        return launch_sized(k_transport_persistent<DirectTally32, true>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    }
+    if (merge) return launch_sized(k_transport_persistent<MergeTally32, false>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    return launch_sized(k_transport_persistent<DirectTally32, false>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
 }
 
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,

@@ -338,9 +338,12 @@ struct Counters {
     __device__ __forceinline__ void fate(int f)
     {
         packets++;
-        absorbed += (f == 0);
+        if (f == 0) {
+            absorbed++;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) exits[i] += (f == i + 1);
+            for (int i = 0; i < 6; ++i) exits[i] += (f == i + 1);
+        }
     }
     __device__ __forceinline__ void commit(unsigned long long *g) const
     {
