@@ -267,11 +267,9 @@ def run_ours(args, cfg, name):
         t.set_option(k, int(v))
     t.set_optics(rk, cfg["albedo"], cfg["hgg"], flags=cfg["flags"])
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(tamc.comm_unique_id()), dtype=torch.uint8).to(dev)
-        dist.broadcast(idt, 0)
-        t.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+        from tamc import dist as tdist
+
+        t.comm_init(world, rank, tdist.broadcast_unique_id(tamc.comm_unique_id, dist, dev))
     stream = torch.cuda.ExternalStream(t.stream, device=dev)
 
     try:

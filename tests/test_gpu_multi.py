@@ -1,0 +1,68 @@
+"""Two GPUs, one process each (skipped on a single-GPU box): the NCCL all-reduce inside tamc_run gives
+every rank the sum of the per-rank tallies == one GPU running all the ids."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "tissue-ablation-mc_b200")]
+    import torch
+    import torch.distributed as dist
+
+    import tamc
+    from tamc import dist as tdist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = tamc.configs.scaled("skin200", 64)
+    t = tamc.MCTransport(64, 64, 64, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=rank)
+    t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=cfg["flags"])
+    t.comm_init(world, rank, tdist.broadcast_unique_id(tamc.comm_unique_id, dist))
+    jm1, st1 = t.run(20000, 99)          # ids [rank*20000, (rank+1)*20000), cursor -> 40000
+    jm2, st2 = t.run(20000, 99)          # ids 40000 + ...
+    assert st1["packets"] == 20000 and st1["allreduce_ms"] > 0
+    np.save(f"{out}.{rank}.npy", np.stack([jm1, jm2]))
+    dist.barrier()
+    t.close()
+    dist.destroy_process_group()
+
+
+def test_allreduce_equals_single_gpu(tmp_path):
+    import torch
+
+    import tamc
+    from tests.util import compare_grids, voxel_tau
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "jm")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = np.load(out + ".0.npy"), np.load(out + ".1.npy")
+    assert np.array_equal(a, b)                          # every rank holds the same reduced grid
+    cfg = tamc.configs.scaled("skin200", 64)
+    t = tamc.MCTransport(64, 64, 64, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=0)
+    rk = cfg["rhokap"]()
+    t.set_optics(rk, cfg["albedo"], cfg["hgg"], flags=cfg["flags"])
+    for call in range(2):
+        t.run_async(40000, 99, call * 40000)
+        compare_grids(a[call], t.get_jmean(), rtol=1e-9, dep_scale=voxel_tau(cfg, rk))
+    t.close()

@@ -1,0 +1,47 @@
+!
+!  mcpolar_patch.f90 -- what a maintainer adds to the reference's src/mcpolar.f90 to run the photon
+!  loop on B200s through libtamc.so.  Not a stand-alone program: three fragments, each marked with the
+!  reference lines it goes next to or replaces.  Everything else in mcpolar.f90 (input.params, gridset,
+!  init_opt1, the 3dFD heat / ablation coupling, writer) is unchanged.  Shipped as source; there is no
+!  Fortran compiler in this image (INTEGRATION.md).
+!
+!  One MPI rank drives one GPU (rank id -> device mod(id, ngpus)), exactly as the reference gives each
+!  rank its own `do j = 1, nphotons` loop; the ranks' tallies are summed by NCCL over NVLink instead of
+!  MPI_allREDUCE.
+!
+
+!--- (1) declarations, next to mcpolar.f90:26-34 ---------------------------------------------------
+      use tamc_mod
+      type(c_ptr)            :: tamc
+      integer(c_int)         :: ierr, oflags
+      character(kind=c_char) :: nccl_id(128)
+      integer(c_int64_t)     :: seed64
+
+!--- (2) set-up, after gridset/delta at mcpolar.f90:109-112 ----------------------------------------
+      ierr = tamc_init(int(mod(id, tamc_device_count()), c_int), nxg, nyg, nzg, xmax, ymax, zmax, delta, tamc)
+      call tamc_check(ierr, 'tamc_init')
+      !  every rank needs the same NCCL id: rank 0 makes it, MPI carries it once
+      if(id == 0)then
+         ierr = tamc_comm_unique_id(nccl_id)
+         call tamc_check(ierr, 'tamc_comm_unique_id')
+      end if
+      call MPI_Bcast(nccl_id, 128, MPI_CHARACTER, 0, new_comm)
+      ierr = tamc_comm_init(tamc, int(numproc, c_int), int(id, c_int), nccl_id)
+      call tamc_check(ierr, 'tamc_comm_init')
+      !  optional: page-lock the two arrays that cross PCIe every MC call
+      ierr = tamc_pin_host(c_loc(rhokap), int(size(rhokap), c_int64_t)*8_c_int64_t)
+      ierr = tamc_pin_host(c_loc(jmeanGLOBAL), int(size(jmeanGLOBAL), c_int64_t)*8_c_int64_t)
+      seed64 = 95648324_c_int64_t          ! mcpolar.f90:97: the run seed; ranks are told apart by packet id
+      oflags = 0                           ! TAMC_SCATTER to run the albedo/stokes loop instead of the stub
+
+!--- (3) the hot path: REPLACES mcpolar.f90:151-173 (photon loop + MPI_allREDUCE) --------------------
+      !  rhokap was rewritten by setupThermalCoeff at the end of the previous iteration (mcpolar.f90:182)
+      ierr = tamc_set_optics(tamc, rhokap, albedo, hgg, n1, n2, oflags)
+      call tamc_check(ierr, 'tamc_set_optics')
+      !  nphotons packets on this rank, tally summed over all ranks, UNSCALED sum into jmeanGLOBAL
+      ierr = tamc_run(tamc, int(nphotons, c_int64_t), seed64, jmeanGLOBAL, c_null_ptr)
+      call tamc_check(ierr, 'tamc_run')
+      !  mcpolar.f90:174 (the power / packet-count / voxel-volume scaling) stays exactly as it is.
+
+!--- (4) before MPI_Finalize at mcpolar.f90:215 ------------------------------------------------------
+      ierr = tamc_finalize(tamc)

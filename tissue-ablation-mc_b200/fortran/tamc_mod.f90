@@ -1,0 +1,116 @@
+module tamc_mod
+!
+!  iso_c_binding interface to libtamc.so (include/tamc.h): the GPU photon transport that takes the
+!  place of the per-rank photon loop and of the jmean reduction in mcpolar.f90 (lines 151-173 of the
+!  reference driver).  Shipped as source: this image has no Fortran compiler, so the module is not
+!  built or tested here (see INTEGRATION.md); the same entry points are exercised through the C++
+!  driver shim (tissue-ablation-mc_b200/driver) and the Python ctypes binding.
+!
+!  The reference is compiled with -freal-4-real-8 (src/Makefile:3), so its default `real` arrays
+!  (rhokap, jmean, jmeanGLOBAL in iarray.f90) are c_double and can be passed without a copy.
+!
+    use, intrinsic :: iso_c_binding
+
+    implicit none
+
+    integer(c_int), parameter :: TAMC_OK = 0
+    integer(c_int), parameter :: TAMC_SCATTER = 1
+
+    !  mirrors tamc_stats (include/tamc.h)
+    type, bind(C) :: tamc_stats
+        integer(c_int64_t) :: packets, voxel_steps, scatters, absorbed
+        integer(c_int64_t) :: exits(6)
+        real(c_double)     :: zero_ms, kernel_ms, allreduce_ms, h2d_ms, d2h_ms
+        integer(c_int64_t) :: gpu_launches
+    end type tamc_stats
+
+    interface
+
+        integer(c_int) function tamc_init(device, nxg, nyg, nzg, xmax, ymax, zmax, delta, handle) &
+                bind(C, name="tamc_init")
+            import :: c_int, c_double, c_ptr
+            integer(c_int), value :: device, nxg, nyg, nzg
+            real(c_double), value :: xmax, ymax, zmax, delta
+            type(c_ptr), intent(out) :: handle
+        end function tamc_init
+
+        integer(c_int) function tamc_finalize(handle) bind(C, name="tamc_finalize")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: handle
+        end function tamc_finalize
+
+        integer(c_int) function tamc_set_source_co2(handle, spot_diameter_cm) bind(C, name="tamc_set_source_co2")
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value    :: handle
+            real(c_double), value :: spot_diameter_cm
+        end function tamc_set_source_co2
+
+        !  rhokap is passed as the whole allocatable rhokap(0:nxg+1,0:nyg+1,0:nzg+1): contiguous, so the
+        !  compiler hands over the address of rhokap(0,0,0) without a temporary.
+        integer(c_int) function tamc_set_optics(handle, rhokap, albedo, hgg, n1, n2, flags) &
+                bind(C, name="tamc_set_optics")
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value        :: handle
+            real(c_double), intent(in) :: rhokap(*)
+            real(c_double), value     :: albedo, hgg, n1, n2
+            integer(c_int), value     :: flags
+        end function tamc_set_optics
+
+        integer(c_int) function tamc_run(handle, nphotons, seed, jmean_global, stats) bind(C, name="tamc_run")
+            import :: c_int, c_int64_t, c_double, c_ptr
+            type(c_ptr), value           :: handle
+            integer(c_int64_t), value    :: nphotons, seed
+            real(c_double), intent(out)  :: jmean_global(*)
+            type(c_ptr), value           :: stats        ! c_loc(a tamc_stats) or c_null_ptr
+        end function tamc_run
+
+        integer(c_int) function tamc_comm_unique_id(id128) bind(C, name="tamc_comm_unique_id")
+            import :: c_int, c_char
+            character(kind=c_char), intent(out) :: id128(128)
+        end function tamc_comm_unique_id
+
+        integer(c_int) function tamc_comm_init(handle, nranks, rank, id128) bind(C, name="tamc_comm_init")
+            import :: c_int, c_char, c_ptr
+            type(c_ptr), value     :: handle
+            integer(c_int), value  :: nranks, rank
+            character(kind=c_char), intent(in) :: id128(128)
+        end function tamc_comm_init
+
+        integer(c_int) function tamc_pin_host(ptr, bytes) bind(C, name="tamc_pin_host")
+            import :: c_int, c_int64_t, c_ptr
+            type(c_ptr), value        :: ptr
+            integer(c_int64_t), value :: bytes
+        end function tamc_pin_host
+
+        integer(c_int) function tamc_device_count() bind(C, name="tamc_device_count")
+            import :: c_int
+        end function tamc_device_count
+
+        function tamc_last_error() bind(C, name="tamc_last_error") result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function tamc_last_error
+
+    end interface
+
+    contains
+
+        subroutine tamc_check(ierr, where)
+        !  reference convention on failure is print + error stop (inttau2.f90:171-172, 3dFD.f90:49)
+            integer(c_int),   intent(in) :: ierr
+            character(len=*), intent(in) :: where
+
+            character(kind=c_char), pointer :: cmsg(:)
+            integer :: n
+
+            if(ierr == TAMC_OK)return
+            call c_f_pointer(tamc_last_error(), cmsg, [512])
+            n = 1
+            do while(n < 512 .and. cmsg(n) /= c_null_char)
+                n = n + 1
+            end do
+            print*, 'libtamc error ', ierr, ' in ', where, ': ', cmsg(1:n-1)
+            error stop 1
+        end subroutine tamc_check
+
+end module tamc_mod
