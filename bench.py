@@ -379,7 +379,7 @@ def run_ours(args, cfg, name):
                        "parallelism": f"packets partitioned over {world} GPU(s), one Philox stream per packet, one ncclAllReduce(jmean) per step",
                        "l2": "flushed between timed steps (256 MiB device fill outside the timed events)",
                        "rng": "Philox4x32-10, key=seed, counter=(packet id, event)",
-                       "options": {k: t.get_option(k) for k in ("variant", "block", "ctas_per_sm", "chunk", "scatter_min", "merge")}},
+                       "options": {k: t.get_option(k) for k in ("variant", "block", "ctas_per_sm", "chunk", "scatter_min", "merge", "min_ctas")}},
             "voxel_steps_per_s": vsteps_per_s,
             "voxel_steps_per_packet": res["voxel_steps"] / total_packets,
             "breakdown_ms_per_step": {"kernel": res["kernel_ms"] / args.steps, "allreduce": res["allreduce_ms"] / args.steps,

@@ -106,7 +106,7 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    LaunchCfg cfg{1, 256, 0, 148, 0, 16, -1};
+    LaunchCfg cfg{1, 256, 0, 148, 0, 20, -1, 3};
     int reduce = 1;
 
     // bookkeeping of the last call
@@ -138,6 +138,11 @@ static DevGrid make_grid(const tamc_context *c)
     g.zcur0 = g.zp0 + c->zmax;
     g.cellk0 = (int)((double)c->nzg * (g.zp0 + c->zmax) / (2. * c->zmax)) + 1;
     g.flags = c->flags;
+    g.sc.one_m_g2 = 1. - g.g2;                                         // stokes.f90:48
+    g.sc.one_p_g2 = 1. + g.g2;
+    g.sc.one_m_g = 1. - g.hgg;
+    g.sc.two_g = 2. * g.hgg;
+    g.sc.inv_two_g = (g.hgg != 0.) ? 1. / (2. * g.hgg) : 0.;
     g.rhokap = c->d_rhokap; g.jmean = c->d_jmean; g.faces = c->d_faces;
     return g;
 }
@@ -543,6 +548,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "chunk")) return &h->cfg.chunk;
     if (!strcmp(name, "scatter_min")) return &h->cfg.scatter_min;
     if (!strcmp(name, "merge")) return &h->cfg.merge;
+    if (!strcmp(name, "min_ctas")) return &h->cfg.min_ctas;
     if (!strcmp(name, "reduce")) return &h->reduce;
     return nullptr;
 }
@@ -555,6 +561,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (slot == &h->cfg.variant && (value < 0 || value > 2)) return fail(TAMC_EINVAL, "variant must be 0, 1 or 2");
     if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
     if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");
+    if (slot == &h->cfg.min_ctas && (value < 2 || value > 3)) return fail(TAMC_EINVAL, "min_ctas must be 2 or 3");
     if (slot == &h->cfg.ctas_per_sm && (value < 0 || value > 32)) return fail(TAMC_EINVAL, "ctas_per_sm must be in [0,32]");
     *slot = (int)value;
     return TAMC_OK;

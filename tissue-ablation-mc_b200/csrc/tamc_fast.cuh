@@ -47,7 +47,7 @@ __device__ __forceinline__ void set_direction(FastPhoton &p)
         // one division for the three reciprocals (the products cannot under/overflow for unit vectors
         // whose smallest component is far above 1e-100)
         const double xy = p.nxp * p.nyp;
-        const double r = 1. / (xy * p.nzp);
+        const double r = __drcp_rn(xy * p.nzp);
         p.inz = xy * r;
         const double rz = r * p.nzp;
         p.inx = p.nyp * rz;
@@ -136,7 +136,7 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     }
     double dcell = dwall;
     if (kNeedPos) {
-        const double dpart = rest / rk;                               // inttau2.f90:51 (unused when rk == 0: wall is true)
+        const double dpart = rest * __drcp_rn(rk);                    // inttau2.f90:51 (unused when rk == 0: wall is true)
         dcell = wall ? dwall : dpart;
         tally.add(p.jidx, wall ? taucell : dpart * rk);
     }
@@ -161,15 +161,11 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     return out ? STEP_EXIT : STEP_WALL;
 }
 
-struct ScatterConsts {
-    double one_m_g2, one_p_g2, one_m_g, two_g, inv_two_g;
-};
-
 // stokes.f90:6-153 as a rotation of the direction vector (see the header comment).
 // u1 -> stokes.f90:24/:48, u2 -> :32/:64, u3 -> the next tauint1 draw (inttau2.f90:36).
-__device__ __forceinline__ void scatter_fast(const DevGrid &g, const ScatterConsts &sc, FastPhoton &p, double u1, double u2,
-                                             double u3)
+__device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double u3)
 {
+    const ScatterConsts &sc = g.sc;
     p.taurun = 0.;
     p.tau = -log(u3);
     // the centred position round trip of inttau2.f90:65-67 / :24-26
@@ -188,7 +184,7 @@ __device__ __forceinline__ void scatter_fast(const DevGrid &g, const ScatterCons
         set_direction(p);
         return;
     }
-    const double q = sc.one_m_g2 / (sc.one_m_g + sc.two_g * u1);      // stokes.f90:48
+    const double q = sc.one_m_g2 * __drcp_rn(sc.one_m_g + sc.two_g * u1);   // stokes.f90:48
     double bmu = (sc.one_p_g2 - q * q) * sc.inv_two_g;
     bmu = fmin(1., fmax(-1., bmu));
     if (bmu == 1. || bmu == -1.) return;                               // goto 100, stokes.f90:71-77
@@ -228,6 +224,31 @@ __device__ __forceinline__ int exit_face_fast(const FastPhoton &p, const DevGrid
     if (p.cellk < 1 || p.cellk > g.nzg) return p.nzp > 0. ? 6 : 5;
     return 0;
 }
+
+// Counters kept in shared memory, one set per warp, updated when a packet ends.  Used by the
+// scattering kernel, where packets end rarely (once per tens of events) and registers are scarce.
+struct WarpCounters {
+    unsigned long long *w;      // CNT_N slots of this warp
+    __device__ __forceinline__ void clear()
+    {
+        for (int i = threadIdx.x & 31; i < CNT_N; i += 32) w[i] = 0ull;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void death(int f, int nsteps, int nscatt, bool err)
+    {
+        atomicAdd(w + CNT_PACKETS, 1ull);
+        atomicAdd(w + CNT_STEPS, (unsigned long long)nsteps);
+        atomicAdd(w + CNT_SCATTERS, (unsigned long long)nscatt);
+        atomicAdd(w + (f == 0 ? CNT_ABSORBED : CNT_EXIT0 + f - 1), 1ull);
+        if (err) atomicAdd(w + CNT_ERRORS, 1ull);
+    }
+    __device__ __forceinline__ void commit(unsigned long long *g) const
+    {
+        __syncwarp();
+        const int i = threadIdx.x & 31;
+        if (i < 12 && w[i]) atomicAdd(g + i, w[i]);
+    }
+};
 
 // Tally policies on 32-bit voxel indices (tamc_init bounds the grid so they fit).
 struct DirectTally32 {

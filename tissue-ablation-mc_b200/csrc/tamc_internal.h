@@ -11,14 +11,15 @@ namespace tamc {
 struct LaunchCfg {
     int variant;        // 0 = thread-per-packet grid-stride, 1 = persistent warps (default), 2 = variant 0 on the exact arithmetic
     int block;          // threads per CTA
-    int ctas_per_sm;    // resident CTAs per SM the grid is sized for
+    int ctas_per_sm;    // resident CTAs per SM the grid is sized for (0 = ask the occupancy API)
     int num_sms;
     int chunk;          // persistent: packet ids a warp claims per atomic (0 = auto)
     int scatter_min;    // persistent: run the scattering phase once this many lanes wait for it
     int merge;          // merge consecutive same-voxel deposits in registers (-1 = auto: on with TAMC_SCATTER)
+    int min_ctas;       // scattering kernel: the __launch_bounds__ min-CTAs-per-SM build to use (2 or 3)
 };
 
-// production transport (Philox).  d_rec may be null; when non-null variant 0 is used.
+// production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.
 cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
                              unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches);
 

@@ -13,21 +13,12 @@
 //              (device-side cross-check of the production arithmetic in tamc_fast.cuh).
 // The path is a random walk over an fp64 grid with fp64 atomics: no dense contraction, no tensor
 // cores.
+#include <type_traits>
+
 #include "tamc_fast.cuh"
 #include "tamc_internal.h"
 
 namespace tamc {
-
-__device__ __forceinline__ ScatterConsts scatter_consts(const DevGrid &g)
-{
-    ScatterConsts sc;
-    sc.one_m_g2 = 1. - g.g2;
-    sc.one_p_g2 = 1. + g.g2;
-    sc.one_m_g = 1. - g.hgg;
-    sc.two_g = 2. * g.hgg;
-    sc.inv_two_g = (g.hgg != 0.) ? 1. / (2. * g.hgg) : 0.;
-    return sc;
-}
 
 // Adds the packet's deposit sum for the records path.
 template <class Base>
@@ -49,7 +40,6 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
     const double *xf, *yf, *zf;
     stage_faces(g, s_faces, xf, yf, zf);
     const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
-    const ScatterConsts sc = scatter_consts(g);
     const LaunchConsts lc{g.zcur0, g.cellk0};
 
     Counters c;
@@ -77,7 +67,7 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
             if (!scatter_on) break;                               // mcpolar.f90:166-169 stub
             rng.block(u);
             if (u[0] < g.albedo) {
-                scatter_fast(g, sc, p, u[1], u[2], u[3]);
+                scatter_fast(g, p, u[1], u[2], u[3]);
                 ++nscatt;
                 ndraws += 4;
             } else {
@@ -142,8 +132,10 @@ struct WarpReservoir {
 
 // kScatter = false is the shipped regime (mcpolar.f90:166-169 stub): no scattering phase, no azimuth,
 // no position after the final partial step -- the compiler drops that state and its registers.
-template <class Tally, bool kScatter>
-__global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
+// With scattering the per-packet state is large; the counters then live in shared memory (one set per
+// warp, touched only when a packet ends) and kMinCtas selects the register budget the kernel is built for.
+template <class Tally, bool kScatter, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                               int chunk, int scatter_min,
                                                               unsigned long long *__restrict__ cnt)
 {
@@ -152,14 +144,16 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
     stage_faces(g, s_faces, xf, yf, zf);
     const int nfaces = g.nxg + g.nyg + g.nzg + 3;
     WarpReservoir &R = reinterpret_cast<WarpReservoir *>(s_faces + nfaces)[threadIdx.x >> 5];
+    unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(
+        reinterpret_cast<WarpReservoir *>(s_faces + nfaces) + (blockDim.x >> 5)) + (threadIdx.x >> 5) * CNT_N;
 
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const ScatterConsts sc = scatter_consts(g);
     const LaunchConsts lc{g.zcur0, g.cellk0};
 
-    Counters c;
+    typename std::conditional<kScatter, WarpCounters, Counters>::type c;
+    if constexpr (kScatter) c.w = s_cnt;
     c.clear();
     Tally tally;
     tally.jm = g.jmean;
@@ -236,14 +230,12 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
             if (mode == LANE_INTERACT) {
                 rng.block(u);
                 if (u[0] < g.albedo) {                    // draw < albedo ? stokes : absorbed
-                    scatter_fast(g, sc, p, u[1], u[2], u[3]);
+                    scatter_fast(g, p, u[1], u[2], u[3]);
                     ++nscatt;
                     mode = LANE_WALK;
                 } else {
                     tally.flush();
-                    c.steps += (unsigned long long)steps;
-                    c.scatters += (unsigned long long)nscatt;
-                    c.fate(0);
+                    c.death(0, steps, nscatt, false);
                     mode = LANE_IDLE;
                 }
             }
@@ -258,10 +250,7 @@ __global__ void __launch_bounds__(256) k_transport_persistent(const DevGrid g, l
                 mode = LANE_INTERACT;
             } else if (r != STEP_WALL || steps >= kMaxStepsPerPacket) {
                 tally.flush();
-                c.steps += (unsigned long long)steps;
-                c.scatters += (unsigned long long)nscatt;
-                c.errors += (r == STEP_WALL);
-                c.fate(r == STEP_EXIT ? exit_face_fast(p, g) : 0);
+                c.death(r == STEP_EXIT ? exit_face_fast(p, g) : 0, steps, nscatt, r == STEP_WALL);
                 mode = LANE_IDLE;
             }
         }
@@ -373,7 +362,7 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
     // persistent warps: faces + one reservoir per warp in shared memory
-    const size_t psmem = smem + (size_t)(cfg.block / 32) * sizeof(WarpReservoir);
+    const size_t psmem = smem + (size_t)(cfg.block / 32) * (sizeof(WarpReservoir) + CNT_N * sizeof(unsigned long long));
     int chunk = cfg.chunk;
     if (chunk <= 0) {
         // aim for >= 8 chunks per resident warp so the tail is short, within [32, 1024] ids per claim
@@ -383,11 +372,15 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n
         chunk = (int)(c / 32 * 32);
     }
     if (g.flags & TAMC_SCATTER) {
-        if (merge) return launch_sized(k_transport_persistent<MergeTally32, true>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
-        return launch_sized(k_transport_persistent<DirectTally32, true>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        if (cfg.min_ctas >= 3) {
+            if (merge) return launch_sized(k_transport_persistent<MergeTally32, true, 3>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+            return launch_sized(k_transport_persistent<DirectTally32, true, 3>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        }
+        if (merge) return launch_sized(k_transport_persistent<MergeTally32, true, 2>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        return launch_sized(k_transport_persistent<DirectTally32, true, 2>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
     }
-    if (merge) return launch_sized(k_transport_persistent<MergeTally32, false>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
-    return launch_sized(k_transport_persistent<DirectTally32, false>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    if (merge) return launch_sized(k_transport_persistent<MergeTally32, false, 4>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    return launch_sized(k_transport_persistent<DirectTally32, false, 4>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
 }
 
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,

@@ -31,6 +31,11 @@ constexpr int kMaxStepsPerPacket = 1 << 26;
 
 enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_WORK = 12, CNT_N = 16 };
 
+// Constants of the Henyey-Greenstein draw (stokes.f90:48), formed once on the host.
+struct ScatterConsts {
+    double one_m_g2, one_p_g2, one_m_g, two_g, inv_two_g;
+};
+
 struct DevGrid {
     int nxg, nyg, nzg;
     int sx;               // rhokap stride in j: nxg+2
@@ -43,6 +48,7 @@ struct DevGrid {
     double zcur0;         // zp0 + zmax: every packet starts at this height (inttau2.f90:26)
     int cellk0;           // int(nzg*(zp0+zmax)/(2.*zmax))+1, sourceph.f90:47
     int flags;
+    ScatterConsts sc;
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
     const double *faces;  // xface(1:nxg+1) | yface(1:nyg+1) | zface(1:nzg+1)
@@ -344,6 +350,13 @@ struct Counters {
 #pragma unroll
             for (int i = 0; i < 6; ++i) exits[i] += (f == i + 1);
         }
+    }
+    __device__ __forceinline__ void death(int f, int nsteps, int nscatt, bool err)
+    {
+        steps += (unsigned long long)nsteps;
+        scatters += (unsigned long long)nscatt;
+        errors += err;
+        fate(f);
     }
     __device__ __forceinline__ void commit(unsigned long long *g) const
     {
