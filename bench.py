@@ -285,7 +285,6 @@ def run_ours(args, cfg, name):
         t.sync()
     sampler = ClockSampler(gpu_id) if rank == 0 else None
     res = timed_steps(t, stream, packets, args.steps, world, dist, dev, torch)
-    clocks = sampler.stop() if sampler else None
     total_packets = float(packets) * world * args.steps
     value = total_packets / (res["dev_ms"] * 1e-3)
     vsteps_per_s = res["voxel_steps"] / (res["dev_ms"] * 1e-3)
@@ -313,6 +312,7 @@ def run_ours(args, cfg, name):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = total_packets / float(e2e_s.item())
+    clocks = sampler.stop() if sampler else None      # sampled across both timed regions (device-resident + e2e)
     jm_sum = float(jm.sum())
 
     # ---- context numbers (rank 0, single GPU semantics)
