@@ -41,11 +41,12 @@ def _philox_exact(cfg, n, first=0, rhokap=None):
             compare_records(rec, want["records"], rtol=1e-4, scale=scale, flip_fraction=1e-3, p99_rtol=5e-6)
             compare_grids(jm, o.jmean, **gk_fast)
     # both kernel shapes and both tally policies give the same grid and counters
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         for merge in (0, 1):
             for thr in ((32, 1), (0, 16), (64, 32)):
-                if variant != 1 and thr != (32, 1):
+                if variant not in (1, 3) and thr != (32, 1):
                     continue
+                t.set_option("block", 128 if (variant == 3 and thr[1] == 16) else 256)
                 t.set_option("variant", variant)
                 t.set_option("merge", merge)
                 t.set_option("chunk", thr[0])

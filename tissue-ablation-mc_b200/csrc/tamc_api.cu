@@ -558,7 +558,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     int *slot = option_slot(h, name);
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
     if (slot == &h->cfg.block && (value < 32 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be a multiple of 32 in [32,256]");
-    if (slot == &h->cfg.variant && (value < 0 || value > 2)) return fail(TAMC_EINVAL, "variant must be 0, 1 or 2");
+    if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");
     if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
     if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");
     if (slot == &h->cfg.min_ctas && (value < 2 || value > 3)) return fail(TAMC_EINVAL, "min_ctas must be 2 or 3");

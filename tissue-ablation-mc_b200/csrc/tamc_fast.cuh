@@ -163,16 +163,24 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
 
 // stokes.f90:6-153 as a rotation of the direction vector (see the header comment).
 // u1 -> stokes.f90:24/:48, u2 -> :32/:64, u3 -> the next tauint1 draw (inttau2.f90:36).
+__device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2);
+
 __device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double u3)
 {
-    const ScatterConsts &sc = g.sc;
     p.taurun = 0.;
     p.tau = -log(u3);
     // the centred position round trip of inttau2.f90:65-67 / :24-26
     p.xcur = (p.xcur - g.xmax) + g.xmax;
     p.ycur = (p.ycur - g.ymax) + g.ymax;
     p.zcur = (p.zcur - g.zmax) + g.zmax;
+    scatter_dir(g, p, u1, u2);
+}
 
+// The direction part of a scattering event: reads and writes nxp,nyp,nzp, sint,cosp,sinp, the
+// reciprocals and dflags of `p`; position and optical depths are untouched.
+__device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2)
+{
+    const ScatterConsts &sc = g.sc;
     if (g.hgg == 0.0) {                                   // isotropic, stokes.f90:23-38
         const double cost = 2. * u1 - 1.;
         const double s2 = 1. - cost * cost;

@@ -17,6 +17,7 @@
 
 #include "tamc_fast.cuh"
 #include "tamc_internal.h"
+#include "tamc_pool.cuh"
 
 namespace tamc {
 
@@ -360,6 +361,20 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n
     if (cfg.variant == 0) {
         if (merge) return launch_sized(k_transport_simple<MergeTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
+    }
+    if (cfg.variant == 3 && (g.flags & TAMC_SCATTER)) {
+        // work-queue regrouping: faces + one 64-packet pool per warp in shared memory
+        int chunk = cfg.chunk > 0 ? cfg.chunk : 64;
+        if (cfg.block <= 128) {
+            LaunchCfg c2 = cfg;
+            c2.block = 128;
+            const size_t qsmem = smem + 4 * sizeof(WarpPool);
+            return launch_sized(k_transport_pool<128, 5>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        }
+        LaunchCfg c2 = cfg;
+        c2.block = 256;
+        const size_t qsmem = smem + 8 * sizeof(WarpPool);
+        return launch_sized(k_transport_pool<256, 2>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
     }
     // persistent warps: faces + one reservoir per warp in shared memory
     const size_t psmem = smem + (size_t)(cfg.block / 32) * (sizeof(WarpReservoir) + CNT_N * sizeof(unsigned long long));
