@@ -141,7 +141,9 @@ double *tamc_rhokap_device(tamc_handle h); /* device opacity grid with halo */
 /* Page-lock a caller-owned host array once so uploads/downloads run at PCIe speed. */
 int tamc_pin_host(void *ptr, uint64_t bytes);
 int tamc_unpin_host(void *ptr);
-/* Tuning knobs: "variant" (transport kernel), "block", "ctas_per_sm", "reduce" (0 = skip). */
+/* Tuning knobs: "variant" (0 thread-per-packet, 1 persistent warps, 2 exact arithmetic, 3 = default:
+ * persistent warps + work-queue regrouping when scattering), "block" (0 = auto), "ctas_per_sm",
+ * "chunk", "scatter_min", "merge", "min_ctas", "reduce" (0 = skip the all-reduce). */
 int tamc_set_option(tamc_handle h, const char *name, int64_t value);
 int64_t tamc_get_option(tamc_handle h, const char *name);
 /* Access-pattern-only kernel: the tally/grid address stream of `nphotons` straight-down packets

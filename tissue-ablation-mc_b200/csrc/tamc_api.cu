@@ -106,7 +106,7 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    LaunchCfg cfg{1, 256, 0, 148, 0, 20, -1, 3};
+    LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3};
     int reduce = 1;
 
     // bookkeeping of the last call
@@ -557,7 +557,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
 {
     int *slot = option_slot(h, name);
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
-    if (slot == &h->cfg.block && (value < 32 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be a multiple of 32 in [32,256]");
+    if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");
     if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
     if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");

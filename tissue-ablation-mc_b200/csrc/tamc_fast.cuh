@@ -22,6 +22,8 @@
 
 namespace tamc {
 
+constexpr double kInvPi = 0.31830988618379067154;   // 1/pi (the true pi: only converts radians for sincospi)
+
 struct FastPhoton {
     double xcur, ycur, zcur;      // shifted frame, inttau2.f90:24-26
     double nxp, nyp, nzp;         // direction cosines (nzp = cost)
@@ -78,7 +80,7 @@ __device__ __forceinline__ Launched launch_fast(const DevGrid &g, const double u
     const double r = u[0] * g.spot_r2;
     const double theta = u[1] * kTWOPI;
     double s, c;
-    sincos(theta, &s, &c);
+    sincospi(theta * kInvPi, &s, &c);
     const double sr = sqrt(r);
     L.xcur = sr * c + g.xmax;
     L.ycur = sr * s + g.ymax;
@@ -89,7 +91,7 @@ __device__ __forceinline__ Launched launch_fast(const DevGrid &g, const double u
     L.jidx = (celli - 1) + g.nxg * ((cellj - 1) + g.nyg * (g.cellk0 - 1));
     L.cosp = 1.;
     L.sinp = 0.;
-    if (need_azimuth) sincos(kTWOPI * u[2], &L.sinp, &L.cosp);   // phi is first used by the first scattering
+    if (need_azimuth) sincospi(kTWOPI * u[2] * kInvPi, &L.sinp, &L.cosp);   // phi is first used by the first scattering
     L.tau = -log(u[3]);
     return L;
 }
@@ -105,6 +107,11 @@ __device__ __forceinline__ void adopt(const DevGrid &g, const LaunchConsts &lc, 
     p.celli = L.cells & 0xffff; p.cellj = L.cells >> 16; p.cellk = lc.cellk0;
     p.ridx = L.ridx;
     p.jidx = L.jidx;
+}
+
+__device__ __forceinline__ double flip_sign(double v, int neg)
+{
+    return __hiloint2double(__double2hiint(v) ^ (neg << 31), __double2loint(v));
 }
 
 // One voxel-step, inttau2.f90:37-63, written without divergent branches: the wall-crossing step
@@ -146,9 +153,12 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     const bool hy = wall & !hz & (dwall == dy);
     const bool hx = wall & !hz & !hy;
     const double xn = p.xcur + p.nxp * dcell, yn = p.ycur + p.nyp * dcell, zn = p.zcur + p.nzp * dcell;
-    p.xcur = hx ? (negx ? fx - g.delta : fx + g.delta) : xn;          // inttau2.f90:140-170
-    p.ycur = hy ? (negy ? fy - g.delta : fy + g.delta) : yn;
-    p.zcur = hz ? (negz ? fz - g.delta : fz + g.delta) : zn;
+    // face -+ delta (inttau2.f90:140-170): the sign of delta follows the direction, flipped in the sign bit
+    const double sxd = flip_sign(g.delta, negx), syd = flip_sign(g.delta, negy), szd = flip_sign(g.delta, negz);
+    const double xs = fx + sxd, ys = fy + syd, zs = fz + szd;
+    p.xcur = hx ? xs : xn;
+    p.ycur = hy ? ys : yn;
+    p.zcur = hz ? zs : zn;
     const int sx = hx ? 1 - 2 * negx : 0, sy = hy ? 1 - 2 * negy : 0, sz = hz ? 1 - 2 * negz : 0;
     p.celli += sx;
     p.cellj += sy;
@@ -185,7 +195,7 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
         const double cost = 2. * u1 - 1.;
         const double s2 = 1. - cost * cost;
         p.sint = (s2 <= 0.) ? 0. : sqrt(s2);
-        sincos(kTWOPI * u2, &p.sinp, &p.cosp);
+        sincospi(kTWOPI * u2 * kInvPi, &p.sinp, &p.cosp);
         p.nxp = p.sint * p.cosp;
         p.nyp = p.sint * p.sinp;
         p.nzp = cost;
@@ -203,7 +213,7 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
     const double ri1 = kTWOPI * u2;
     const bool upper = ri1 > kPI;
     double si, ci;
-    sincos(upper ? kTWOPI - ri1 : ri1, &si, &ci);
+    sincospi((upper ? kTWOPI - ri1 : ri1) * kInvPi, &si, &ci);   // sin/cos of the angle, argument reduced exactly
     si = upper ? -si : si;
 
     const double costp = p.nzp, sintp = p.sint;

@@ -337,10 +337,13 @@ static cudaError_t launch_sized(K kernel, const LaunchCfg &cfg, size_t smem, lon
     return cudaGetLastError();
 }
 
-cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
+cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long long n, uint64_t seed, uint64_t first_id,
                              unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches)
 {
     if (n <= 0) return cudaSuccess;
+    LaunchCfg cfg = cfg_in;
+    const bool pool = cfg.variant == 3 && (g.flags & TAMC_SCATTER) && !d_rec;
+    if (cfg.block <= 0) cfg.block = pool ? 128 : 256;       // auto
     const bool merge = cfg.merge < 0 ? (g.flags & TAMC_SCATTER) != 0 : cfg.merge != 0;
     const size_t smem = faces_bytes(g);
     if (launches) *launches += 1;
@@ -362,10 +365,10 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n
         if (merge) return launch_sized(k_transport_simple<MergeTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
-    if (cfg.variant == 3 && (g.flags & TAMC_SCATTER)) {
+    if (pool) {
         // work-queue regrouping: faces + one 64-packet pool per warp in shared memory
         int chunk = cfg.chunk > 0 ? cfg.chunk : 64;
-        if (cfg.block <= 128) {
+        if (cfg.block <= 128) {   // 0 = auto: 128 threads, 5 CTAs per SM
             LaunchCfg c2 = cfg;
             c2.block = 128;
             const size_t qsmem = smem + 4 * sizeof(WarpPool);
@@ -402,7 +405,9 @@ cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, ui
                          cudaStream_t s)
 {
     const float disk_r_vox = (float)(sqrt(g.spot_r2) * g.inv_dx);
-    return launch_sized(k_probe, cfg, 0, n, s, g, n, seed, disk_r_vox, d_cnt);
+    LaunchCfg c2 = cfg;
+    if (c2.block <= 0) c2.block = 256;
+    return launch_sized(k_probe, c2, 0, n, s, g, n, seed, disk_r_vox, d_cnt);
 }
 
 cudaError_t launch_fill(double *p, size_t n, double v, int num_sms, cudaStream_t s)
