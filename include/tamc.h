@@ -152,6 +152,50 @@ int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *m
 /* Writes >= bytes of device memory to evict L2 between timed steps. */
 int tamc_flush_l2(tamc_handle h, uint64_t bytes);
 
+/* ---- next to the hot path: the heat / ablation step on the device ------- */
+
+/* The run-time parameters the Heat module takes from res/input.params (mcpolar.f90:85-94). */
+typedef struct {
+    double power;             /* W */
+    double energyPerPixel;    /* mJ */
+    double total_time;        /* s (overridden for gaussian pulses, mcpolar.f90:134-137) */
+    double repetitionRate_1;  /* Hz */
+    double ablateTemp;        /* C */
+    int32_t loops;            /* heat sub-steps per MC call */
+    int32_t pulsesToDo;
+    int32_t pulsetype;        /* 0 tophat, 1 gaussian, 2 triangular (3dFD.f90:294-307) */
+    int32_t pad_;
+} tamc_heat_params;
+
+enum {   /* tamc_heat_array ids; arrays are Fortran column-major fp64 as the reference allocates them */
+    TAMC_HEAT_TEMP = 0, TAMC_HEAT_RHOKAP, TAMC_HEAT_KAPPA, TAMC_HEAT_DENSITY, TAMC_HEAT_HEATCAP, TAMC_HEAT_COEFF,
+    TAMC_HEAT_ALPHA,          /* the seven above: (0:n+1)^3 */
+    TAMC_HEAT_WATER, TAMC_HEAT_Q, TAMC_HEAT_TISSUE,   /* n^3 */
+    TAMC_HEAT_THRESTIME,      /* (n,n,n,3) */
+    TAMC_HEAT_JMEAN           /* n^3: the resident tally (scaled by mcpolar.f90:174 once tamc_heat_step ran) */
+};
+enum {   /* tamc_heat_scalar ids */
+    TAMC_HEAT_S_DELT = 0, TAMC_HEAT_S_TIME, TAMC_HEAT_S_TOTAL_TIME, TAMC_HEAT_S_PULSELENGTH, TAMC_HEAT_S_REALPULSELENGTH,
+    TAMC_HEAT_S_LASERON, TAMC_HEAT_S_PULSECOUNT, TAMC_HEAT_S_REPETITIONCOUNT, TAMC_HEAT_S_LASER_FLAG, TAMC_HEAT_S_QVAPOR,
+    TAMC_HEAT_S_PWR, TAMC_HEAT_S_COUNTER
+};
+
+/* initThermalCoeff (3dFD.f90:233-309) + the driver's temperature boundary set-up and total_time
+ * override (mcpolar.f90:65-71,123-140), on device arrays.  Needs nxg = nyg = nzg and a resident
+ * rhokap (tamc_set_optics).  delt receives the time step (may be NULL). */
+int tamc_heat_init(tamc_handle h, const tamc_heat_params *p, double *delt);
+/* mcpolar.f90:174-182 on the resident arrays: scale the tally left by the last MC call, heat_sim_3D
+ * (3dFD.f90:21-230, single-rank semantics), Arrhenius (:424-466), setupThermalCoeff (:312-361, which
+ * rewrites the resident rhokap for the next MC call). */
+int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc);
+/* The whole `do while(time <= total_time)` loop (mcpolar.f90:148-186): MC call, all-reduce, heat step,
+ * property update, with nothing crossing PCIe.  max_iterations < 0 = run to total_time. */
+int tamc_coupled_loop(tamc_handle h, int64_t nphotons, int64_t seed, int64_t max_iterations, int64_t *iterations_done,
+                      int64_t *packets_done);
+/* Download (upload = 0) or upload (upload = 1) one of the heat arrays / read one of its scalars. */
+int tamc_heat_array(tamc_handle h, int which, double *host, int upload);
+int tamc_heat_scalar(tamc_handle h, int which, double *out);
+
 const char *tamc_last_error(void);
 int tamc_version(void);
 int tamc_device_count(void);

@@ -55,13 +55,14 @@ def build(fast: bool = False, out_dir: str | None = None) -> str:
     out_dir = out_dir or _HERE
     out = os.path.join(out_dir, name)
     src = os.path.join(_HERE, "tamc_oracle.c")
+    src2 = os.path.join(_HERE, "heat_oracle.c")
     if os.path.exists(out) and os.path.getmtime(out) >= max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "tamc_oracle.h"))
+        os.path.getmtime(src), os.path.getmtime(src2), os.path.getmtime(os.path.join(_HERE, "tamc_oracle.h"))
     ):
         return out
     opt = ["-O3", "-march=native", "-flto"] if fast else ["-O2", "-ffp-contract=off"]
     cmd = ["gcc", "-std=c11", "-D_POSIX_C_SOURCE=200809L", "-fPIC", "-shared", "-pthread", *opt,
-           "-o", out, src, "-lm"]
+           "-o", out, src, src2, "-lm"]
     subprocess.run(cmd, check=True, capture_output=True)
     return out
 
@@ -100,6 +101,23 @@ def _bind(path: str) -> C.CDLL:
     lib.orc_run.restype = i
     lib.orc_run.argtypes = [p, i64, p, p, i64, p, C.POINTER(Stats)]
     lib.orc_run_ranks.restype = i
+    # heat / ablation step (heat_oracle.c)
+    lib.heat_create.restype = p
+    lib.heat_create.argtypes = [i, d, d, d]
+    lib.heat_destroy.argtypes = [p]
+    lib.heat_array.restype = C.POINTER(d)
+    lib.heat_array.argtypes = [p, i]
+    lib.heat_scalar.restype = d
+    lib.heat_scalar.argtypes = [p, i]
+    lib.heat_init.restype = d
+    lib.heat_init.argtypes = [p, d, d, d, i, d, i, i, d]
+    lib.heat_getPwr.restype = d
+    lib.heat_getPwr.argtypes = [p]
+    lib.heat_scale_jmean.restype = d
+    lib.heat_scale_jmean.argtypes = [p, p, d]
+    lib.heat_sim_3d.argtypes = [p, p, i]
+    lib.heat_arrhenius.argtypes = [p]
+    lib.heat_setup_thermal_coeff.argtypes = [p, d]
     lib.orc_run_ranks.argtypes = [i, i, i, i, d, d, d, p, d, d, d, i, i64, p, C.POINTER(Stats), C.POINTER(d)]
     return lib
 
@@ -243,3 +261,63 @@ def run_ranks(nranks, nxg, nyg, nzg, xmax, ymax, zmax, rhokap_halo, albedo, hgg,
                              C.byref(sec))
     return {"jmean": jm.reshape((nxg, nyg, nzg), order="F"), "stats": st.as_dict(), "seconds": sec.value,
             "threads": used}
+
+
+PULSETYPES = {"tophat": 0, "gaussian": 1, "triangular": 2}
+HEAT_ARRAYS = {"temp": (0, True), "rhokap": (1, True), "kappa": (2, True), "density": (3, True), "heatcap": (4, True),
+               "coeff": (5, True), "alpha": (6, True), "watercontent": (7, False), "Q": (8, False), "tissue": (9, False)}
+HEAT_SCALARS = {"delt": 0, "time": 1, "total_time": 2, "pulselength": 3, "realPulseLength": 4, "laserOn": 5,
+                "pulseCount": 6, "repetitionCount": 7, "laser_flag": 8, "QVapor": 9, "volumeVoxel": 10,
+                "pulsesDone": 11, "negative_temp": 12, "massVoxel": 13}
+
+
+class HeatOracle:
+    """The Heat module of 3dFD.f90 for one rank, plus the driver lines around it (mcpolar.f90:123-185)."""
+
+    def __init__(self, n, xmax, ymax, zmax):
+        self.lib = load()
+        self.n = int(n)
+        self.h = self.lib.heat_create(self.n, float(xmax), float(ymax), float(zmax))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.heat_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def init(self, power=70.0, energyPerPixel=400.0, total_time=2.0, loops=1, repetitionRate_1=1e7, pulsesToDo=1,
+             pulsetype="gaussian", kappa=680.0):
+        return self.lib.heat_init(self.h, power, energyPerPixel, total_time, loops, repetitionRate_1, pulsesToDo,
+                                  PULSETYPES[pulsetype], kappa)
+
+    def array(self, name) -> np.ndarray:
+        idx, halo = HEAT_ARRAYS[name]
+        m = self.n + 2 if halo else self.n
+        flat = np.ctypeslib.as_array(self.lib.heat_array(self.h, idx), shape=(m ** 3,))
+        return flat.reshape((m, m, m), order="F")
+
+    def threstime(self) -> np.ndarray:
+        flat = np.ctypeslib.as_array(self.lib.heat_array(self.h, 10), shape=(3 * self.n ** 3,))
+        return flat.reshape((self.n, self.n, self.n, 3), order="F")
+
+    def scalar(self, name) -> float:
+        return self.lib.heat_scalar(self.h, HEAT_SCALARS[name])
+
+    def get_pwr(self) -> float:
+        return self.lib.heat_getPwr(self.h)
+
+    def scale_jmean(self, jmean: np.ndarray, nphotons_total: float) -> float:
+        assert jmean.flags.f_contiguous and jmean.dtype == np.float64
+        return self.lib.heat_scale_jmean(self.h, jmean.ctypes.data, float(nphotons_total))
+
+    def sim_3d(self, jmean: np.ndarray, counter: int):
+        assert jmean.flags.f_contiguous and jmean.dtype == np.float64 and jmean.shape == (self.n,) * 3
+        self.lib.heat_sim_3d(self.h, jmean.ctypes.data, int(counter))
+
+    def arrhenius(self):
+        self.lib.heat_arrhenius(self.h)
+
+    def setup_thermal_coeff(self, ablate_temp: float):
+        self.lib.heat_setup_thermal_coeff(self.h, float(ablate_temp))

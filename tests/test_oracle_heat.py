@@ -1,0 +1,95 @@
+"""The heat / ablation oracle (oracle/heat_oracle.c) against values that follow from the reference's own
+formulas and shipped parameters (res/input.params, 3dFD.f90:249-293) -- SURVEY.md 3.1 quotes the same numbers."""
+import numpy as np
+
+from oracle import oracle as orc
+
+
+def test_init_matches_shipped_parameter_arithmetic():
+    h = orc.HeatOracle(80, 0.03, 0.03, 0.06)
+    delt = h.init()
+    # dx = dy = 2*0.03e-2/82, dz = 2*0.06e-2/82; alpha = kappa/(rho*c) of skin at 75 % water
+    w, prot = 0.75, 0.25
+    rho = 1000.0 / (w + 0.649 * prot)
+    c = 1000.0 * (4.2 * w + 1.09 * prot)
+    kap = rho * (6.28e-4 * w + 1.17e-4 * prot)
+    alpha = kap / (rho * c)
+    dx, dz = 2 * 0.03e-2 / 82, 2 * 0.06e-2 / 82
+    assert delt == 1.0 / (alpha * (2 / dx ** 2 + 1 / dz ** 2)) or abs(delt / (1.0 / (alpha * (2 / dx ** 2 + 1 / dz ** 2))) - 1) < 1e-14
+    assert abs(delt - 1.62798e-4) < 1e-9
+    assert abs(h.scalar("pulselength") - 0.4 * 81 / 70) < 1e-15        # 0.462857 s
+    assert abs(h.scalar("total_time") - 2.17989) < 1e-5                # gaussian override, mcpolar.f90:134-137
+    assert h.scalar("realPulseLength") == h.scalar("total_time")
+    assert int(h.scalar("total_time") / delt) == 13390
+    t = h.array("temp")
+    assert t[5, 5, 0] == 298.0 and t[5, 5, 81] == 298.0 and t[0, 5, 5] == 278.0 and t[0, 0, 0] == 298.0 and t[40, 40, 40] == 278.0
+    assert h.array("kappa")[0, 3, 3] != h.array("kappa")[1, 3, 3]      # air halo vs skin
+    assert h.array("coeff")[0, 1, 1] == 0.0 and h.array("coeff")[1, 1, 1] > 0
+
+
+def test_diffusion_conserves_and_relaxes():
+    # no laser: a hot voxel in the middle spreads out; total enthalpy-like sum changes only through the boundary
+    h = orc.HeatOracle(16, 0.03, 0.03, 0.03)
+    h.init(pulsetype="tophat", power=1.0)
+    t = h.array("temp")
+    t[...] = 300.0
+    t[8, 8, 8] = 340.0
+    jm = np.zeros((16, 16, 16), order="F")
+    before = t[1:-1, 1:-1, 1:-1].sum()
+    for it in range(5):
+        h.sim_3d(jm, it)
+    t = h.array("temp")
+    assert t[8, 8, 8] < 340.0 and t[7, 8, 8] > 300.0 and t[8, 8, 9] > 300.0
+    assert abs(t[1:-1, 1:-1, 1:-1].sum() - before) < 1e-6 * before
+    assert h.scalar("time") == 5 * h.scalar("delt")
+
+
+def test_boiling_sink_and_ablation_rule():
+    n = 12
+    h = orc.HeatOracle(n, 0.03, 0.03, 0.03)
+    h.init(pulsetype="tophat", power=70.0)
+    qv = h.scalar("QVapor")
+    t = h.array("temp")
+    t[1:-1, 1:-1, 1:-1] = 373.0                    # at the boiling point: energy goes into Q, temperature pinned
+    jm = np.full((n, n, n), 1e12, order="F")
+    h.sim_3d(jm, 0)
+    assert np.all(h.array("temp")[2:-2, 2:-2, 2:-2] == 373.0)
+    q = h.array("Q")
+    assert q.max() <= qv and q[5, 5, 5] > 0
+    # water loss lowers the opacity: rhokap = w*510 + 170 with w = 0.75*(1 - Q/QVapor)
+    h.setup_thermal_coeff(500.0)
+    w = h.array("watercontent")
+    assert np.allclose(h.array("rhokap")[1:-1, 1:-1, 1:-1], w * 510.0 + 170.0)
+    # ablation: above ablateTemp -> rhokap 0 and air properties; a voxel whose six neighbours are gone goes too
+    t = h.array("temp")
+    t[1:-1, 1:-1, 1:-1] = 300.0
+    t[4:9, 4:9, 4:9] = 900.0
+    t[6, 6, 6] = 300.0                              # cold kernel fully enclosed by ablated voxels
+    h.setup_thermal_coeff(500.0)
+    rk = h.array("rhokap").copy()
+    # sweep-order quirk (3dFD.f90:347-349): the neighbours ahead of the sweep still hold last call's opacity,
+    # so the enclosed voxel survives this call ...
+    assert rk[6, 6, 6] > 0 and rk[3, 6, 6] > 0
+    rk[6, 6, 6] = 0.0
+    assert np.all(rk[4:9, 4:9, 4:9] == 0.0)
+    # ... and goes in the next one
+    h.setup_thermal_coeff(500.0)
+    assert h.array("rhokap")[6, 6, 6] == 0.0
+    assert h.array("heatcap")[6, 6, 6] == 1.006e3 and h.array("heatcap")[5, 6, 6] == 1.006e3
+
+
+def test_arrhenius_thresholds():
+    n = 6
+    h = orc.HeatOracle(n, 0.03, 0.03, 0.03)
+    h.init(pulsetype="tophat", power=70.0)
+    t = h.array("temp")
+    t[1:-1, 1:-1, 1:-1] = 273.0 + 70.0
+    jm = np.zeros((n, n, n), order="F")
+    h.sim_3d(jm, 0)
+    h.arrhenius()
+    rate = 3.1e98 * np.exp(-6.3e5 / (8.314 * h.array("temp")[3, 3, 3]))
+    assert abs(h.array("tissue")[2, 2, 2] / (h.scalar("delt") * rate) - 1) < 1e-9
+    for _ in range(200):
+        h.arrhenius()
+    th = h.threstime()
+    assert th[2, 2, 2, 0] == h.scalar("time") and h.array("tissue")[2, 2, 2] >= 0.53

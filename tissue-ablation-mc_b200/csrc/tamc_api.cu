@@ -83,36 +83,7 @@ static NcclApi *nccl_api()
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-enum { EV_ZERO0 = 0, EV_K0, EV_K1, EV_AR1, EV_H0, EV_H1, EV_D0, EV_D1, EV_N };
-
-struct tamc_context {
-    int device = 0;
-    int num_sms = 148;
-    int nxg = 0, nyg = 0, nzg = 0;
-    double xmax = 0, ymax = 0, zmax = 0, delta = 0;
-    double spot = 250e-4;               // sourceph.f90:23
-    double albedo = 0, hgg = 0.9, n1 = 1, n2 = 1;
-    int flags = 0;
-    bool optics_set = false;
-
-    size_t n_rhokap = 0, n_jmean = 0;
-    double *d_rhokap = nullptr, *d_jmean = nullptr, *d_faces = nullptr, *d_flush = nullptr;
-    size_t flush_elems = 0;
-    unsigned long long *d_cnt = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[EV_N] = {};
-
-    ncclComm_t comm = nullptr;
-    int nranks = 1, rank = 0;
-    int64_t cursor = 0;
-
-    LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3};
-    int reduce = 1;
-
-    // bookkeeping of the last call
-    int64_t last_launches = 0;
-    bool timed_reduce = false, timed_h2d = false, timed_d2h = false, ran = false;
-};
+#include "tamc_context.h"
 
 static int check(tamc_handle h)
 {
@@ -146,6 +117,10 @@ static DevGrid make_grid(const tamc_context *c)
     g.rhokap = c->d_rhokap; g.jmean = c->d_jmean; g.faces = c->d_faces;
     return g;
 }
+
+int tamc_fail_(int code, const std::string &msg) { return fail(code, msg); }
+int tamc_check_(tamc_handle h) { return check(h); }
+DevGrid tamc_make_grid_(const tamc_context *c) { return make_grid(c); }
 
 static bool host_is_pinned(const void *p)
 {
@@ -237,6 +212,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
+    tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_cnt); cudaFree(h->d_flush);
     for (int i = 0; i < EV_N; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);

@@ -1,0 +1,53 @@
+// tamc_context.h -- the state behind a tamc_handle, shared by the C-ABI translation units.
+#pragma once
+
+#include <nccl.h>
+
+#include <cstdint>
+#include <string>
+
+#include "tamc_internal.h"
+
+struct tamc_heat;   // device-resident heat / ablation state (tamc_heat.cu)
+
+enum { EV_ZERO0 = 0, EV_K0, EV_K1, EV_AR1, EV_H0, EV_H1, EV_D0, EV_D1, EV_N };
+
+struct tamc_context {
+    // (members are documented where they are used in tamc_api.cu)
+    int device = 0;
+    int num_sms = 148;
+    int nxg = 0, nyg = 0, nzg = 0;
+    double xmax = 0, ymax = 0, zmax = 0, delta = 0;
+    double spot = 250e-4;               // sourceph.f90:23
+    double albedo = 0, hgg = 0.9, n1 = 1, n2 = 1;
+    int flags = 0;
+    bool optics_set = false;
+
+    size_t n_rhokap = 0, n_jmean = 0;
+    double *d_rhokap = nullptr, *d_jmean = nullptr, *d_faces = nullptr, *d_flush = nullptr;
+    size_t flush_elems = 0;
+    unsigned long long *d_cnt = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_N] = {};
+
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    int64_t cursor = 0;
+
+    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3};
+    int reduce = 1;
+
+    tamc_heat *heat = nullptr;
+
+    // bookkeeping of the last call
+    int64_t last_launches = 0;
+    bool timed_reduce = false, timed_h2d = false, timed_d2h = false, ran = false;
+};
+
+
+// helpers defined in tamc_api.cu
+int tamc_fail_(int code, const std::string &msg);
+int tamc_check_(tamc_handle h);
+tamc::DevGrid tamc_make_grid_(const tamc_context *c);
+// defined in tamc_heat.cu
+void tamc_heat_release_(tamc_context *c);

@@ -45,6 +45,21 @@ class Stats(C.Structure):
         return d
 
 
+class HeatParams(C.Structure):
+    _fields_ = [
+        ("power", C.c_double), ("energyPerPixel", C.c_double), ("total_time", C.c_double),
+        ("repetitionRate_1", C.c_double), ("ablateTemp", C.c_double),
+        ("loops", C.c_int32), ("pulsesToDo", C.c_int32), ("pulsetype", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+PULSETYPES = {"tophat": 0, "gaussian": 1, "triangular": 2}
+HEAT_ARRAYS = {"temp": 0, "rhokap": 1, "kappa": 2, "density": 3, "heatcap": 4, "coeff": 5, "alpha": 6,
+               "watercontent": 7, "Q": 8, "tissue": 9, "threstime": 10, "jmean": 11}
+HEAT_SCALARS = {"delt": 0, "time": 1, "total_time": 2, "pulselength": 3, "realPulseLength": 4, "laserOn": 5,
+                "pulseCount": 6, "repetitionCount": 7, "laser_flag": 8, "QVapor": 9, "pwr": 10, "counter": 11}
+
+
 def lib_path() -> str:
     return os.path.join(_PKG, "libtamc.so")
 
@@ -87,6 +102,11 @@ def lib() -> C.CDLL:
         "tamc_get_option": (i64, [p, C.c_char_p]),
         "tamc_roofline_probe": (i, [p, i64, i64, C.POINTER(d), C.POINTER(i64)]),
         "tamc_flush_l2": (i, [p, C.c_uint64]),
+        "tamc_heat_init": (i, [p, C.POINTER(HeatParams), C.POINTER(d)]),
+        "tamc_heat_step": (i, [p, i64]),
+        "tamc_coupled_loop": (i, [p, i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]),
+        "tamc_heat_array": (i, [p, i, p, i]),
+        "tamc_heat_scalar": (i, [p, i, C.POINTER(d)]),
         "tamc_last_error": (C.c_char_p, []),
         "tamc_version": (i, []),
         "tamc_device_count": (i, []),
@@ -105,6 +125,7 @@ EXPORTS = [
     "tamc_comm_unique_id", "tamc_comm_init", "tamc_stream", "tamc_jmean_device", "tamc_rhokap_device",
     "tamc_pin_host", "tamc_unpin_host", "tamc_set_option", "tamc_get_option", "tamc_roofline_probe",
     "tamc_flush_l2", "tamc_last_error", "tamc_version", "tamc_device_count",
+    "tamc_heat_init", "tamc_heat_step", "tamc_coupled_loop", "tamc_heat_array", "tamc_heat_scalar",
 ]
 
 
@@ -245,6 +266,44 @@ class MCTransport:
         _ck(self.L.tamc_run_records(self.h, int(nphotons), int(seed), int(first_packet_id), rec.ctypes.data,
                                     jm.ctypes.data))
         return rec, jm
+
+    # -- heat / ablation step on the device (3dFD.f90) -----------------------------------------
+    def heat_init(self, power=70.0, energyPerPixel=400.0, total_time=2.0, loops=1, repetitionRate_1=1e7,
+                  pulsesToDo=1, pulsetype="gaussian", ablateTemp=500.0) -> float:
+        """initThermalCoeff + the driver's temperature set-up; returns delt."""
+        prm = HeatParams(power, energyPerPixel, total_time, repetitionRate_1, ablateTemp, loops, pulsesToDo,
+                         PULSETYPES[pulsetype], 0)
+        delt = C.c_double(0)
+        _ck(self.L.tamc_heat_init(self.h, C.byref(prm), C.byref(delt)))
+        return delt.value
+
+    def heat_step(self, nphotons_times_numproc: int):
+        _ck(self.L.tamc_heat_step(self.h, int(nphotons_times_numproc)))
+
+    def coupled_loop(self, nphotons: int, seed: int, max_iterations: int = -1):
+        it, pk = C.c_int64(0), C.c_int64(0)
+        _ck(self.L.tamc_coupled_loop(self.h, int(nphotons), int(seed), int(max_iterations), C.byref(it), C.byref(pk)))
+        return it.value, pk.value
+
+    def heat_array(self, name: str) -> np.ndarray:
+        n = self.nxg
+        if name == "threstime":
+            out = np.zeros((n, n, n, 3), dtype=np.float64, order="F")
+        elif name in ("watercontent", "Q", "tissue", "jmean"):
+            out = np.zeros((n, n, n), dtype=np.float64, order="F")
+        else:
+            out = np.zeros((n + 2, n + 2, n + 2), dtype=np.float64, order="F")
+        _ck(self.L.tamc_heat_array(self.h, HEAT_ARRAYS[name], out.ctypes.data, 0))
+        return out
+
+    def heat_upload(self, name: str, a: np.ndarray):
+        a = np.asfortranarray(a, dtype=np.float64)
+        _ck(self.L.tamc_heat_array(self.h, HEAT_ARRAYS[name], a.ctypes.data, 1))
+
+    def heat_scalar(self, name: str) -> float:
+        v = C.c_double(0)
+        _ck(self.L.tamc_heat_scalar(self.h, HEAT_SCALARS[name], C.byref(v)))
+        return v.value
 
     # -- multi-GPU ----------------------------------------------------------------------------
     def comm_init(self, nranks, rank, unique_id: bytes):
