@@ -172,7 +172,7 @@ enum {   /* tamc_heat_array ids; arrays are Fortran column-major fp64 as the ref
     TAMC_HEAT_ALPHA,          /* the seven above: (0:n+1)^3 */
     TAMC_HEAT_WATER, TAMC_HEAT_Q, TAMC_HEAT_TISSUE,   /* n^3 */
     TAMC_HEAT_THRESTIME,      /* (n,n,n,3) */
-    TAMC_HEAT_JMEAN           /* n^3: the resident tally (scaled by mcpolar.f90:174 once tamc_heat_step ran) */
+    TAMC_HEAT_JMEAN           /* n^3: the resident, unscaled tally of the last MC call */
 };
 enum {   /* tamc_heat_scalar ids */
     TAMC_HEAT_S_DELT = 0, TAMC_HEAT_S_TIME, TAMC_HEAT_S_TOTAL_TIME, TAMC_HEAT_S_PULSELENGTH, TAMC_HEAT_S_REALPULSELENGTH,
@@ -184,7 +184,7 @@ enum {   /* tamc_heat_scalar ids */
  * override (mcpolar.f90:65-71,123-140), on device arrays.  Needs nxg = nyg = nzg and a resident
  * rhokap (tamc_set_optics).  delt receives the time step (may be NULL). */
 int tamc_heat_init(tamc_handle h, const tamc_heat_params *p, double *delt);
-/* mcpolar.f90:174-182 on the resident arrays: scale the tally left by the last MC call, heat_sim_3D
+/* mcpolar.f90:174-182 on the resident arrays: the tally left by the last MC call, scaled on the fly, heat_sim_3D
  * (3dFD.f90:21-230, single-rank semantics), Arrhenius (:424-466), setupThermalCoeff (:312-361, which
  * rewrites the resident rhokap for the next MC call). */
 int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc);

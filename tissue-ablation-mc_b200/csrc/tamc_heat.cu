@@ -4,7 +4,7 @@
 // ablation loop of /root/reference/src/mcpolar.f90:148-186 runs with jmean, temp and rhokap resident
 // in HBM: no PCIe copy per MC call.
 //
-//   k_scale            mcpolar.f90:174        jmeanGLOBAL *= (getPwr()/81)/(nphotons*numproc*Vvoxel)
+//   (in k_heat_step)   mcpolar.f90:174        jmeanGLOBAL *= (getPwr()/81)/(nphotons*numproc*Vvoxel)
 //   k_heat_step        3dFD.f90:113-186       FTCS 7-point stencil with variable kappa/rho/c, boiling sink
 //   k_arrhenius        3dFD.f90:424-466
 //   k_water .. k_air   3dFD.f90:312-361       setupThermalCoeff, incl. its sweep-order "six neighbours
@@ -40,7 +40,7 @@ struct tamc_heat {
     // host-side scalars, advanced exactly as the reference does
     double pulseCount = 0, repetitionCount = 0, time = 0, laserOn = 1, total_time = 0, repetitionRate_1 = 0, energyPerPixel = 0;
     double Power = 0, pulselength = 0, delt = 0, realPulseLength = 0;
-    double dx = 0, dy = 0, dz = 0, massVoxel = 0, volumeVoxel = 0, QVapor = 0, ablateTemp = 0;
+    double dx = 0, dy = 0, dz = 0, massVoxel = 0, volumeVoxel = 0, QVapor = 0, ablateTemp = 0, jscale = 0;
     bool laser_flag = true, pulseFlag = false;
     int loops = 1, pulsesToDo = 1, pulsesDone = 0, pulsetype = 1, counter = 0;
     // device arrays
@@ -73,19 +73,14 @@ __device__ __forceinline__ bool voxel_of_thread(int n, int &i, int &j, int &k)
     return true;
 }
 
-__global__ void k_scale(double *__restrict__ jm, size_t n, double f)
-{
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) jm[t] = jm[t] * f;
-}
-
 // 3dFD.f90:113-186, one sub-step: reads t0, writes tn and Q
 __global__ void __launch_bounds__(256) k_heat_step(int n, const double *__restrict__ t0, double *__restrict__ tn,
                                                    const double *__restrict__ kappa, const double *__restrict__ density,
                                                    const double *__restrict__ heatcap, const double *__restrict__ coeff,
                                                    const double *__restrict__ jmean, double *__restrict__ Q,
                                                    double dx, double dy, double dz, double delt, double laserOn,
-                                                   double volumeVoxel, double massVoxel, double QVapor, int *__restrict__ flags)
+                                                   double volumeVoxel, double massVoxel, double QVapor, double jscale,
+                                                   int *__restrict__ flags)
 {
     int i, j, k;
     if (!voxel_of_thread(n, i, j, k)) return;
@@ -106,7 +101,7 @@ __global__ void __launch_bounds__(256) k_heat_step(int n, const double *__restri
     const double u_yy = second_derivative(sy, dy);
     const double u_xx = second_derivative(sx, dx);
 
-    const double jv = jmean[qi];
+    const double jv = jmean[qi] * jscale;          // mcpolar.f90:174 applied on the fly: the resident tally stays unscaled
     const double tempIncrease = delt * (u_xx + u_yy + u_zz);
     const double energyIncrease = laserOn * jv * delt * volumeVoxel + hc * massVoxel * tempIncrease;
     const double q = Q[qi];
@@ -365,17 +360,18 @@ extern "C" int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc)
     cudaStream_t st = h->stream;
     const int gi = blocks_for(s->ni);
 
-    if (s->laser_flag) {                                                                 // :149,174
+    // mcpolar.f90:149,174: jmeanGLOBAL is rescaled only while the laser is on; afterwards the array keeps its last
+    // scaled values (and laserOn = 0 multiplies them away).  The factor is applied inside the stencil kernel.
+    if (s->laser_flag) {
         if (nphotons_times_numproc <= 0) return tamc_fail_(TAMC_EINVAL, "tamc_heat_step: packet count must be positive");
-        const double f = (get_pwr(s) / 81.) / ((double)nphotons_times_numproc * (2. * h->xmax * 1.e-2 / n) *
-                                               (2. * h->ymax * 1.e-2 / n) * (2. * h->zmax * 1.e-2 / n));
-        k_scale<<<gi, 256, 0, st>>>(h->d_jmean, s->ni, f);
+        s->jscale = (get_pwr(s) / 81.) / ((double)nphotons_times_numproc * (2. * h->xmax * 1.e-2 / n) *
+                                          (2. * h->ymax * 1.e-2 / n) * (2. * h->zmax * 1.e-2 / n));
     }
     // heat_sim_3D, 3dFD.f90:101-214
     if (s->pulselength < s->delt) s->delt = s->pulselength / 100.;
     for (int p = 1; p <= s->loops; ++p) {
         k_heat_step<<<gi, 256, 0, st>>>(n, s->temp, s->tn, s->kappa, s->density, s->heatcap, s->coeff, h->d_jmean, s->Q, s->dx,
-                                        s->dy, s->dz, s->delt, s->laserOn, s->volumeVoxel, s->massVoxel, s->QVapor, s->flags);
+                                        s->dy, s->dz, s->delt, s->laserOn, s->volumeVoxel, s->massVoxel, s->QVapor, s->jscale, s->flags);
         std::swap(s->temp, s->tn);                                                       // t0 = tn (both hold the same halo)
         if (s->pulseCount >= s->realPulseLength && s->laser_flag) {                      // :199-211
             s->laser_flag = false; s->laserOn = 0.; s->pulseCount = 0.; s->pulsesDone += 1; s->repetitionCount = 0.;

@@ -13,7 +13,12 @@
 // ablated" rule.  That is BASELINE.json config 5: many small MC calls, each preceded by a re-upload
 // of rhokap, latency per call reported with its breakdown.
 //
-//   usage: mcgrid_shim [--params FILE] [--calls N] [--nxg N] [--scatter] [--out DIR] [--device D]
+// With --resident the heat step is the real one (3dFD.f90 on the device, tamc_heat_*) and the whole
+// `do while(time <= total_time)` loop runs through tamc_coupled_loop with jmean, temp and rhokap resident
+// in HBM; --calls then bounds the number of loop iterations (-1 = run to total_time, 13 390 for the
+// shipped parameters).
+//
+//   usage: mcgrid_shim [--params FILE] [--calls N] [--nxg N] [--scatter] [--resident] [--out DIR] [--device D]
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -142,7 +147,7 @@ int main(int argc, char **argv)
 {
     std::string params_path, out_dir;
     int calls = 200, nxg = 80, device = 0;
-    bool scatter = false;
+    bool scatter = false, resident = false;
     for (int a = 1; a < argc; ++a) {
         const std::string s = argv[a];
         auto next = [&](const char *name) -> const char * {
@@ -155,6 +160,7 @@ int main(int argc, char **argv)
         else if (s == "--device") device = std::atoi(next("--device"));
         else if (s == "--out") out_dir = next("--out");
         else if (s == "--scatter") scatter = true;
+        else if (s == "--resident") resident = true;
         else { std::fprintf(stderr, "unknown argument %s\n", s.c_str()); return 2; }
     }
     Params P;
@@ -175,6 +181,44 @@ int main(int argc, char **argv)
     std::vector<double> jmeanGLOBAL((size_t)g.nxg * g.nyg * g.nzg, 0.);
     tamc_pin_host(g.rhokap.data(), g.rhokap.size() * sizeof(double));
     tamc_pin_host(jmeanGLOBAL.data(), jmeanGLOBAL.size() * sizeof(double));
+
+    if (resident) {
+        // the reference's loop with its real heat / ablation step, nothing crossing PCIe per iteration
+        rc = tamc_set_optics(h, g.rhokap.data(), o.albedo, o.hgg, P.n1, P.n2, 0);
+        if (rc) die("tamc_set_optics", rc);
+        tamc_heat_params hp{};
+        hp.power = P.power; hp.energyPerPixel = P.energyPerPixel; hp.total_time = P.total_time;
+        hp.repetitionRate_1 = P.repetitionRate_1; hp.ablateTemp = P.ablateTemp; hp.loops = P.loops; hp.pulsesToDo = P.pulsesToDo;
+        hp.pulsetype = P.pulsetype == "tophat" ? 0 : (P.pulsetype == "gaussian" ? 1 : 2);
+        double delt = 0., total = 0.;
+        rc = tamc_heat_init(h, &hp, &delt);
+        if (rc) die("tamc_heat_init", rc);
+        tamc_heat_scalar(h, TAMC_HEAT_S_TOTAL_TIME, &total);
+        std::printf("delt %.6e s, total_time %.5f s -> %d loop iterations\n", delt, total, (int)(total / delt));
+        const auto t0 = std::chrono::steady_clock::now();
+        int64_t iters = 0, pk = 0;
+        rc = tamc_coupled_loop(h, P.nphotons, 95648324, calls, &iters, &pk);
+        if (rc) die("tamc_coupled_loop", rc);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        double tsim = 0.;
+        tamc_heat_scalar(h, TAMC_HEAT_S_TIME, &tsim);
+        std::vector<double> temp((size_t)(nxg + 2) * (nxg + 2) * (nxg + 2));
+        tamc_heat_array(h, TAMC_HEAT_TEMP, temp.data(), 0);
+        tamc_heat_array(h, TAMC_HEAT_RHOKAP, g.rhokap.data(), 0);
+        double tmax = 0.; long long ablated = 0;
+        for (int k = 1; k <= nxg; ++k) for (int j = 1; j <= nxg; ++j) for (int i = 1; i <= nxg; ++i) {
+            const size_t c = (size_t)i + (size_t)(nxg + 2) * ((size_t)j + (size_t)(nxg + 2) * k);
+            if (temp[c] > tmax) tmax = temp[c];
+            if (g.rhokap[c] == 0.) ++ablated;
+        }
+        std::printf("resident coupled loop: %lld iterations, %lld packets in %.3f s -> %.1f us per iteration (MC call + heat + "
+                    "Arrhenius + property update), simulated time %.5f s, max temp %.1f C, ablated voxels %lld\n",
+                    (long long)iters, (long long)pk, sec, 1e6 * sec / (double)(iters > 0 ? iters : 1), tsim, tmax - 273., ablated);
+        tamc_unpin_host(g.rhokap.data());
+        tamc_unpin_host(jmeanGLOBAL.data());
+        tamc_finalize(h);
+        return 0;
+    }
 
     std::vector<double> wall_ms, kernel_ms, h2d_ms, d2h_ms;
     long long packets = 0, vsteps = 0;
