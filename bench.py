@@ -320,7 +320,7 @@ def run_ours(args, cfg, name):
     k_ms = res["local_kernel_ms"] / args.steps
     achieved = BYTES_PER_VOXEL_STEP * (res["local_voxel_steps"] / args.steps) / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(name), "peak_source": peak_src, "kernel": "k_transport_persistent" if t.get_option("variant") == 1 else "k_transport_simple",
+                "traffic": ncu_traffic(name), "peak_source": peak_src, "kernel": {0: "k_transport_simple", 2: "k_transport_exact"}.get(t.get_option("variant"), "k_transport_pool" if cfg["flags"] & 1 and t.get_option("variant") == 3 else "k_transport_persistent"),
                 "kernel_ms": k_ms, "algorithmic_bytes_per_voxel_step": BYTES_PER_VOXEL_STEP,
                 "note": "random-walk + fp64 atomics: latency/ALU bound, see DESIGN.md; frac is against the HBM copy peak"}
     probe = None
@@ -329,7 +329,7 @@ def run_ours(args, cfg, name):
             pms, psteps = t.roofline_probe(packets, SEED)
             pms, psteps = t.roofline_probe(packets, SEED)
             probe = {"voxel_steps_per_s": psteps / (pms * 1e-3), "ms": pms,
-                     "what": "same straight-down address stream (fp64 load + fp64 RED per voxel), no transport arithmetic"}
+                     "what": "L2-atomic / grid-lookup roofline: same address stream (column under the beam, geometric step count), one fp64 load of rhokap + one fp64 RED into jmean per voxel-step, no transport arithmetic"}
             roofline["probe"] = probe
             roofline["frac_of_probe"] = (res["local_voxel_steps"] / args.steps / (k_ms * 1e-3)) / probe["voxel_steps_per_s"]
         except Exception as e:  # the probe is context, never fatal
@@ -357,6 +357,26 @@ def run_ours(args, cfg, name):
             t2.close()
         except Exception as e:
             also = {"error": str(e)}
+
+    # the first "next" row: device-resident coupled loop with the reference's heat step
+    if rank == 0 and not args.no_also:
+        try:
+            c5 = tamc.configs.CONFIGS["shipped80"]
+            t5 = tamc.MCTransport(80, 80, 80, c5["xmax"], c5["ymax"], c5["zmax"], device=local)
+            t5.set_optics(c5["rhokap"](), c5["albedo"], c5["hgg"], flags=0)
+            t5.heat_init()
+            t5.coupled_loop(125000, SEED, 200)
+            w0 = time.perf_counter()
+            it5, pk5 = t5.coupled_loop(125000, SEED, 2000)
+            w5 = time.perf_counter() - w0
+            also = dict(also or {})
+            also["coupled_loop_shipped80"] = {
+                "us_per_iteration": 1e6 * w5 / it5, "packets_per_s": pk5 / w5, "iterations": it5,
+                "what": "mcpolar.f90:148-186 resident on the device: MC call of 125 000 packets + heat_sim_3d + arrhenius + setupThermalCoeff per iteration, no PCIe copy (host clock)"}
+            t5.close()
+        except Exception as e:
+            also = dict(also or {})
+            also["coupled_loop_shipped80"] = {"error": str(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -24,6 +24,15 @@ module tamc_mod
         integer(c_int64_t) :: gpu_launches
     end type tamc_stats
 
+    !  mirrors tamc_heat_params (include/tamc.h): the Heat-module inputs of res/input.params
+    type, bind(C) :: tamc_heat_params
+        real(c_double)     :: power, energyPerPixel, total_time, repetitionRate_1, ablateTemp
+        integer(c_int32_t) :: loops, pulsesToDo, pulsetype, pad_
+    end type tamc_heat_params
+
+    integer(c_int), parameter :: TAMC_HEAT_TEMP = 0, TAMC_HEAT_RHOKAP = 1, TAMC_HEAT_WATER = 7, TAMC_HEAT_Q = 8, &
+                                 TAMC_HEAT_TISSUE = 9, TAMC_HEAT_THRESTIME = 10, TAMC_HEAT_JMEAN = 11
+
     interface
 
         integer(c_int) function tamc_init(device, nxg, nyg, nzg, xmax, ymax, zmax, delta, handle) &
@@ -85,6 +94,37 @@ module tamc_mod
         integer(c_int) function tamc_device_count() bind(C, name="tamc_device_count")
             import :: c_int
         end function tamc_device_count
+
+        !  ---- optional: the heat / ablation step on the device (replaces heat_sim_3d + arrhenius +
+        !  setupThermalCoeff, mcpolar.f90:174-182) and the whole time loop resident on the GPU (:148-186)
+        integer(c_int) function tamc_heat_init(handle, params, delt) bind(C, name="tamc_heat_init")
+            import :: c_int, c_double, c_ptr, tamc_heat_params
+            type(c_ptr), value          :: handle
+            type(tamc_heat_params), intent(in) :: params
+            real(c_double), intent(out) :: delt
+        end function tamc_heat_init
+
+        integer(c_int) function tamc_heat_step(handle, nphotons_times_numproc) bind(C, name="tamc_heat_step")
+            import :: c_int, c_int64_t, c_ptr
+            type(c_ptr), value        :: handle
+            integer(c_int64_t), value :: nphotons_times_numproc
+        end function tamc_heat_step
+
+        integer(c_int) function tamc_coupled_loop(handle, nphotons, seed, max_iterations, iterations_done, packets_done) &
+                bind(C, name="tamc_coupled_loop")
+            import :: c_int, c_int64_t, c_ptr
+            type(c_ptr), value              :: handle
+            integer(c_int64_t), value       :: nphotons, seed, max_iterations
+            integer(c_int64_t), intent(out) :: iterations_done, packets_done
+        end function tamc_coupled_loop
+
+        !  which = TAMC_HEAT_TEMP ... (include/tamc.h); upload = 0 copies device -> host
+        integer(c_int) function tamc_heat_array(handle, which, host, upload) bind(C, name="tamc_heat_array")
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value    :: handle
+            integer(c_int), value :: which, upload
+            real(c_double)        :: host(*)
+        end function tamc_heat_array
 
         function tamc_last_error() bind(C, name="tamc_last_error") result(msg)
             import :: c_ptr
