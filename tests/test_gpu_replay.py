@@ -118,3 +118,20 @@ def test_replay_empty_and_short_draw_lists():
         t.run_replay(off, out["draws"][:-1])
     assert e.value.code == 6                        # TAMC_EREPLAY
     t.close()
+
+
+def test_replay_full_scale_chunk_homog200():
+    """BASELINE config 2(i): one 5e6-packet chunk of the full-scale replay on the 200^3 grid (20e6 ran2 draws
+    streamed through the C ABI in 4M-packet pieces)."""
+    import tamc
+
+    worst, gerr = _replay_case(tamc.configs.CONFIGS["homog200"], 5_000_000, rank=6)
+    assert worst < 1e-9 and gerr < 1e-10
+
+
+def test_replay_phantom400_subset():
+    """BASELINE config 4 (400^3, albedo 0.999, ~750 voxel-steps and ~300 scatterings per packet): a small
+    subset replayed on the full-size grid (grids of 0.5 GB each exceed L2)."""
+    import tamc
+
+    _replay_case(tamc.configs.CONFIGS["phantom400"], 300, rank=2, cap_per_packet=60000)
