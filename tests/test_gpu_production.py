@@ -47,6 +47,7 @@ def _philox_exact(cfg, n, first=0, rhokap=None):
                 if variant not in (1, 3) and thr != (32, 1):
                     continue
                 t.set_option("block", 128 if (variant == 3 and thr[1] == 16) else 256)
+                t.set_option("tile", 3 if thr[1] == 16 else (0 if thr[1] == 1 else -1))   # stub regime: smem tally tile
                 t.set_option("variant", variant)
                 t.set_option("merge", merge)
                 t.set_option("chunk", thr[0])

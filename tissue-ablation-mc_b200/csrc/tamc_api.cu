@@ -525,6 +525,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "scatter_min")) return &h->cfg.scatter_min;
     if (!strcmp(name, "merge")) return &h->cfg.merge;
     if (!strcmp(name, "min_ctas")) return &h->cfg.min_ctas;
+    if (!strcmp(name, "tile")) return &h->cfg.tile;
     if (!strcmp(name, "reduce")) return &h->reduce;
     return nullptr;
 }

@@ -138,14 +138,14 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     const double rest = p.tau - p.taurun;
 
     if (!kNeedPos) {
-        tally.add(p.jidx, wall ? taucell : rest);
+        tally.add(p, wall ? taucell : rest);
         if (!wall) return STEP_INTERACT;
     }
     double dcell = dwall;
     if (kNeedPos) {
         const double dpart = rest * __drcp_rn(rk);                    // inttau2.f90:51 (unused when rk == 0: wall is true)
         dcell = wall ? dwall : dpart;
-        tally.add(p.jidx, wall ? taucell : dpart * rk);
+        tally.add(p, wall ? taucell : dpart * rk);
     }
     p.taurun += taucell;
     // which face: the later axis wins ties (inttau2.f90:116-118); none on the final partial step
@@ -272,9 +272,9 @@ struct WarpCounters {
 struct DirectTally32 {
     double *jm;
     __device__ __forceinline__ void begin() {}
-    __device__ __forceinline__ void add(int idx, double v)
+    __device__ __forceinline__ void add(const FastPhoton &p, double v)
     {
-        if (v != 0.) atomicAdd(jm + idx, v);              // RED.E.ADD.F64
+        if (v != 0.) atomicAdd(jm + p.jidx, v);           // RED.E.ADD.F64
     }
     __device__ __forceinline__ void flush() {}
 };
@@ -284,8 +284,9 @@ struct MergeTally32 {
     int pidx;
     double pval;
     __device__ __forceinline__ void begin() { pidx = -1; pval = 0.; }
-    __device__ __forceinline__ void add(int idx, double v)
+    __device__ __forceinline__ void add(const FastPhoton &p, double v)
     {
+        const int idx = p.jidx;
         if (idx == pidx) { pval += v; return; }
         if (pval != 0.) atomicAdd(jm + pidx, pval);
         pidx = idx;
@@ -297,6 +298,34 @@ struct MergeTally32 {
         pidx = -1;
         pval = 0.;
     }
+};
+
+// Stub regime (straight-down flights): the top `layers` planes of the tally under the beam's bounding box
+// are privatised in shared memory, one tile per CTA, and flushed with one RED per non-zero entry at the end
+// of the kernel.  Two thirds of all deposits land there, so the global fp64 REDs -- which share the L1TEX
+// address throughput with the rhokap loads, the limit of this regime -- drop by that much.  fp64 atomicAdd
+// on shared memory is a compare-and-swap loop (ATOMS.CAST.SPIN): a few instructions, rarely contended
+// (tens of thousands of tile entries per CTA).
+struct TileGeom {
+    int i0, j0;        // first voxel (1-based) of the tile in x and y
+    int tw, th;        // tile extent in x and y
+    int layers;        // planes from the top face: k = nzg, nzg-1, ...
+};
+
+struct TiledTally32 {
+    double *jm;
+    double *tile;
+    TileGeom t;
+    int nzg;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void add(const FastPhoton &p, double v)
+    {
+        const unsigned di = (unsigned)(p.celli - t.i0), dj = (unsigned)(p.cellj - t.j0), dk = (unsigned)(nzg - p.cellk);
+        if (v == 0.) return;
+        if (di < (unsigned)t.tw && dj < (unsigned)t.th && dk < (unsigned)t.layers) atomicAdd(tile + (di + t.tw * (dj + t.th * dk)), v);
+        else atomicAdd(jm + p.jidx, v);
+    }
+    __device__ __forceinline__ void flush() {}
 };
 
 }  // namespace tamc

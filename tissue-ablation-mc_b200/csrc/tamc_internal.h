@@ -17,6 +17,7 @@ struct LaunchCfg {
     int scatter_min;    // persistent: run the scattering phase once this many lanes wait for it
     int merge;          // merge consecutive same-voxel deposits in registers (-1 = auto: on with TAMC_SCATTER)
     int min_ctas;       // scattering kernel: the __launch_bounds__ min-CTAs-per-SM build to use (2 or 3)
+    int tile;           // stub regime: shared-memory tally tile; -1 = auto, 0 = off, k > 0 = at most k planes
 };
 
 // production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.

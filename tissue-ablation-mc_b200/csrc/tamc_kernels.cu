@@ -18,6 +18,7 @@
 #include "tamc_fast.cuh"
 #include "tamc_internal.h"
 #include "tamc_pool.cuh"
+#include "tamc_stub_tile.cuh"
 
 namespace tamc {
 
@@ -26,7 +27,7 @@ template <class Base>
 struct SumTally : Base {
     double packet_sum;
     __device__ __forceinline__ void begin() { packet_sum = 0.; Base::begin(); }
-    __device__ __forceinline__ void add(int idx, double v) { packet_sum += v; Base::add(idx, v); }
+    __device__ __forceinline__ void add(const FastPhoton &p, double v) { packet_sum += v; Base::add(p, v); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -391,6 +392,35 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long lon
         c2.block = 256;
         const size_t qsmem = smem + 8 * sizeof(WarpPool);
         return launch_sized(k_transport_pool<256, 2>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+    }
+    // shipped (stub) regime with enough packets to pay for zeroing and flushing a tile per SM: privatise the
+    // top planes of the tally under the beam in shared memory
+    if (!(g.flags & TAMC_SCATTER) && cfg.tile != 0 && (cfg.tile > 0 || n >= (1ll << 21))) {
+        const double R = sqrt(g.spot_r2);
+        TileGeom tg;
+        tg.i0 = max(1, (int)((g.xmax - R) * g.inv_dx) + 1);
+        tg.j0 = max(1, (int)((g.ymax - R) * g.inv_dy) + 1);
+        tg.tw = min(g.nxg, (int)((g.xmax + R) * g.inv_dx) + 1) - tg.i0 + 1;
+        tg.th = min(g.nyg, (int)((g.ymax + R) * g.inv_dy) + 1) - tg.j0 + 1;
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const long long avail = (long long)optin - (long long)smem - 32 * (long long)sizeof(MiniReservoir) - 1024;
+        const long long plane = (long long)tg.tw * tg.th * (long long)sizeof(double);
+        long long layers = plane > 0 ? avail / plane : 0;
+        layers = min(layers, (long long)min(g.nzg, cfg.tile > 0 ? cfg.tile : 8));
+        // auto: only narrow beams (few thousand columns), where the same tally addresses are hit so often that
+        // the L2 atomic unit serialises; on a wide footprint (homog200: 7 500 columns) the tile is neutral.
+        const bool wanted = cfg.tile > 0 || (long long)tg.tw * tg.th <= 4096;
+        if (wanted && tg.tw > 0 && tg.th > 0 && layers >= 1) {
+            tg.layers = (int)layers;
+            const size_t tsmem = smem + (size_t)(plane * layers) + 32 * sizeof(MiniReservoir);
+            int chunk = cfg.chunk > 0 ? cfg.chunk : 1024;
+            cudaError_t e = cudaFuncSetAttribute(k_transport_stub_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+            if (e != cudaSuccess) return e;
+            k_transport_stub_tiled<<<cfg.num_sms, 1024, tsmem, s>>>(g, n, seed, first_id, chunk, tg, d_cnt);
+            return cudaGetLastError();
+        }
     }
     // persistent warps: faces + one reservoir per warp in shared memory
     const size_t psmem = smem + (size_t)(cfg.block / 32) * (sizeof(WarpReservoir) + CNT_N * sizeof(unsigned long long));
