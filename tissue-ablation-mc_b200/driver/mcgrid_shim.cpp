@@ -214,6 +214,46 @@ int main(int argc, char **argv)
         std::printf("resident coupled loop: %lld iterations, %lld packets in %.3f s -> %.1f us per iteration (MC call + heat + "
                     "Arrhenius + property update), simulated time %.5f s, max temp %.1f C, ablated voxels %lld\n",
                     (long long)iters, (long long)pk, sec, 1e6 * sec / (double)(iters > 0 ? iters : 1), tsim, tmax - 273., ablated);
+        if (!out_dir.empty()) {
+            // mcpolar.f90:193-206 + writer.f90:6-81: the eight raw fp64 stream files, reference names and contents
+            const size_t ni = (size_t)nxg * nxg * nxg;
+            std::vector<double> tissue(ni), water(ni), thres(3 * ni), inner(ni);
+            tamc_heat_array(h, TAMC_HEAT_TISSUE, tissue.data(), 0);
+            tamc_heat_array(h, TAMC_HEAT_WATER, water.data(), 0);
+            tamc_heat_array(h, TAMC_HEAT_THRESTIME, thres.data(), 0);
+            tamc_heat_array(h, TAMC_HEAT_JMEAN, jmeanGLOBAL.data(), 0);
+            // the file holds the scaled jmeanGLOBAL of the last MC call (mcpolar.f90:174)
+            double pwr = 0.;
+            tamc_heat_scalar(h, TAMC_HEAT_S_PWR, &pwr);
+            const double vox = (2. * P.xmax * 1e-2 / nxg) * (2. * P.ymax * 1e-2 / nxg) * (2. * P.zmax * 1e-2 / nxg);
+            for (double &v : jmeanGLOBAL) v *= (pwr / 81.) / ((double)P.nphotons * numproc * vox);
+            // delete damage info about the ablation crater (mcpolar.f90:196-205)
+            for (int k = 1; k <= nxg; ++k) for (int j = 1; j <= nxg; ++j) for (int i = 1; i <= nxg; ++i) {
+                const size_t c = (size_t)i + (size_t)(nxg + 2) * ((size_t)j + (size_t)(nxg + 2) * k);
+                const size_t q = (size_t)(i - 1) + (size_t)nxg * ((size_t)(j - 1) + (size_t)nxg * (k - 1));
+                if (g.rhokap[c] <= 0.1) tissue[q] = -1.;
+                inner[q] = g.rhokap[c];
+            }
+            for (double &v : temp) v -= 273.;
+            const std::string tail = "w-" + std::to_string(nxg) + "-" + fstr(P.ablateTemp, 3) + "-" + fstr((int)P.energyPerPixel, 3) +
+                                     "-" + fstr(P.xmax, 5) + "-" + fstr(P.ymax, 5) + "-" + fstr(P.zmax, 5) + ".dat";
+            auto dump = [&](const std::string &stem, const double *d, size_t cnt) {
+                const std::string name = out_dir + "/" + stem + std::to_string((int)P.power) + tail;
+                FILE *f = std::fopen(name.c_str(), "wb");
+                if (!f) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return; }
+                std::fwrite(d, sizeof(double), cnt, f);
+                std::fclose(f);
+                std::printf("wrote %s\n", name.c_str());
+            };
+            dump("jmean-t", jmeanGLOBAL.data(), ni);
+            dump("rhokap-t", inner.data(), ni);                     // rhokap(1:nxg,1:nyg,1:nzg)
+            dump("temp-t", temp.data(), temp.size());               // temp - 273, halo included
+            dump("water-t", water.data(), ni);
+            dump("tissue-t", tissue.data(), ni);
+            dump("time-t-1-", thres.data(), ni);
+            dump("time-t-2-", thres.data() + ni, ni);
+            dump("time-t-3-", thres.data() + 2 * ni, ni);
+        }
         tamc_unpin_host(g.rhokap.data());
         tamc_unpin_host(jmeanGLOBAL.data());
         tamc_finalize(h);
