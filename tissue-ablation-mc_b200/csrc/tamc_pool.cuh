@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const LaunchConsts lc{g.zcur0, g.cellk0};
+    const int launch_min = 16;
 
     // queues: everything free at the start
     P.fq[lane] = (unsigned char)lane;
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
         }
 
         // ---- (2) launch into free slots when the walk queue cannot feed the empty lanes
-        if (nw < nempty && nf > 0 && !exhausted) {
+        // (batched: at least `launch_min` free slots, unless lanes would otherwise starve)
+        if (!exhausted && nf > 0 && (nf >= launch_min ? nw < nempty : (nw == 0 && ni < scatter_min && nempty > 0))) {
             if (next >= end) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(cnt + CNT_WORK, (unsigned long long)chunk);
