@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TAMC_VERSION 100
+#define TAMC_VERSION 101
 
 enum {
     TAMC_OK = 0,
@@ -40,8 +40,12 @@ enum {
 
 /* tamc_set_optics flags */
 enum {
-    TAMC_SCATTER = 1     /* run the albedo test + stokes() loop the driver's shell implies
+    TAMC_SCATTER = 1,    /* run the albedo test + stokes() loop the driver's shell implies
                             (mcpolar.f90:165-169, stokes.f90:6-153) instead of the shipped stub */
+    TAMC_FRESNEL = 2     /* EXTENSION, no upstream semantics (the reference reads n1, n2 and never uses them,
+                            mcpolar.f90:84-85, inttau2.f90:125): specular reflection at launch with probability
+                            ((n1-n2)/(n1+n2))^2, and unpolarised Fresnel reflection / escape (n2 inside, n1 outside,
+                            total internal reflection past the critical angle) at the six outer faces of the grid */
 };
 
 typedef struct tamc_context *tamc_handle;
@@ -71,6 +75,8 @@ typedef struct {
     double allreduce_ms;          /* ncclAllReduce of the tally (0 without a communicator) */
     double h2d_ms, d2h_ms;        /* rhokap upload / jmean download inside the last calls */
     int64_t gpu_launches;         /* kernels launched by the library for this call */
+    int64_t specular;             /* TAMC_FRESNEL: reflected at the top surface before entering (also in exits[5]) */
+    int64_t internal_reflections; /* TAMC_FRESNEL: reflections back into the grid at an outer face */
 } tamc_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */

@@ -15,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 FLAG_SCATTER = 1
+FLAG_FRESNEL = 2
 
 RECORD_DTYPE = np.dtype(
     [
@@ -39,13 +40,16 @@ class Stats(C.Structure):
         ("exits", C.c_int64 * 6),
         ("draws", C.c_int64),
         ("deposit_sum", C.c_double),
+        ("specular", C.c_int64),
+        ("internal_reflections", C.c_int64),
     ]
 
     def as_dict(self):
         return {
             "packets": self.packets, "voxel_steps": self.voxel_steps, "scatters": self.scatters,
             "absorbed": self.absorbed, "exits": list(self.exits), "draws": self.draws,
-            "deposit_sum": self.deposit_sum,
+            "deposit_sum": self.deposit_sum, "specular": self.specular,
+            "internal_reflections": self.internal_reflections,
         }
 
 
@@ -86,6 +90,7 @@ def _bind(path: str) -> C.CDLL:
     lib.orc_init_opt1.argtypes = [p]
     lib.orc_set_optics.argtypes = [p, d, d]
     lib.orc_set_spot.argtypes = [p, d]
+    lib.orc_set_indices.argtypes = [p, d, d]
     lib.orc_set_flags.argtypes = [p, i]
     lib.orc_zero_jmean.argtypes = [p]
     lib.orc_seed_ran2.argtypes = [p, i]
@@ -200,6 +205,9 @@ class Oracle:
     def set_optics(self, albedo: float, hgg: float):
         self.albedo, self.hgg = float(albedo), float(hgg)
         self.lib.orc_set_optics(self.h, self.albedo, self.hgg)
+
+    def set_indices(self, n1: float, n2: float):
+        self.lib.orc_set_indices(self.h, float(n1), float(n2))
 
     def set_spot(self, diameter: float):
         self.lib.orc_set_spot(self.h, float(diameter))

@@ -36,7 +36,7 @@ struct orc_state {
     double *xface, *yface, *zface;
     double *rhokap, *jmean;
     /* opt_prop.f90:5 */
-    double mua, mus, g2, hgg, kappa, albedo, mu_water, mu_protein;
+    double mua, mus, g2, hgg, kappa, albedo, mu_water, mu_protein, n1, n2;
     /* photon_vars.f90:11 */
     double xp, yp, zp, nxp, nyp, nzp, sint, cost, sinp, cosp, phi;
     /* ran2.f:8-9 SAVEd state */
@@ -55,6 +55,8 @@ struct orc_state {
     /* per-packet counters */
     int32_t steps, nscatt;
     double deposit;
+    int64_t pkt_bdraws;         /* boundary-stream draws consumed by the current packet */
+    int64_t internal_reflections;
 };
 
 #define RHOKAP(o, i, j, k) ((o)->rhokap[(size_t)(i) + (size_t)((o)->nxg + 2) * ((size_t)(j) + (size_t)((o)->nyg + 2) * (size_t)(k))])
@@ -89,6 +91,7 @@ orc_state *orc_create(int nxg, int nyg, int nzg, double xmax, double ymax, doubl
     o->iy = 0;
     o->iseed = -95648324;
     o->rng_mode = ORC_RNG_RAN2;
+    o->n1 = 1.; o->n2 = 1.;
     orc_init_opt1(o);
     return o;
 }
@@ -139,6 +142,7 @@ void orc_set_optics(orc_state *o, double albedo, double hgg)
 }
 
 void orc_set_spot(orc_state *o, double d) { o->spotSize = d; }
+void orc_set_indices(orc_state *o, double n1, double n2) { o->n1 = n1; o->n2 = n2; }
 void orc_set_flags(orc_state *o, int flags) { o->flags = flags; }
 void orc_zero_jmean(orc_state *o) { memset(o->jmean, 0, sizeof(double) * (size_t)o->nxg * o->nyg * o->nzg); }
 
@@ -236,6 +240,39 @@ static double draw(orc_state *o)
     }
     o->draw_n++;
     return r;
+}
+
+/* ---- builder-defined extension: Fresnel boundaries (ORC_FLAG_FRESNEL) -------------------------
+ * The reference reads n1, n2 (mcpolar.f90:84-85) and never uses them; the only trace of boundary optics is a
+ * comment (inttau2.f90:125).  What the north-star asks for is specified here, default off:
+ *   - at launch the packet is specularly reflected with probability ((n1-n2)/(n1+n2))^2 (normal incidence);
+ *   - when a wall crossing would take the packet out of the grid through a face, it is reflected back with the
+ *     unpolarised Fresnel reflectance for n2 -> n1 at its angle of incidence (total internal reflection
+ *     beyond the critical angle): the normal direction cosine changes sign, the position is snapped to
+ *     `face -+ delta` INSIDE the grid, the optical-depth integration simply continues.
+ * Boundary decisions draw from their own stream (ran2: the same sequential generator; Philox: counter word 3
+ * = 1), so switching the flag on with n1 == n2 changes nothing in the packets' paths. */
+static double draw_boundary(orc_state *o)
+{
+    if (o->rng_mode == ORC_RNG_RAN2) return ran2(o, &o->iseed);
+    {
+        uint32_t b[4];
+        orc_philox4x32_10((uint32_t)o->ph_seed, (uint32_t)(o->ph_seed >> 32), (uint32_t)o->ph_packet,
+                          (uint32_t)(o->ph_packet >> 32), (uint32_t)(o->pkt_bdraws >> 2), 1u, b);
+        return ((double)b[o->pkt_bdraws++ & 3] + 0.5) * (1.0 / 4294967296.0);
+    }
+}
+
+static double fresnel_reflectance(double n_in, double n_out, double ci)
+{
+    const double ratio = n_in / n_out;
+    const double si2 = (ratio * ratio) * (1. - ci * ci);
+    double ct, rs, rp;
+    if (si2 >= 1.) return 1.;
+    ct = sqrt(1. - si2);
+    rs = (n_in * ci - n_out * ct) / (n_in * ci + n_out * ct);
+    rp = (n_in * ct - n_out * ci) / (n_in * ct + n_out * ci);
+    return 0.5 * (rs * rs + rp * rp);
 }
 
 double orc_ran2(orc_state *o) { return ran2(o, &o->iseed); }
@@ -384,7 +421,35 @@ static void tauint1(orc_state *o, double xmax, double ymax, double zmax, int *xc
             d = d + dcell;
             JMEAN(o, celli, cellj, cellk) = JMEAN(o, celli, cellj, cellk) + dcell * RHOKAP(o, celli, cellj, cellk);
             o->deposit += dcell * RHOKAP(o, celli, cellj, cellk);
-            update_pos(o, &xcur, &ycur, &zcur, &celli, &cellj, &cellk, dcell, 1, dir, delta);
+            {
+                const int pi = celli, pj = cellj, pk = cellk;
+                update_pos(o, &xcur, &ycur, &zcur, &celli, &cellj, &cellk, dcell, 1, dir, delta);
+                if ((o->flags & ORC_FLAG_FRESNEL) && (celli == -1 || cellj == -1 || cellk == -1)) {
+                    /* extension: the crossed face is an outer face of the grid */
+                    const int a = dir[0] ? 0 : (dir[1] ? 1 : 2);
+                    const double na = a == 0 ? o->nxp : (a == 1 ? o->nyp : o->nzp);
+                    const int only = (a == 0 && celli == -1 && cellj != -1 && cellk != -1) ||
+                                     (a == 1 && cellj == -1 && celli != -1 && cellk != -1) ||
+                                     (a == 2 && cellk == -1 && celli != -1 && cellj != -1);
+                    if (only && draw_boundary(o) < fresnel_reflectance(o->n2, o->n1, fabs(na))) {
+                        o->internal_reflections++;
+                        if (a == 0) {
+                            xcur = (na > 0.) ? XFACE(o, pi + 1) - delta : XFACE(o, pi) + delta;
+                            celli = pi;
+                            o->nxp = -o->nxp; o->cosp = -o->cosp;
+                        } else if (a == 1) {
+                            ycur = (na > 0.) ? YFACE(o, pj + 1) - delta : YFACE(o, pj) + delta;
+                            cellj = pj;
+                            o->nyp = -o->nyp; o->sinp = -o->sinp;
+                        } else {
+                            zcur = (na > 0.) ? ZFACE(o, pk + 1) - delta : ZFACE(o, pk) + delta;
+                            cellk = pk;
+                            o->nzp = -o->nzp; o->cost = -o->cost;
+                        }
+                        if (a != 2) o->phi = atan2(o->sinp, o->cosp);   /* keeps (cost, sint, phi) consistent for stokes */
+                    }
+                }
+            }
         } else {
             dcell = (tau - taurun) / RHOKAP(o, celli, cellj, cellk);
             d = d + dcell;
@@ -544,8 +609,9 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
     o->draw_n = 0;
     o->draw_overflow = 0;
 
+    o->internal_reflections = 0;
     for (j = 1; j <= nphotons; j++) {
-        int absorbed = 0;
+        int absorbed = 0, specular = 0;
         tflag = 0;
         o->pkt_draws = 0;
         o->steps = 0;
@@ -553,8 +619,19 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
         o->deposit = 0.;
         if (offsets) offsets[j - 1] = o->draw_n;
 
+        o->pkt_bdraws = 0;
         sourcephCO2(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell);
-        tauint1(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell, &tflag, o->delta);
+        if (o->flags & ORC_FLAG_FRESNEL) {
+            /* extension: specular reflection at the top surface, normal incidence */
+            const double r0 = (o->n1 - o->n2) / (o->n1 + o->n2);
+            if (draw_boundary(o) < r0 * r0) {
+                specular = 1;
+                tflag = 1;
+                o->nzp = 1.;        /* leaves upwards */
+                zcell = -1;
+            }
+        }
+        if (!tflag) tauint1(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell, &tflag, o->delta);
 
         while (!tflag) {
             if (!(o->flags & ORC_FLAG_SCATTER)) { /* mcpolar.f90:167-168 */
@@ -582,6 +659,7 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
             st.deposit_sum += o->deposit;
             if (fate == 0) st.absorbed++;
             else st.exits[fate - 1]++;
+            st.specular += specular;
             if (records) {
                 orc_packet_record *r = &records[j - 1];
                 r->xp = o->xp; r->yp = o->yp; r->zp = o->zp;
@@ -595,6 +673,7 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
         if (o->rng_mode == ORC_RNG_PHILOX) o->ph_packet++;
     }
     if (offsets) offsets[nphotons] = o->draw_n;
+    st.internal_reflections = o->internal_reflections;
     if (stats) *stats = st;
     o->draw_log = NULL;
     return o->draw_overflow ? -1 : 0;
@@ -676,6 +755,8 @@ int orc_run_ranks(int nranks, int nxg, int nyg, int nzg, double xmax, double yma
             stats->absorbed += rstats[r].absorbed;
             stats->draws += rstats[r].draws;
             stats->deposit_sum += rstats[r].deposit_sum;
+            stats->specular += rstats[r].specular;
+            stats->internal_reflections += rstats[r].internal_reflections;
             for (f = 0; f < 6; f++) stats->exits[f] += rstats[r].exits[f];
         }
     }

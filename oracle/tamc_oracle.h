@@ -46,12 +46,14 @@ typedef struct {
     int64_t exits[6];       /* -x,+x,-y,+y,-z,+z */
     int64_t draws;
     double  deposit_sum;
+    int64_t specular;       /* ORC_FLAG_FRESNEL: reflected at the top surface before entering (also counted in exits[5]) */
+    int64_t internal_reflections;
 } orc_stats;
 
 typedef struct orc_state orc_state;
 
 enum { ORC_RNG_RAN2 = 0, ORC_RNG_PHILOX = 1 };
-enum { ORC_FLAG_SCATTER = 1 };
+enum { ORC_FLAG_SCATTER = 1, ORC_FLAG_FRESNEL = 2 };
 
 /* Allocate module state for an nxg*nyg*nzg grid and build the face arrays
  * (gridset.f90:23-31); rhokap and jmean start at zero. */
@@ -71,6 +73,9 @@ void orc_gridset_uniform(orc_state *o, double kappa);
 /* ch_opt.f90:15-23 shipped optics: hgg .9, g2, mua 680, mus 0, kappa, albedo; returns kappa */
 double orc_init_opt1(orc_state *o);
 void orc_set_optics(orc_state *o, double albedo, double hgg);
+/* Builder-defined extension (no upstream semantics): refractive indices outside / inside the grid
+ * for ORC_FLAG_FRESNEL -- specular reflection at launch, Fresnel reflection or escape at the six outer faces. */
+void orc_set_indices(orc_state *o, double n1, double n2);
 void orc_set_spot(orc_state *o, double spot_diameter);   /* sourceph.f90:23, default 250d-4 */
 void orc_set_flags(orc_state *o, int flags);
 void orc_zero_jmean(orc_state *o);

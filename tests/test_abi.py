@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libtamc.so does not export {n}"
     assert sorted(binding.EXPORTS) == names          # the Python binding covers the whole ABI
-    assert tamc.lib().tamc_version() == 100
+    assert tamc.lib().tamc_version() == 101
 
 
 def test_record_and_stats_layout_match_header():
     import tamc
 
     assert tamc.RECORD_DTYPE.itemsize == 88
-    assert C.sizeof(tamc.Stats) == 8 * 10 + 8 * 5 + 8
+    assert C.sizeof(tamc.Stats) == 8 * 10 + 8 * 5 + 8 + 16
     from oracle import oracle as orc
 
     assert orc.RECORD_DTYPE == tamc.RECORD_DTYPE

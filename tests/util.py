@@ -16,6 +16,7 @@ def make_oracle(cfg, rhokap=None):
     o.set_rhokap(rhokap if rhokap is not None else cfg["rhokap"]())
     o.set_optics(cfg["albedo"], cfg["hgg"])
     o.set_flags(cfg["flags"])
+    o.set_indices(cfg.get("n1", 1.0), cfg.get("n2", 1.0))
     if "spot" in cfg:
         o.set_spot(cfg["spot"])
     return o
@@ -28,7 +29,8 @@ def make_transport(cfg, rhokap=None, device=0):
     t = tamc.MCTransport(n, n, n, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=device)
     if "spot" in cfg:
         t.set_source_co2(cfg["spot"])
-    t.set_optics(rhokap if rhokap is not None else cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=cfg["flags"])
+    t.set_optics(rhokap if rhokap is not None else cfg["rhokap"](), cfg["albedo"], cfg["hgg"], n1=cfg.get("n1", 1.0),
+                 n2=cfg.get("n2", 1.0), flags=cfg["flags"])
     return t
 
 

@@ -109,6 +109,8 @@ static DevGrid make_grid(const tamc_context *c)
     g.zcur0 = g.zp0 + c->zmax;
     g.cellk0 = (int)((double)c->nzg * (g.zp0 + c->zmax) / (2. * c->zmax)) + 1;
     g.flags = c->flags;
+    g.n1 = c->n1; g.n2 = c->n2;
+    g.r0sq = ((c->n1 - c->n2) / (c->n1 + c->n2)) * ((c->n1 - c->n2) / (c->n1 + c->n2));
     g.sc.one_m_g2 = 1. - g.g2;                                         // stokes.f90:48
     g.sc.one_p_g2 = 1. + g.g2;
     g.sc.one_m_g = 1. - g.hgg;
@@ -239,7 +241,8 @@ extern "C" int tamc_set_optics(tamc_handle h, const double *rhokap, double albed
     if (int rc = check(h)) return rc;
     if (!(albedo >= 0. && albedo <= 1.)) return fail(TAMC_EINVAL, "tamc_set_optics: albedo must be in [0,1]");
     if (!(hgg > -1. && hgg < 1.)) return fail(TAMC_EINVAL, "tamc_set_optics: hgg must be in (-1,1)");
-    if (flags & ~TAMC_SCATTER) return fail(TAMC_EINVAL, "tamc_set_optics: unknown flag bits");
+    if (flags & ~(TAMC_SCATTER | TAMC_FRESNEL)) return fail(TAMC_EINVAL, "tamc_set_optics: unknown flag bits");
+    if ((flags & TAMC_FRESNEL) && !(n1 > 0. && n2 > 0.)) return fail(TAMC_EINVAL, "tamc_set_optics: TAMC_FRESNEL needs positive n1, n2");
     if (!rhokap && !h->optics_set) return fail(TAMC_ESTATE, "tamc_set_optics: first call needs the rhokap grid");
     h->timed_h2d = false;
     if (rhokap) {
@@ -366,6 +369,8 @@ extern "C" int tamc_get_stats(tamc_handle h, tamc_stats *st)
     st->scatters = (int64_t)cnt[CNT_SCATTERS];
     st->absorbed = (int64_t)cnt[CNT_ABSORBED];
     for (int f = 0; f < 6; ++f) st->exits[f] = (int64_t)cnt[CNT_EXIT0 + f];
+    st->specular = (int64_t)cnt[CNT_SPECULAR];
+    st->internal_reflections = (int64_t)cnt[CNT_REFLECT];
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, h->ev[EV_ZERO0], h->ev[EV_K0])); st->zero_ms = ms;
     CU(cudaEventElapsedTime(&ms, h->ev[EV_K0], h->ev[EV_K1])); st->kernel_ms = ms;
@@ -403,6 +408,7 @@ extern "C" int tamc_run_replay(tamc_handle h, int64_t npackets, const int64_t *d
 {
     if (int rc = check(h)) return rc;
     if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run_replay: tamc_set_optics has not been called");
+    if (h->flags & TAMC_FRESNEL) return fail(TAMC_EINVAL, "tamc_run_replay: the reference has no boundary optics to replay (TAMC_FRESNEL set)");
     if (npackets < 0 || (npackets > 0 && (!draw_offsets || !draws))) return fail(TAMC_EINVAL, "tamc_run_replay: bad arguments");
     const DevGrid g = make_grid(h);
     CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));

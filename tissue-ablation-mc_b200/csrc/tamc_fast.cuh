@@ -235,6 +235,31 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
     set_direction(p);
 }
 
+// TAMC_FRESNEL on the production arithmetic.  After STEP_EXIT exactly one index is out of range (only the
+// crossed axis is re-indexed).  Returns true when the packet was reflected back into the grid.
+__device__ __forceinline__ bool fresnel_reflect_fast(const DevGrid &g, const double *xf, const double *yf, const double *zf,
+                                                     FastPhoton &p, uint2 key, uint32_t id_lo, uint32_t id_hi, int &nb)
+{
+    const int a = ((unsigned)(p.celli - 1) >= (unsigned)g.nxg) ? 0 : (((unsigned)(p.cellj - 1) >= (unsigned)g.nyg) ? 1 : 2);
+    const double na = a == 0 ? p.nxp : (a == 1 ? p.nyp : p.nzp);
+    if (!(boundary_draw(key, id_lo, id_hi, nb) < fresnel_reflectance(g.n2, g.n1, fabs(na)))) return false;
+    const int back = (na > 0.) ? -1 : 1;             // undo the index step of the crossing
+    if (a == 0) {
+        p.xcur = (na > 0.) ? xf[g.nxg] - g.delta : xf[0] + g.delta;
+        p.celli += back; p.ridx += back; p.jidx += back;
+        p.nxp = -p.nxp; p.inx = -p.inx; p.cosp = -p.cosp; p.dflags ^= 1;
+    } else if (a == 1) {
+        p.ycur = (na > 0.) ? yf[g.nyg] - g.delta : yf[0] + g.delta;
+        p.cellj += back; p.ridx += back * g.sx; p.jidx += back * g.nxg;
+        p.nyp = -p.nyp; p.iny = -p.iny; p.sinp = -p.sinp; p.dflags ^= 2;
+    } else {
+        p.zcur = (na > 0.) ? zf[g.nzg] - g.delta : zf[0] + g.delta;
+        p.cellk += back; p.ridx += back * (int)g.sxy; p.jidx += back * (g.nxg * g.nyg);
+        p.nzp = -p.nzp; p.inz = -p.inz; p.dflags ^= 4;
+    }
+    return true;
+}
+
 __device__ __forceinline__ int exit_face_fast(const FastPhoton &p, const DevGrid &g)
 {
     if (p.celli < 1 || p.celli > g.nxg) return p.nxp > 0. ? 2 : 1;
@@ -260,11 +285,12 @@ struct WarpCounters {
         atomicAdd(w + (f == 0 ? CNT_ABSORBED : CNT_EXIT0 + f - 1), 1ull);
         if (err) atomicAdd(w + CNT_ERRORS, 1ull);
     }
+    __device__ __forceinline__ void note(int slot) { atomicAdd(w + slot, 1ull); }
     __device__ __forceinline__ void commit(unsigned long long *g) const
     {
         __syncwarp();
         const int i = threadIdx.x & 31;
-        if (i < 12 && w[i]) atomicAdd(g + i, w[i]);
+        if (i < CNT_N && i != CNT_WORK && w[i]) atomicAdd(g + i, w[i]);
     }
 };
 

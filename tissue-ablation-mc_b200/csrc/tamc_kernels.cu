@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
     const double *xf, *yf, *zf;
     stage_faces(g, s_faces, xf, yf, zf);
     const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
+    const bool fresnel = (g.flags & TAMC_FRESNEL) != 0;
     const LaunchConsts lc{g.zcur0, g.cellk0};
 
     Counters c;
@@ -57,15 +58,31 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
         FastPhoton p;
         adopt(g, lc, p, launch_fast(g, u, scatter_on));
         tally.begin();
-        int steps = 0, nscatt = 0, fate = 0, ndraws = 4;
-        for (;;) {
+        int steps = 0, nscatt = 0, fate = 0, ndraws = 4, nb = 0;
+        bool specular = false;
+        if (fresnel && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < g.r0sq) {
+            specular = true;                                      // reflected at the top surface before entering
+            fate = 6;
+            ndraws = 3;
+            p.nzp = 1.;
+            p.cellk = g.nzg + 1;
+            c.note(CNT_SPECULAR);
+        }
+        while (!specular) {
             const int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
             ++steps;
             if (r == STEP_WALL) {
                 if (steps >= kMaxStepsPerPacket) { c.errors++; break; }
                 continue;
             }
-            if (r == STEP_EXIT) { fate = exit_face_fast(p, g); break; }
+            if (r == STEP_EXIT) {
+                if (fresnel && fresnel_reflect_fast(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb)) {
+                    c.note(CNT_REFLECT);
+                    continue;
+                }
+                fate = exit_face_fast(p, g);
+                break;
+            }
             if (!scatter_on) break;                               // mcpolar.f90:166-169 stub
             rng.block(u);
             if (u[0] < g.albedo) {
@@ -163,7 +180,8 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
     FastPhoton p;
     PhiloxRng rng;
     rng.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    int mode = LANE_IDLE, steps = 0, nscatt = 0;
+    int mode = LANE_IDLE, steps = 0, nscatt = 0, nb = 0;
+    const bool fresnel = kScatter && (g.flags & TAMC_FRESNEL) != 0;
     int count = 0;                       // launched packets parked in the reservoir (warp-uniform)
     long long next = 0, end = 0;         // ids of the chunk this warp currently owns
     bool exhausted = false;
@@ -220,7 +238,13 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
                 tally.begin();
                 steps = 0;
                 nscatt = 0;
+                nb = 0;
                 mode = LANE_WALK;
+                if (fresnel && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < g.r0sq) {
+                    c.note(CNT_SPECULAR);                 // reflected at the top surface: never enters
+                    c.death(6, 0, 0, false);
+                    mode = LANE_IDLE;
+                }
             }
             count -= min(nidle, count);
             __syncwarp();
@@ -246,8 +270,12 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
         }
         // ---- one voxel-step for every walking lane
         if (mode == LANE_WALK) {
-            const int r = voxel_step_fast<kScatter>(g, xf, yf, zf, p, tally);
+            int r = voxel_step_fast<kScatter>(g, xf, yf, zf, p, tally);
             ++steps;
+            if (fresnel && r == STEP_EXIT && fresnel_reflect_fast(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb)) {
+                c.note(CNT_REFLECT);
+                r = STEP_WALL;
+            }
             if (kScatter && r == STEP_INTERACT) {
                 mode = LANE_INTERACT;
             } else if (r != STEP_WALL || steps >= kMaxStepsPerPacket) {
@@ -375,7 +403,8 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long lon
         if (merge) return launch_sized(k_transport_simple<MergeTally32, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
         return launch_sized(k_transport_simple<DirectTally32, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
     }
-    if (cfg.variant == 0) {
+    // Fresnel boundaries without the scatter loop: the stub kernels keep no packet id, use the thread-per-packet kernel
+    if (cfg.variant == 0 || ((g.flags & TAMC_FRESNEL) && !(g.flags & TAMC_SCATTER))) {
         if (merge) return launch_sized(k_transport_simple<MergeTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
@@ -386,12 +415,16 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long lon
             LaunchCfg c2 = cfg;
             c2.block = 128;
             const size_t qsmem = smem + 4 * sizeof(WarpPool);
-            return launch_sized(k_transport_pool<128, 5>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+            if (g.flags & TAMC_FRESNEL)
+                return launch_sized(k_transport_pool<128, 5, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+            return launch_sized(k_transport_pool<128, 5, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
         }
         LaunchCfg c2 = cfg;
         c2.block = 256;
         const size_t qsmem = smem + 8 * sizeof(WarpPool);
-        return launch_sized(k_transport_pool<256, 2>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        if (g.flags & TAMC_FRESNEL)
+            return launch_sized(k_transport_pool<256, 2, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        return launch_sized(k_transport_pool<256, 2, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
     }
     // shipped (stub) regime with enough packets to pay for zeroing and flushing a tile per SM: privatise the
     // top planes of the tally under the beam in shared memory

@@ -33,14 +33,15 @@ struct WarpPool {
     double tau[kPool], pval[kPool];                   // optical depth to the next interaction; pending deposit
     int cells[kPool], cellk[kPool];                   // celli | cellj << 16 ; cellk
     int ridx[kPool], jidx[kPool], pidx[kPool];
-    int steps[kPool], nscat[kPool], dfl[kPool];
+    int steps[kPool], nscat[kPool], dfl[kPool], nbnd[kPool];
     unsigned int idlo[kPool], idhi[kPool];
     unsigned char wq[kPool], iq[kPool], fq[kPool];    // walk / interact / free queues (stacks of slot numbers)
     unsigned char pad[64];
     unsigned long long cnt[CNT_N];
 };
 
-template <int kBlock, int kMinCtas>
+// kFresnel compiles the boundary-optics extension in (TAMC_FRESNEL); the default build carries none of it.
+template <int kBlock, int kMinCtas, bool kFresnel>
 __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                                   int chunk, int scatter_min,
                                                                   unsigned long long *__restrict__ cnt)
@@ -73,7 +74,9 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
     MergeTally32 tally;
     tally.jm = g.jmean;
     tally.begin();
-    int steps = 0;
+    int steps = 0, nb = 0;
+    bool doa = false;                        // dead on arrival: specularly reflected at the surface (TAMC_FRESNEL)
+    constexpr bool fresnel = kFresnel;
     // per-lane accumulators, folded into the warp's counters at the end
     unsigned long long acc_steps = 0ull, acc_scat = 0ull;
     unsigned int acc_pk = 0u, acc_abs = 0u;
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                     P.ix[s] = 0.; P.iy[s] = 0.; P.iz[s] = -1.; P.dfl[s] = 4 | 8 | 16;
                     P.tau[s] = L.tau; P.pval[s] = 0.; P.pidx[s] = -1;
                     P.cells[s] = L.cells; P.cellk[s] = lc.cellk0; P.ridx[s] = L.ridx; P.jidx[s] = L.jidx;
-                    P.steps[s] = 0; P.nscat[s] = 0;
+                    P.steps[s] = 0; P.nscat[s] = 0; P.nbnd[s] = 0;
                     P.idlo[s] = (uint32_t)gid; P.idhi[s] = (uint32_t)(gid >> 32);
                     P.wq[nw + lane] = (unsigned char)s;
                 }
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 p.nzp = P.nz[slot];
                 const double st = P.st[slot];
                 p.nxp = st * P.cp[slot]; p.nyp = st * P.sp[slot];                      // stokes.f90:143-148
+                if (kFresnel) { p.sint = st; p.cosp = P.cp[slot]; p.sinp = P.sp[slot]; }
                 p.inx = P.ix[slot]; p.iny = P.iy[slot]; p.inz = P.iz[slot]; p.dflags = P.dfl[slot];
                 p.tau = P.tau[slot]; p.taurun = 0.;
                 const int c = P.cells[slot];
@@ -177,7 +181,12 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 p.ridx = P.ridx[slot]; p.jidx = P.jidx[slot];
                 tally.pidx = P.pidx[slot]; tally.pval = P.pval[slot];
                 steps = P.steps[slot];
+                if (kFresnel) nb = P.nbnd[slot];
                 walking = true;
+                if (fresnel && nb == 0 && boundary_draw(key, P.idlo[slot], P.idhi[slot], nb) < g.r0sq) {
+                    walking = false;                      // fresh packet reflected at the top surface: never enters
+                    doa = true;
+                }
             }
             nw -= k;
             __syncwarp();
@@ -187,9 +196,19 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
 
         // ---- (4) one voxel-step for every walking lane; park or retire the packet when the flight ends
         bool park = false, retire = false;
-        if (walking) {
-            const int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
+        if (doa) {
+            doa = false;
+            retire = true;
+            acc_pk++;
+            atomicAdd(&P.cnt[CNT_EXIT0 + 5], 1ull);
+            atomicAdd(&P.cnt[CNT_SPECULAR], 1ull);
+        } else if (walking) {
+            int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
             ++steps;
+            if (fresnel && r == STEP_EXIT && fresnel_reflect_fast(g, xf, yf, zf, p, key, P.idlo[slot], P.idhi[slot], nb)) {
+                atomicAdd(&P.cnt[CNT_REFLECT], 1ull);
+                r = STEP_WALL;
+            }
             if (r == STEP_INTERACT) {
                 // the centred-position round trip of inttau2.f90:65-67 / :24-26
                 P.px[slot] = (p.xcur - g.xmax) + g.xmax;
@@ -199,6 +218,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 P.ridx[slot] = p.ridx; P.jidx[slot] = p.jidx;
                 P.pidx[slot] = tally.pidx; P.pval[slot] = tally.pval;
                 P.steps[slot] = steps;
+                if (kFresnel) {
+                    P.nbnd[slot] = nb;            // a reflection may have turned the packet around since it was adopted
+                    P.nz[slot] = p.nzp; P.cp[slot] = p.cosp; P.sp[slot] = p.sinp;
+                    P.ix[slot] = p.inx; P.iy[slot] = p.iny; P.iz[slot] = p.inz; P.dfl[slot] = p.dflags;
+                }
                 park = true;
                 walking = false;
             } else if (r == STEP_EXIT || steps >= kMaxStepsPerPacket) {
@@ -232,7 +256,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
         if (lane == 0) P.cnt[i] += x;
     }
     __syncwarp();
-    if (lane < 12 && P.cnt[lane]) atomicAdd(cnt + lane, P.cnt[lane]);
+    if (lane < CNT_N && lane != CNT_WORK && P.cnt[lane]) atomicAdd(cnt + lane, P.cnt[lane]);
 }
 
 }  // namespace tamc

@@ -29,7 +29,8 @@ constexpr double kTWOPI = 6.283185;
 // against a caller-supplied delta below the ulp of a face coordinate (the reference would spin).
 constexpr int kMaxStepsPerPacket = 1 << 26;
 
-enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_WORK = 12, CNT_N = 16 };
+enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_WORK = 12,
+       CNT_SPECULAR = 13, CNT_REFLECT = 14, CNT_N = 16 };
 
 // Constants of the Henyey-Greenstein draw (stokes.f90:48), formed once on the host.
 struct ScatterConsts {
@@ -48,6 +49,7 @@ struct DevGrid {
     double zcur0;         // zp0 + zmax: every packet starts at this height (inttau2.f90:26)
     int cellk0;           // int(nzg*(zp0+zmax)/(2.*zmax))+1, sourceph.f90:47
     int flags;
+    double n1, n2, r0sq;  // TAMC_FRESNEL: indices outside / inside the grid, ((n1-n2)/(n1+n2))**2
     ScatterConsts sc;
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
@@ -76,6 +78,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c)
 __device__ __forceinline__ double u32_to_unit(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
 struct PhiloxRng {
+    static constexpr bool kHasBoundary = true;
     uint2 key;
     uint32_t id_lo, id_hi, blk;
     __device__ __forceinline__ void seed(uint64_t s, uint64_t packet)
@@ -92,8 +95,31 @@ struct PhiloxRng {
     }
 };
 
+// Boundary decisions (TAMC_FRESNEL) draw from a stream of their own: counter word 3 = 1, draw nb of the packet.
+__device__ __forceinline__ double boundary_draw(uint2 key, uint32_t id_lo, uint32_t id_hi, int &nb)
+{
+    const uint4 r = philox4x32_10(key, make_uint4(id_lo, id_hi, (uint32_t)(nb >> 2), 1u));
+    const int l = nb & 3;
+    ++nb;
+    return u32_to_unit(l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w)));
+}
+
+// Unpolarised Fresnel reflectance going from index n_in to n_out at cosine of incidence ci (1 beyond the
+// critical angle).  Builder-defined extension: the reference has no boundary optics.
+__device__ __forceinline__ double fresnel_reflectance(double n_in, double n_out, double ci)
+{
+    const double ratio = n_in / n_out;
+    const double si2 = (ratio * ratio) * (1. - ci * ci);
+    if (si2 >= 1.) return 1.;
+    const double ct = sqrt(1. - si2);
+    const double rs = (n_in * ci - n_out * ct) / (n_in * ci + n_out * ct);
+    const double rp = (n_in * ct - n_out * ci) / (n_in * ct + n_out * ci);
+    return 0.5 * (rs * rs + rp * rp);
+}
+
 // Replay: the packet's slice of the reference ran2 sequence, consumed in the reference's order.
 struct ReplayRng {
+    static constexpr bool kHasBoundary = false;   // the reference has no boundary optics to replay
     const double *p;
     long long pos, end;
     __device__ __forceinline__ void block(double u[4])
@@ -321,6 +347,39 @@ __device__ __forceinline__ void stokes(const DevGrid &g, Photon &p, double u1, d
     p.nzp = p.cost;
 }
 
+// TAMC_FRESNEL on the exact arithmetic: the packet stands just outside the grid on exactly one axis; decide
+// reflection and, if reflected, put it back like the extended oracle does (position face -+ delta inside, last
+// voxel on that axis, normal cosine flipped, phi rebuilt from the flipped azimuth).
+__device__ __forceinline__ bool fresnel_reflect_exact(const DevGrid &g, const double *xf, const double *yf, const double *zf,
+                                                      Photon &p, uint2 key, uint32_t id_lo, uint32_t id_hi, int &nb)
+{
+    const int out = (p.celli == -1) + (p.cellj == -1) + (p.cellk == -1);
+    if (out != 1) return false;
+    const int a = (p.celli == -1) ? 0 : ((p.cellj == -1) ? 1 : 2);
+    const double na = a == 0 ? p.nxp : (a == 1 ? p.nyp : p.nzp);
+    if (!(boundary_draw(key, id_lo, id_hi, nb) < fresnel_reflectance(g.n2, g.n1, fabs(na)))) return false;
+    double s, c;
+    if (a == 0) {
+        p.xcur = (na > 0.) ? xf[g.nxg] - g.delta : xf[0] + g.delta;
+        p.celli = (na > 0.) ? g.nxg : 1;
+        p.nxp = -p.nxp;
+        sincos(p.phi, &s, &c);
+        p.phi = atan2(s, -c);
+    } else if (a == 1) {
+        p.ycur = (na > 0.) ? yf[g.nyg] - g.delta : yf[0] + g.delta;
+        p.cellj = (na > 0.) ? g.nyg : 1;
+        p.nyp = -p.nyp;
+        sincos(p.phi, &s, &c);
+        p.phi = atan2(-s, c);
+    } else {
+        p.zcur = (na > 0.) ? zf[g.nzg] - g.delta : zf[0] + g.delta;
+        p.cellk = (na > 0.) ? g.nzg : 1;
+        p.nzp = -p.nzp;
+        p.cost = -p.cost;
+    }
+    return true;
+}
+
 __device__ __forceinline__ int exit_face(const Photon &p)
 {
     if (p.celli == -1) return p.nxp > 0. ? 2 : 1;
@@ -332,12 +391,12 @@ __device__ __forceinline__ int exit_face(const Photon &p)
 // Per-thread counters, folded into the global counters once per warp at kernel end.
 struct Counters {
     unsigned long long steps, scatters;
-    unsigned int packets, absorbed, errors, overflow;
+    unsigned int packets, absorbed, errors, overflow, specular, reflections;
     unsigned int exits[6];
     __device__ __forceinline__ void clear()
     {
         steps = scatters = 0ull;
-        packets = absorbed = errors = overflow = 0u;
+        packets = absorbed = errors = overflow = specular = reflections = 0u;
 #pragma unroll
         for (int f = 0; f < 6; ++f) exits[f] = 0u;
     }
@@ -351,6 +410,11 @@ struct Counters {
             for (int i = 0; i < 6; ++i) exits[i] += (f == i + 1);
         }
     }
+    __device__ __forceinline__ void note(int slot)
+    {
+        if (slot == CNT_SPECULAR) specular++;
+        else reflections++;
+    }
     __device__ __forceinline__ void death(int f, int nsteps, int nscatt, bool err)
     {
         steps += (unsigned long long)nsteps;
@@ -360,14 +424,15 @@ struct Counters {
     }
     __device__ __forceinline__ void commit(unsigned long long *g) const
     {
-        unsigned long long v[12] = {packets, steps, scatters, absorbed, exits[0], exits[1], exits[2],
-                                    exits[3], exits[4], exits[5], errors, overflow};
+        unsigned long long v[14] = {packets, steps, scatters, absorbed, exits[0], exits[1], exits[2],
+                                    exits[3], exits[4], exits[5], errors, overflow, specular, reflections};
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
+        for (int i = 0; i < 14; ++i) {
             unsigned long long x = v[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) == 0 && x) atomicAdd(g + i, x);
+            const int slot = i < 12 ? i : i + 1;            // CNT_WORK sits between CNT_OVERFLOW and CNT_SPECULAR
+            if ((threadIdx.x & 31) == 0 && x) atomicAdd(g + slot, x);
         }
     }
 };
@@ -385,14 +450,35 @@ __device__ __forceinline__ void transport_packet(const DevGrid &g, const double 
     launch(g, p, u);
     tally.begin();
     int ndraws = 4, steps = 0, nscatt = 0, fate = 0;
-    for (;;) {
+    int nb = 0;
+    bool specular = false;
+    if constexpr (Rng::kHasBoundary) {
+        if ((g.flags & TAMC_FRESNEL) && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < g.r0sq) {
+            specular = true;                                       // reflected at the top surface before entering
+            fate = 6;
+            ndraws = 3;                                            // the optical depth was never drawn
+            p.nzp = 1.;
+            p.cellk = -1;
+            cnt.specular++;
+        }
+    }
+    while (!specular) {
         const int r = voxel_step(g, xf, yf, zf, p, tally);
         ++steps;
         if (r == STEP_WALL) {
             if (steps >= kMaxStepsPerPacket) { cnt.errors++; break; }
             continue;
         }
-        if (r == STEP_EXIT) { fate = exit_face(p); break; }
+        if (r == STEP_EXIT) {
+            if constexpr (Rng::kHasBoundary) {
+                if ((g.flags & TAMC_FRESNEL) && fresnel_reflect_exact(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb)) {
+                    cnt.reflections++;
+                    continue;
+                }
+            }
+            fate = exit_face(p);
+            break;
+        }
         if (!(g.flags & TAMC_SCATTER)) break;                      // stub: tflag = .true.; exit
         rng.block(u);
         if (u[0] < g.albedo) {

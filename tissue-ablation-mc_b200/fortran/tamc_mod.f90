@@ -14,14 +14,14 @@ module tamc_mod
     implicit none
 
     integer(c_int), parameter :: TAMC_OK = 0
-    integer(c_int), parameter :: TAMC_SCATTER = 1
+    integer(c_int), parameter :: TAMC_SCATTER = 1, TAMC_FRESNEL = 2
 
     !  mirrors tamc_stats (include/tamc.h)
     type, bind(C) :: tamc_stats
         integer(c_int64_t) :: packets, voxel_steps, scatters, absorbed
         integer(c_int64_t) :: exits(6)
         real(c_double)     :: zero_ms, kernel_ms, allreduce_ms, h2d_ms, d2h_ms
-        integer(c_int64_t) :: gpu_launches
+        integer(c_int64_t) :: gpu_launches, specular, internal_reflections
     end type tamc_stats
 
     !  mirrors tamc_heat_params (include/tamc.h): the Heat-module inputs of res/input.params

@@ -7,6 +7,7 @@ import os
 import numpy as np
 
 SCATTER = 1
+FRESNEL = 2
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -37,6 +38,7 @@ class Stats(C.Structure):
         ("zero_ms", C.c_double), ("kernel_ms", C.c_double), ("allreduce_ms", C.c_double),
         ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("gpu_launches", C.c_int64),
+        ("specular", C.c_int64), ("internal_reflections", C.c_int64),
     ]
 
     def as_dict(self):
