@@ -346,7 +346,7 @@ def run_ours(args, cfg, name):
             t2.set_optics(c2["rhokap"](), c2["albedo"], c2["hgg"], flags=c2["flags"])
             if world > 1:
                 t2.set_option("reduce", 0)
-            p2 = 2_000_000
+            p2 = 8_000_000
             s2 = torch.cuda.ExternalStream(t2.stream, device=dev)
             t2.run_async(p2, SEED); t2.sync()
             r2 = timed_steps(t2, s2, p2, 3, world, dist, dev, torch)

@@ -173,6 +173,7 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
 
 // stokes.f90:6-153 as a rotation of the direction vector (see the header comment).
 // u1 -> stokes.f90:24/:48, u2 -> :32/:64, u3 -> the next tauint1 draw (inttau2.f90:36).
+template <bool kSetDir = true>
 __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2);
 
 __device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double u3)
@@ -183,11 +184,12 @@ __device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, do
     p.xcur = (p.xcur - g.xmax) + g.xmax;
     p.ycur = (p.ycur - g.ymax) + g.ymax;
     p.zcur = (p.zcur - g.zmax) + g.zmax;
-    scatter_dir(g, p, u1, u2);
+    scatter_dir<true>(g, p, u1, u2);
 }
 
 // The direction part of a scattering event: reads and writes nxp,nyp,nzp, sint,cosp,sinp, the
-// reciprocals and dflags of `p`; position and optical depths are untouched.
+// reciprocals and dflags of `p` (the last two only with kSetDir); position and optical depths are untouched.
+template <bool kSetDir>
 __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2)
 {
     const ScatterConsts &sc = g.sc;
@@ -199,7 +201,7 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
         p.nxp = p.sint * p.cosp;
         p.nyp = p.sint * p.sinp;
         p.nzp = cost;
-        set_direction(p);
+        if (kSetDir) set_direction(p);
         return;
     }
     const double q = sc.one_m_g2 * __drcp_rn(sc.one_m_g + sc.two_g * u1);   // stokes.f90:48
@@ -232,7 +234,7 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
     p.nxp = p.sint * p.cosp;                                            // stokes.f90:143-148
     p.nyp = p.sint * p.sinp;
     p.nzp = uz;
-    set_direction(p);
+    if (kSetDir) set_direction(p);
 }
 
 // TAMC_FRESNEL on the production arithmetic.  After STEP_EXIT exactly one index is out of range (only the

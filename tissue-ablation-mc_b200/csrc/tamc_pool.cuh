@@ -29,11 +29,10 @@ constexpr int kPool = 64;
 struct WarpPool {
     double px[kPool], py[kPool], pz[kPool];           // position (shifted frame)
     double nz[kPool], st[kPool], cp[kPool], sp[kPool]; // cost, sint, cos(phi), sin(phi)
-    double ix[kPool], iy[kPool], iz[kPool];           // reciprocal direction cosines
     double tau[kPool], pval[kPool];                   // optical depth to the next interaction; pending deposit
     int cells[kPool], cellk[kPool];                   // celli | cellj << 16 ; cellk
-    int ridx[kPool], jidx[kPool], pidx[kPool];
-    int steps[kPool], nscat[kPool], dfl[kPool], nbnd[kPool];
+    int pidx[kPool];
+    int steps[kPool], nscat[kPool], nbnd[kPool];
     unsigned int idlo[kPool], idhi[kPool];
     unsigned char wq[kPool], iq[kPool], fq[kPool];    // walk / interact / free queues (stacks of slot numbers)
     unsigned char pad[64];
@@ -100,11 +99,9 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                     FastPhoton q;
                     q.nzp = P.nz[s]; q.sint = P.st[s]; q.cosp = P.cp[s]; q.sinp = P.sp[s];
                     q.nxp = q.sint * q.cosp; q.nyp = q.sint * q.sinp;
-                    q.xcur = q.ycur = q.zcur = 0.;            // the position stays parked in the slot
-                    q.inx = P.ix[s]; q.iny = P.iy[s]; q.inz = P.iz[s]; q.dflags = P.dfl[s];
-                    scatter_dir(g, q, u32_to_unit(r.y), u32_to_unit(r.z));
+                    // the position stays parked in the slot; the walker re-derives reciprocals and indices
+                    scatter_dir<false>(g, q, u32_to_unit(r.y), u32_to_unit(r.z));
                     P.nz[s] = q.nzp; P.st[s] = q.sint; P.cp[s] = q.cosp; P.sp[s] = q.sinp;
-                    P.ix[s] = q.inx; P.iy[s] = q.iny; P.iz[s] = q.inz; P.dfl[s] = q.dflags;
                     P.tau[s] = -log(u32_to_unit(r.w));
                     P.nscat[s] = ns + 1;
                     survive = true;
@@ -149,9 +146,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                     const Launched L = launch_fast(g, u, true);
                     P.px[s] = L.xcur; P.py[s] = L.ycur; P.pz[s] = lc.zcur0;
                     P.nz[s] = -1.; P.st[s] = 0.; P.cp[s] = L.cosp; P.sp[s] = L.sinp;   // sourceph.f90:37-42
-                    P.ix[s] = 0.; P.iy[s] = 0.; P.iz[s] = -1.; P.dfl[s] = 4 | 8 | 16;
                     P.tau[s] = L.tau; P.pval[s] = 0.; P.pidx[s] = -1;
-                    P.cells[s] = L.cells; P.cellk[s] = lc.cellk0; P.ridx[s] = L.ridx; P.jidx[s] = L.jidx;
+                    P.cells[s] = L.cells; P.cellk[s] = lc.cellk0;
                     P.steps[s] = 0; P.nscat[s] = 0; P.nbnd[s] = 0;
                     P.idlo[s] = (uint32_t)gid; P.idhi[s] = (uint32_t)(gid >> 32);
                     P.wq[nw + lane] = (unsigned char)s;
@@ -174,11 +170,12 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 const double st = P.st[slot];
                 p.nxp = st * P.cp[slot]; p.nyp = st * P.sp[slot];                      // stokes.f90:143-148
                 if (kFresnel) { p.sint = st; p.cosp = P.cp[slot]; p.sinp = P.sp[slot]; }
-                p.inx = P.ix[slot]; p.iny = P.iy[slot]; p.inz = P.iz[slot]; p.dflags = P.dfl[slot];
+                set_direction(p);                                                     // reciprocals + sign flags
                 p.tau = P.tau[slot]; p.taurun = 0.;
                 const int c = P.cells[slot];
                 p.celli = c & 0xffff; p.cellj = c >> 16; p.cellk = P.cellk[slot];
-                p.ridx = P.ridx[slot]; p.jidx = P.jidx[slot];
+                p.ridx = p.celli + g.sx * (p.cellj + (g.nyg + 2) * p.cellk);
+                p.jidx = (p.celli - 1) + g.nxg * ((p.cellj - 1) + g.nyg * (p.cellk - 1));
                 tally.pidx = P.pidx[slot]; tally.pval = P.pval[slot];
                 steps = P.steps[slot];
                 if (kFresnel) nb = P.nbnd[slot];
@@ -215,13 +212,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 P.py[slot] = (p.ycur - g.ymax) + g.ymax;
                 P.pz[slot] = (p.zcur - g.zmax) + g.zmax;
                 P.cells[slot] = p.celli | (p.cellj << 16); P.cellk[slot] = p.cellk;
-                P.ridx[slot] = p.ridx; P.jidx[slot] = p.jidx;
                 P.pidx[slot] = tally.pidx; P.pval[slot] = tally.pval;
                 P.steps[slot] = steps;
                 if (kFresnel) {
                     P.nbnd[slot] = nb;            // a reflection may have turned the packet around since it was adopted
                     P.nz[slot] = p.nzp; P.cp[slot] = p.cosp; P.sp[slot] = p.sinp;
-                    P.ix[slot] = p.inx; P.iy[slot] = p.iny; P.iz[slot] = p.inz; P.dfl[slot] = p.dflags;
                 }
                 park = true;
                 walking = false;
