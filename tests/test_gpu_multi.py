@@ -66,3 +66,55 @@ def test_allreduce_equals_single_gpu(tmp_path):
         t.run_async(40000, 99, call * 40000)
         compare_grids(a[call], t.get_jmean(), rtol=1e-9, dep_scale=voxel_tau(cfg, rk))
     t.close()
+
+
+def _coupled_worker(rank, world, port, out):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "tissue-ablation-mc_b200")]
+    import torch
+    import torch.distributed as dist
+
+    import tamc
+    from tamc import dist as tdist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n = 24
+    t = tamc.MCTransport(n, n, n, 0.03, 0.03, 0.06, device=rank)
+    t.set_optics(tamc.gridset(0.03, 0.03, 0.06, n, n, n, 680.0)[3], 0.0, 0.9)
+    t.comm_init(world, rank, tdist.broadcast_unique_id(tamc.comm_unique_id, dist))
+    t.heat_init(pulsetype="tophat", power=20.0, energyPerPixel=4000.0, ablateTemp=150.0, loops=2)
+    it, pk = t.coupled_loop(10000, 5, 12)             # 10 000 packets per rank per call, tally all-reduced
+    assert it == 12 and pk == 12 * 10000 * world
+    np.save(f"{out}.{rank}.npy", np.stack([t.heat_array("temp"), t.heat_array("rhokap")]))
+    dist.barrier()
+    t.close()
+    dist.destroy_process_group()
+
+
+def test_coupled_loop_two_ranks_equals_one_rank_with_all_packets(tmp_path):
+    """Every rank repeats the (deterministic) heat step on the all-reduced tally: both replicas stay identical and
+    equal one GPU that runs all the packets itself."""
+    import torch
+
+    import tamc
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "heat")
+    mp.spawn(_coupled_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = np.load(out + ".0.npy"), np.load(out + ".1.npy")
+    assert np.array_equal(a, b)
+    n = 24
+    t = tamc.MCTransport(n, n, n, 0.03, 0.03, 0.06, device=0)
+    t.set_optics(tamc.gridset(0.03, 0.03, 0.06, n, n, n, 680.0)[3], 0.0, 0.9)
+    t.heat_init(pulsetype="tophat", power=20.0, energyPerPixel=4000.0, ablateTemp=150.0, loops=2)
+    t.coupled_loop(20000, 5, 12)                      # same ids 0..20000 per call on one GPU
+    assert np.allclose(t.heat_array("temp"), a[0], rtol=1e-9, atol=0)
+    assert np.array_equal(t.heat_array("rhokap") == 0, a[1] == 0)
+    t.close()
