@@ -8,6 +8,7 @@
 import numpy as np
 import pytest
 
+from oracle import oracle as orc
 from tests.util import compare_grids, compare_records, make_oracle, make_transport, voxel_tau
 
 pytestmark = pytest.mark.gpu
@@ -308,3 +309,40 @@ def test_fresnel_not_replayable():
         t.run_replay(np.array([0, 4]), np.full(4, 0.5))
     assert e.value.code == 1
     t.close()
+
+
+def test_chi_square_full_size_layered_skin_200():
+    """BASELINE config 3 at its full grid size: 16 x 250 000 packets on the device against 16 emulated MPI ranks x 250 000
+    packets of the oracle on the reference's ran2 streams (host threads).  Per-voxel variance from the device batches
+    (the same under the null hypothesis); z per voxel, chi-square over the well-populated voxels, 3-sigma fraction."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["skin200"]
+    K, per = 16, 250000
+    rk = cfg["rhokap"]()
+    ref = orc.run_ranks(K, 200, 200, 200, cfg["xmax"], cfg["ymax"], cfg["zmax"], rk, cfg["albedo"], cfg["hgg"], per,
+                        flags=cfg["flags"])
+    t = make_transport(cfg, rk)
+    s1 = np.zeros((200, 200, 200), order="F")
+    s2 = np.zeros_like(s1)
+    steps = scat = 0
+    for b in range(K):
+        t.run_async(per, SEED, b * per)
+        j = t.get_jmean()
+        st = t.get_stats()
+        steps += st["voxel_steps"]
+        scat += st["scatters"]
+        s1 += j
+        s2 += j * j
+    t.close()
+    mean = s1 / K
+    var = (s2 / K - mean * mean) * K / (K - 1)
+    sel = (mean > 50.0) & (var > 0)                      # voxels with several hundred deposits per batch
+    z = (ref["jmean"][sel] / K - mean[sel]) / np.sqrt(2.0 * var[sel] / K)
+    assert z.size > 2000
+    chi2 = float((z ** 2).mean())
+    # the variance is itself estimated from 16 batches: E[z^2] = (K-1)/(K-3) = 1.15
+    assert abs(chi2 - 1.15) < 0.12, (chi2, z.size)
+    assert (np.abs(z) > 3).mean() < 0.02 and abs(z.mean()) < 5 / np.sqrt(z.size)
+    assert abs(steps / ref["stats"]["voxel_steps"] - 1) < 0.01 and abs(scat / ref["stats"]["scatters"] - 1) < 0.01
+    assert abs(s1.sum() / ref["jmean"].sum() - 1) < 0.01
