@@ -135,3 +135,41 @@ def test_replay_phantom400_subset():
     import tamc
 
     _replay_case(tamc.configs.CONFIGS["phantom400"], 300, rank=2, cap_per_packet=60000)
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (3, 5, 7), (17, 4, 33)])
+def test_replay_non_cubic_and_degenerate_grids(dims):
+    """nxg != nyg != nzg (the reference fixes 80^3 at compile time; the library takes any box) and the one-voxel grid."""
+    import tamc
+    from oracle import oracle as orc
+
+    nx, ny, nz = dims
+    xmax, ymax, zmax = 0.02, 0.03, 0.05
+    rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+    ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    rk[1:-1, 1:-1, 1:-1] = 15.0 + 4.0 * ((ii + 2 * jj + 3 * kk) % 5)
+    npk = 20000
+    o = orc.Oracle(nx, ny, nz, xmax, ymax, zmax)
+    o.set_rhokap(rk)
+    o.set_optics(0.9, 0.6)
+    o.set_flags(orc.FLAG_SCATTER)
+    o.seed_ran2(9)
+    out = o.run(npk, records=True, draws_cap=npk * 400)
+    t = tamc.MCTransport(nx, ny, nz, xmax, ymax, zmax)
+    t.set_optics(rk, 0.9, 0.6, flags=tamc.SCATTER)
+    rec, jm = t.run_replay(out["offsets"], out["draws"])
+    scale = {"xp": xmax, "yp": ymax, "zp": zmax, "nxp": 1.0, "nyp": 1.0, "nzp": 1.0}
+    compare_records(rec, out["records"], scale=scale)
+    cfgish = dict(n=max(dims), xmax=xmax, ymax=ymax, zmax=zmax)
+    compare_grids(jm, o.jmean, rtol=1e-6, dep_scale=voxel_tau(cfgish, rk))
+    # production kernels on the same box: counters conserve packets, every variant agrees with the others
+    grids = []
+    for variant in (0, 1, 2, 3):
+        t.set_option("variant", variant)
+        t.run_async(npk, 3, 0)
+        grids.append(t.get_jmean())
+        st = t.get_stats()
+        assert st["packets"] == npk == st["absorbed"] + sum(st["exits"])
+    for g in grids[1:]:
+        compare_grids(g, grids[0], rtol=2e-2, dep_scale=voxel_tau(cfgish, rk), sum_rtol=1e-5)
+    t.close()
