@@ -414,14 +414,14 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long lon
         if (cfg.block <= 128) {   // 0 = auto: 128 threads, 5 CTAs per SM
             LaunchCfg c2 = cfg;
             c2.block = 128;
-            const size_t qsmem = smem + 4 * sizeof(WarpPool);
+            const size_t qsmem = ((smem + 15) & ~(size_t)15) + 4 * sizeof(WarpPool);
             if (g.flags & TAMC_FRESNEL)
                 return launch_sized(k_transport_pool<128, 5, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
             return launch_sized(k_transport_pool<128, 5, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
         }
         LaunchCfg c2 = cfg;
         c2.block = 256;
-        const size_t qsmem = smem + 8 * sizeof(WarpPool);
+        const size_t qsmem = ((smem + 15) & ~(size_t)15) + 8 * sizeof(WarpPool);
         if (g.flags & TAMC_FRESNEL)
             return launch_sized(k_transport_pool<256, 2, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
         return launch_sized(k_transport_pool<256, 2, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);

@@ -26,14 +26,22 @@ namespace tamc {
 
 constexpr int kPool = 64;
 
-struct WarpPool {
-    double px[kPool], py[kPool], pz[kPool];           // position (shifted frame)
-    double nz[kPool], st[kPool], cp[kPool], sp[kPool]; // cost, sint, cos(phi), sin(phi)
-    double tau[kPool], pval[kPool];                   // optical depth to the next interaction; pending deposit
-    int cells[kPool], cellk[kPool];                   // celli | cellj << 16 ; cellk
-    int pidx[kPool];
-    int steps[kPool], nscat[kPool], nbnd[kPool];
-    unsigned int idlo[kPool], idhi[kPool];
+// One parked packet: seven 16-byte groups, each moved with a single 128-bit shared-memory access.  With the
+// lanes of a warp touching unrelated slots, 16-byte accesses keep the bank conflicts of the pool traffic
+// close to the bandwidth minimum (the slot stride of 28 words spreads consecutive slots over the bank groups).
+struct alignas(16) PoolSlot {
+    double2 pos_xy;                          // g0: position (shifted frame)
+    double2 pz_pval;                         // g1: z position; pending deposit
+    double2 nz_st;                           // g2: cost, sint
+    double2 cp_sp;                           // g3: cos(phi), sin(phi)
+    int4 tau_ns_nb;                          // g4: tau (lo, hi), scatter count, boundary draws used
+    int4 pidx_steps_cells;                   // g5: pending-deposit voxel, voxel-steps, celli | cellj << 16, cellk
+    uint4 id;                                // g6: packet id (lo, hi)
+};
+static_assert(sizeof(PoolSlot) == 112, "seven 16-byte groups");
+
+struct alignas(16) WarpPool {
+    PoolSlot slot[kPool];
     unsigned char wq[kPool], iq[kPool], fq[kPool];    // walk / interact / free queues (stacks of slot numbers)
     unsigned char pad[64];
     unsigned long long cnt[CNT_N];
@@ -48,7 +56,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
     extern __shared__ double s_faces[];
     const double *xf, *yf, *zf;
     stage_faces(g, s_faces, xf, yf, zf);
-    const int nfaces = g.nxg + g.nyg + g.nzg + 3;
+    const int nfaces = (g.nxg + g.nyg + g.nzg + 3 + 1) & ~1;           // keep the pools 16-byte aligned
     WarpPool &P = reinterpret_cast<WarpPool *>(s_faces + nfaces)[threadIdx.x >> 5];
 
     const unsigned full = 0xffffffffu;
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
     MergeTally32 tally;
     tally.jm = g.jmean;
     tally.begin();
-    int steps = 0, nb = 0;
+    int steps = 0, nb = 0, nscat_reg = 0;
     bool doa = false;                        // dead on arrival: specularly reflected at the surface (TAMC_FRESNEL)
     constexpr bool fresnel = kFresnel;
     // per-lane accumulators, folded into the warp's counters at the end
@@ -93,23 +101,30 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
             bool survive = false, absorbed = false;
             if (lane < k) {
                 s = P.iq[ni - 1 - lane];
-                const int ns = P.nscat[s];
-                const uint4 r = philox4x32_10(key, make_uint4(P.idlo[s], P.idhi[s], (uint32_t)ns + 1u, 0u));
+                PoolSlot &S = P.slot[s];
+                int4 g4 = S.tau_ns_nb;
+                const int ns = g4.z;
+                const uint4 id = S.id;
+                const uint4 r = philox4x32_10(key, make_uint4(id.x, id.y, (uint32_t)ns + 1u, 0u));
                 if (u32_to_unit(r.x) < g.albedo) {            // draw < albedo ? stokes : absorbed
                     FastPhoton q;
-                    q.nzp = P.nz[s]; q.sint = P.st[s]; q.cosp = P.cp[s]; q.sinp = P.sp[s];
+                    const double2 a = S.nz_st, b = S.cp_sp;
+                    q.nzp = a.x; q.sint = a.y; q.cosp = b.x; q.sinp = b.y;
                     q.nxp = q.sint * q.cosp; q.nyp = q.sint * q.sinp;
                     // the position stays parked in the slot; the walker re-derives reciprocals and indices
                     scatter_dir<false>(g, q, u32_to_unit(r.y), u32_to_unit(r.z));
-                    P.nz[s] = q.nzp; P.st[s] = q.sint; P.cp[s] = q.cosp; P.sp[s] = q.sinp;
-                    P.tau[s] = -log(u32_to_unit(r.w));
-                    P.nscat[s] = ns + 1;
+                    S.nz_st = make_double2(q.nzp, q.sint);
+                    S.cp_sp = make_double2(q.cosp, q.sinp);
+                    const double tau = -log(u32_to_unit(r.w));
+                    g4.x = __double2loint(tau); g4.y = __double2hiint(tau); g4.z = ns + 1;
+                    S.tau_ns_nb = g4;
                     survive = true;
                 } else {
                     absorbed = true;
-                    const double pv = P.pval[s];
-                    if (pv != 0.) atomicAdd(g.jmean + P.pidx[s], pv);
-                    acc_steps += (unsigned long long)P.steps[s];
+                    const double pv = S.pz_pval.y;
+                    const int4 g5 = S.pidx_steps_cells;
+                    if (pv != 0.) atomicAdd(g.jmean + g5.x, pv);
+                    acc_steps += (unsigned long long)g5.y;
                     acc_scat += (unsigned long long)ns;
                     acc_pk++;
                     acc_abs++;
@@ -144,12 +159,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                     double u[4];
                     lr.block(u);
                     const Launched L = launch_fast(g, u, true);
-                    P.px[s] = L.xcur; P.py[s] = L.ycur; P.pz[s] = lc.zcur0;
-                    P.nz[s] = -1.; P.st[s] = 0.; P.cp[s] = L.cosp; P.sp[s] = L.sinp;   // sourceph.f90:37-42
-                    P.tau[s] = L.tau; P.pval[s] = 0.; P.pidx[s] = -1;
-                    P.cells[s] = L.cells; P.cellk[s] = lc.cellk0;
-                    P.steps[s] = 0; P.nscat[s] = 0; P.nbnd[s] = 0;
-                    P.idlo[s] = (uint32_t)gid; P.idhi[s] = (uint32_t)(gid >> 32);
+                    PoolSlot &S = P.slot[s];
+                    S.pos_xy = make_double2(L.xcur, L.ycur);
+                    S.pz_pval = make_double2(lc.zcur0, 0.);
+                    S.nz_st = make_double2(-1., 0.);                                       // sourceph.f90:37-42
+                    S.cp_sp = make_double2(L.cosp, L.sinp);
+                    S.tau_ns_nb = make_int4(__double2loint(L.tau), __double2hiint(L.tau), 0, 0);
+                    S.pidx_steps_cells = make_int4(-1, 0, L.cells, lc.cellk0);
+                    S.id = make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), 0u, 0u);
                     P.wq[nw + lane] = (unsigned char)s;
                 }
                 nf -= k;
@@ -165,22 +182,24 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
             const int k = min(nempty, nw);
             if (!walking && rank < k) {
                 slot = P.wq[nw - 1 - rank];
-                p.xcur = P.px[slot]; p.ycur = P.py[slot]; p.zcur = P.pz[slot];
-                p.nzp = P.nz[slot];
-                const double st = P.st[slot];
-                p.nxp = st * P.cp[slot]; p.nyp = st * P.sp[slot];                      // stokes.f90:143-148
-                if (kFresnel) { p.sint = st; p.cosp = P.cp[slot]; p.sinp = P.sp[slot]; }
+                const PoolSlot &S = P.slot[slot];
+                const double2 g0 = S.pos_xy, g1 = S.pz_pval, g2 = S.nz_st, g3 = S.cp_sp;
+                const int4 g4 = S.tau_ns_nb, g5 = S.pidx_steps_cells;
+                p.xcur = g0.x; p.ycur = g0.y; p.zcur = g1.x;
+                p.nzp = g2.x;
+                p.nxp = g2.y * g3.x; p.nyp = g2.y * g3.y;                              // stokes.f90:143-148
+                if (kFresnel) { p.sint = g2.y; p.cosp = g3.x; p.sinp = g3.y; }
                 set_direction(p);                                                     // reciprocals + sign flags
-                p.tau = P.tau[slot]; p.taurun = 0.;
-                const int c = P.cells[slot];
-                p.celli = c & 0xffff; p.cellj = c >> 16; p.cellk = P.cellk[slot];
+                p.tau = __hiloint2double(g4.y, g4.x); p.taurun = 0.;
+                nscat_reg = g4.z;
+                p.celli = g5.z & 0xffff; p.cellj = g5.z >> 16; p.cellk = g5.w;
                 p.ridx = p.celli + g.sx * (p.cellj + (g.nyg + 2) * p.cellk);
                 p.jidx = (p.celli - 1) + g.nxg * ((p.cellj - 1) + g.nyg * (p.cellk - 1));
-                tally.pidx = P.pidx[slot]; tally.pval = P.pval[slot];
-                steps = P.steps[slot];
-                if (kFresnel) nb = P.nbnd[slot];
+                tally.pidx = g5.x; tally.pval = g1.y;
+                steps = g5.y;
+                if (kFresnel) nb = g4.w;
                 walking = true;
-                if (fresnel && nb == 0 && boundary_draw(key, P.idlo[slot], P.idhi[slot], nb) < g.r0sq) {
+                if (fresnel && nb == 0 && boundary_draw(key, S.id.x, S.id.y, nb) < g.r0sq) {
                     walking = false;                      // fresh packet reflected at the top surface: never enters
                     doa = true;
                 }
@@ -202,28 +221,27 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
         } else if (walking) {
             int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
             ++steps;
-            if (fresnel && r == STEP_EXIT && fresnel_reflect_fast(g, xf, yf, zf, p, key, P.idlo[slot], P.idhi[slot], nb)) {
+            if (fresnel && r == STEP_EXIT && fresnel_reflect_fast(g, xf, yf, zf, p, key, P.slot[slot].id.x, P.slot[slot].id.y, nb)) {
                 atomicAdd(&P.cnt[CNT_REFLECT], 1ull);
                 r = STEP_WALL;
             }
             if (r == STEP_INTERACT) {
                 // the centred-position round trip of inttau2.f90:65-67 / :24-26
-                P.px[slot] = (p.xcur - g.xmax) + g.xmax;
-                P.py[slot] = (p.ycur - g.ymax) + g.ymax;
-                P.pz[slot] = (p.zcur - g.zmax) + g.zmax;
-                P.cells[slot] = p.celli | (p.cellj << 16); P.cellk[slot] = p.cellk;
-                P.pidx[slot] = tally.pidx; P.pval[slot] = tally.pval;
-                P.steps[slot] = steps;
-                if (kFresnel) {
-                    P.nbnd[slot] = nb;            // a reflection may have turned the packet around since it was adopted
-                    P.nz[slot] = p.nzp; P.cp[slot] = p.cosp; P.sp[slot] = p.sinp;
+                PoolSlot &S = P.slot[slot];
+                S.pos_xy = make_double2((p.xcur - g.xmax) + g.xmax, (p.ycur - g.ymax) + g.ymax);
+                S.pz_pval = make_double2((p.zcur - g.zmax) + g.zmax, tally.pval);
+                S.pidx_steps_cells = make_int4(tally.pidx, steps, p.celli | (p.cellj << 16), p.cellk);
+                if (kFresnel) {                   // a reflection may have turned the packet around since it was adopted
+                    S.tau_ns_nb = make_int4(0, 0, nscat_reg, nb);
+                    S.nz_st = make_double2(p.nzp, p.sint);
+                    S.cp_sp = make_double2(p.cosp, p.sinp);
                 }
                 park = true;
                 walking = false;
             } else if (r == STEP_EXIT || steps >= kMaxStepsPerPacket) {
                 tally.flush();
                 acc_steps += (unsigned long long)steps;
-                acc_scat += (unsigned long long)P.nscat[slot];
+                acc_scat += (unsigned long long)nscat_reg;
                 acc_pk++;
                 if (r == STEP_EXIT) atomicAdd(&P.cnt[CNT_EXIT0 + exit_face_fast(p, g) - 1], 1ull);
                 else { atomicAdd(&P.cnt[CNT_ERRORS], 1ull); acc_abs++; }
