@@ -254,6 +254,8 @@ extern "C" int tamc_set_optics(tamc_handle h, const double *rhokap, double albed
             CU(cudaMemcpy(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice));
         }
         CU(cudaEventRecord(h->ev[EV_H1], h->stream));
+        // the caller may rewrite rhokap as soon as this returns (no host pointer is kept past the call)
+        CU(cudaStreamSynchronize(h->stream));
         h->timed_h2d = true;
     }
     h->albedo = albedo; h->hgg = hgg; h->n1 = n1; h->n2 = n2; h->flags = flags;
