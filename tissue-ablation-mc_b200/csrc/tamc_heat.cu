@@ -6,9 +6,10 @@
 //
 //   (in k_heat_step)   mcpolar.f90:174        jmeanGLOBAL *= (getPwr()/81)/(nphotons*numproc*Vvoxel)
 //   k_heat_step        3dFD.f90:113-186       FTCS 7-point stencil with variable kappa/rho/c, boiling sink
-//   k_arrhenius        3dFD.f90:424-466
-//   k_water .. k_air   3dFD.f90:312-361       setupThermalCoeff, incl. its sweep-order "six neighbours
-//                                             ablated" rule, solved as a fixed point (see k_rule)
+//   k_post             3dFD.f90:424-466 + :327-345   Arrhenius + the voxel-local half of setupThermalCoeff
+//   k_rule_air         3dFD.f90:347-357       the sweep-order "six neighbours ablated" rule (first pass of a
+//                                             fixed point, see k_rule) + air properties; k_rule / k_air finish
+//                                             the rare cases that need more passes
 // Single-rank semantics (numproc = 1) of heat_sim_3D; with several ranks every GPU repeats the same
 // deterministic step on its own replica (the tally it consumes is already all-reduced), so no exchange
 // is needed.  Compiled with -fmad=false: the arithmetic is the oracle's, operation for operation
@@ -45,7 +46,7 @@ struct tamc_heat {
     int loops = 1, pulsesToDo = 1, pulsesDone = 0, pulsetype = 1, counter = 0;
     // device arrays
     double *coeff = nullptr, *kappa = nullptr, *density = nullptr, *heatcap = nullptr, *alpha = nullptr;   // (0:n+1)^3
-    double *temp = nullptr, *tn = nullptr, *cand = nullptr, *cand2 = nullptr, *cand3 = nullptr;               // (0:n+1)^3
+    double *temp = nullptr, *tn = nullptr, *cand = nullptr, *cand2 = nullptr, *cand3 = nullptr, *rk_new = nullptr;  // (0:n+1)^3
     double *water = nullptr, *Q = nullptr, *tissue = nullptr, *thres = nullptr;                              // n^3 (thres: 3 n^3)
     int *flags = nullptr;                                                                                     // [0] changed, [1] negative temperature
 };
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) k_heat_step(int n, const double *__restri
                                                    const double *__restrict__ kappa, const double *__restrict__ density,
                                                    const double *__restrict__ heatcap, const double *__restrict__ coeff,
                                                    const double *__restrict__ jmean, double *__restrict__ Q,
-                                                   double dx, double dy, double dz, double delt, double laserOn,
+                                                   double inv_dx2, double inv_dy2, double inv_dz2, double delt, double laserOn,
                                                    double volumeVoxel, double massVoxel, double QVapor, double jscale,
                                                    int *__restrict__ flags)
 {
@@ -88,18 +89,19 @@ __global__ void __launch_bounds__(256) k_heat_step(int n, const double *__restri
     const size_t qi = (size_t)(i - 1) + (size_t)n * ((size_t)(j - 1) + (size_t)n * (size_t)(k - 1));
     const double kc = kappa[c], dc = density[c], hc = heatcap[c], tc = t0[c];
 
-    auto second_derivative = [&](size_t s, double h) {
+    // inv_h2 = 1.d0/dz**2 etc. (3dFD.f90:131-132), formed once on the host: the same IEEE quotient
+    auto second_derivative = [&](size_t s, double inv_h2) {
         const double kappaPlusHalf = .5 * (kc + kappa[c + s]), kappaMinHalf = .5 * (kc + kappa[c - s]);
         const double densityPlusHalf = .5 * (dc + density[c + s]), densityMinHalf = .5 * (dc + density[c - s]);
         const double heatcapPlusHalf = .5 * (hc + heatcap[c + s]), heatcapMinHalf = .5 * (hc + heatcap[c - s]);
-        const double a = 0.5 * (kappaMinHalf / (densityMinHalf * heatcapMinHalf)) * (1. / (h * h));
-        const double d = 0.5 * (kappaPlusHalf / (densityPlusHalf * heatcapPlusHalf)) * (1. / (h * h));
+        const double a = 0.5 * (kappaMinHalf / (densityMinHalf * heatcapMinHalf)) * inv_h2;
+        const double d = 0.5 * (kappaPlusHalf / (densityPlusHalf * heatcapPlusHalf)) * inv_h2;
         const double b = 0.5 * (a + d);
         return a * t0[c - s] - 2. * b * tc + d * t0[c + s];
     };
-    const double u_zz = second_derivative(sz, dz);
-    const double u_yy = second_derivative(sy, dy);
-    const double u_xx = second_derivative(sx, dx);
+    const double u_zz = second_derivative(sz, inv_dz2);
+    const double u_yy = second_derivative(sy, inv_dy2);
+    const double u_xx = second_derivative(sx, inv_dx2);
 
     const double jv = jmean[qi] * jscale;          // mcpolar.f90:174 applied on the fly: the resident tally stays unscaled
     const double tempIncrease = delt * (u_xx + u_yy + u_zz);
@@ -119,61 +121,6 @@ __global__ void __launch_bounds__(256) k_heat_step(int n, const double *__restri
         if (tc < 0.) flags[1] = 1;                                // :179-182 (mpi_abort upstream)
     }
     tn[c] = out;
-}
-
-// 3dFD.f90:424-466
-__global__ void __launch_bounds__(256) k_arrhenius(int n, const double *__restrict__ temp, const double *__restrict__ rhokap,
-                                                   double *__restrict__ tissue, double *__restrict__ thres, double delt, double time)
-{
-    int i, j, k;
-    if (!voxel_of_thread(n, i, j, k)) return;
-    const size_t c = h3(n, i, j, k), ni = (size_t)n * n * n;
-    const size_t q = (size_t)(i - 1) + (size_t)n * ((size_t)(j - 1) + (size_t)n * (size_t)(k - 1));
-    const double A = 3.1e98, dE = 6.3e5, R = 8.314;
-    const double T = temp[c];
-    double ts = tissue[q];
-    if (T >= 43. + 273. && T < 100. + 273. && rhokap[c] >= 0.) {
-        ts = ts + delt * A * exp(-dE / (R * T));
-        tissue[q] = ts;
-    }
-    if (thres[q] == 0. && ts >= .53) thres[q] = time;
-    else if (thres[q + ni] == 0. && ts >= 1.) thres[q + ni] = time;
-    else if (thres[q + 2 * ni] == 0. && ts >= 10000.) thres[q + 2 * ni] = time;
-}
-
-// setupThermalCoeff, first half (3dFD.f90:327-345): water content, then the voxel-local update.
-// The candidate opacity goes to `cand`; rhokap itself still holds the previous call's values, which the
-// sweep-order rule needs for the neighbours "ahead" of a voxel.
-__global__ void __launch_bounds__(256) k_local(int n, const double *__restrict__ temp, const double *__restrict__ rhokap,
-                                               double *__restrict__ cand, double *__restrict__ water, const double *__restrict__ Q,
-                                               double *__restrict__ density, double *__restrict__ heatcap, double *__restrict__ kappa,
-                                               double *__restrict__ coeff, double QVapor, double ablateTemp, double delt)
-{
-    int i, j, k;
-    if (!voxel_of_thread(n, i, j, k)) return;
-    const size_t c = h3(n, i, j, k);
-    const size_t q = (size_t)(i - 1) + (size_t)n * ((size_t)(j - 1) + (size_t)n * (size_t)(k - 1));
-    // getWaterContent, thermalConst_mod.f90:46-56
-    double w = kWaterInit - kWaterInit * (Q[q] / QVapor);
-    w = w < kWaterInit ? w : kWaterInit;
-    const double wc = water[q];
-    w = w < wc ? w : wc;
-    w = w > 0.0 ? w : 0.0;
-    water[q] = w;
-
-    double rk = rhokap[c];
-    if (temp[c] >= ablateTemp + 273.) {
-        rk = 0.;
-    } else if (rk > 0.) {
-        const double rho = skinDensity(w);
-        density[c] = rho;
-        rk = w * 510. + 170.;                                    // watercontent*mu_water + mu_protein, ch_opt.f90:17-18
-        const double hcap = skinHeatCap(w);
-        heatcap[c] = hcap;
-        kappa[c] = skinThermalCond(w, rho);
-        coeff[c] = delt / (rho * hcap);
-    }
-    cand[c] = rk;
 }
 
 // The "remove tissue whose six neighbours are ablated" rule (3dFD.f90:347-353) is evaluated upstream
@@ -197,15 +144,6 @@ __global__ void __launch_bounds__(256) k_rule(int n, const double *__restrict__ 
     next[c] = v;
 }
 
-__global__ void __launch_bounds__(256) k_clamp(int n, const double *__restrict__ local, double *__restrict__ out)
-{
-    int i, j, k;
-    if (!voxel_of_thread(n, i, j, k)) return;
-    const size_t c = h3(n, i, j, k);
-    const double v = local[c];
-    out[c] = v <= 0.01 ? 0. : v;
-}
-
 // setupThermalCoeff, last part (3dFD.f90:350-357): store the final opacity; air properties where it is zero
 __global__ void __launch_bounds__(256) k_air(int n, const double *__restrict__ fin, const double *__restrict__ temp,
                                              double *__restrict__ rhokap, double *__restrict__ density, double *__restrict__ heatcap,
@@ -216,6 +154,84 @@ __global__ void __launch_bounds__(256) k_air(int n, const double *__restrict__ f
     const size_t c = h3(n, i, j, k);
     const double v = fin[c];
     rhokap[c] = v;
+    if (v <= 0.01) {
+        const double T = temp[c];
+        const double rho = airDensity(T);
+        density[c] = rho;
+        heatcap[c] = 1.006e3;
+        const double kap = airThermalCond(T);
+        kappa[c] = kap;
+        alpha[c] = kap / (rho * 1.006e3);
+        coeff[c] = delt / (airDensity(T) * 1.006e3);
+    }
+}
+
+// ---- fused passes (the common path of tamc_heat_step) --------------------------------------------------------
+// k_post = Arrhenius + the voxel-local half of setupThermalCoeff + clamp: one read of temp / rhokap / Q per voxel.
+__global__ void __launch_bounds__(256) k_post(int n, const double *__restrict__ temp, const double *__restrict__ rhokap,
+                                              double *__restrict__ tissue, double *__restrict__ thres, double *__restrict__ cand,
+                                              double *__restrict__ cur, double *__restrict__ water, const double *__restrict__ Q,
+                                              double *__restrict__ density, double *__restrict__ heatcap, double *__restrict__ kappa,
+                                              double *__restrict__ coeff, double QVapor, double ablateTemp, double delt, double time)
+{
+    int i, j, k;
+    if (!voxel_of_thread(n, i, j, k)) return;
+    const size_t c = h3(n, i, j, k), ni = (size_t)n * n * n;
+    const size_t q = (size_t)(i - 1) + (size_t)n * ((size_t)(j - 1) + (size_t)n * (size_t)(k - 1));
+    const double T = temp[c];
+    double rk = rhokap[c];
+    // Arrhenius, 3dFD.f90:447-460 (reads the opacity of the previous property update, like upstream)
+    double ts = tissue[q];
+    if (T >= 43. + 273. && T < 100. + 273. && rk >= 0.) {
+        ts = ts + delt * 3.1e98 * exp(-6.3e5 / (8.314 * T));
+        tissue[q] = ts;
+    }
+    if (thres[q] == 0. && ts >= .53) thres[q] = time;
+    else if (thres[q + ni] == 0. && ts >= 1.) thres[q + ni] = time;
+    else if (thres[q + 2 * ni] == 0. && ts >= 10000.) thres[q + 2 * ni] = time;
+    // setupThermalCoeff, 3dFD.f90:327-345
+    double w = kWaterInit - kWaterInit * (Q[q] / QVapor);
+    w = w < kWaterInit ? w : kWaterInit;
+    const double wc = water[q];
+    w = w < wc ? w : wc;
+    w = w > 0.0 ? w : 0.0;
+    water[q] = w;
+    if (T >= ablateTemp + 273.) {
+        rk = 0.;
+    } else if (rk > 0.) {
+        const double rho = skinDensity(w);
+        density[c] = rho;
+        rk = w * 510. + 170.;
+        const double hcap = skinHeatCap(w);
+        heatcap[c] = hcap;
+        kappa[c] = skinThermalCond(w, rho);
+        coeff[c] = delt / (rho * hcap);
+    }
+    cand[c] = rk;
+    cur[c] = rk <= 0.01 ? 0. : rk;
+}
+
+// k_rule_air = the first pass of the neighbour rule + the air-property block, writing the new opacity to a second
+// buffer (the rule still needs last call's values ahead of the sweep).  The set of air voxels only grows in later
+// passes, so the air properties written here never have to be undone; `changed` tells the host whether the rare
+// extra passes (k_rule ... k_air) are needed.
+__global__ void __launch_bounds__(256) k_rule_air(int n, const double *__restrict__ local, const double *__restrict__ cur,
+                                                  double *__restrict__ next, const double *__restrict__ old,
+                                                  const double *__restrict__ temp, double *__restrict__ rk_new,
+                                                  double *__restrict__ density, double *__restrict__ heatcap,
+                                                  double *__restrict__ kappa, double *__restrict__ alpha, double *__restrict__ coeff,
+                                                  double delt, int *__restrict__ flags)
+{
+    int i, j, k;
+    if (!voxel_of_thread(n, i, j, k)) return;
+    const size_t c = h3(n, i, j, k), sy = (size_t)(n + 2), sz = (size_t)(n + 2) * (n + 2);
+    double v = local[c];
+    const double summ = old[c + sz] + old[c + sy] + old[c + 1] + cur[c - sz] + cur[c - sy] + cur[c - 1];
+    if (summ == 0.) v = 0.;
+    if (v <= 0.01) v = 0.;
+    if (v != cur[c]) flags[0] = 1;
+    next[c] = v;
+    rk_new[c] = v;
     if (v <= 0.01) {
         const double T = temp[c];
         const double rho = airDensity(T);
@@ -255,7 +271,7 @@ void tamc_heat_release_(tamc_context *c)
 {
     tamc_heat *s = c->heat;
     if (!s) return;
-    double *arrs[] = {s->coeff, s->kappa, s->density, s->heatcap, s->alpha, s->temp, s->tn, s->cand, s->cand2, s->cand3,
+    double *arrs[] = {s->coeff, s->kappa, s->density, s->heatcap, s->alpha, s->temp, s->tn, s->cand, s->cand2, s->cand3, s->rk_new,
                       s->water, s->Q, s->tissue, s->thres};
     for (double *p : arrs) cudaFree(p);
     cudaFree(s->flags);
@@ -334,6 +350,8 @@ extern "C" int tamc_heat_init(tamc_handle h, const tamc_heat_params *p, double *
     CU(cudaMalloc(&s->cand3, s->nh * sizeof(double)));
     CU(cudaMemset(s->cand, 0, s->nh * sizeof(double))); CU(cudaMemset(s->cand2, 0, s->nh * sizeof(double)));
     CU(cudaMemset(s->cand3, 0, s->nh * sizeof(double)));
+    CU(cudaMalloc(&s->rk_new, s->nh * sizeof(double)));
+    CU(cudaMemset(s->rk_new, 0, s->nh * sizeof(double)));
     std::vector<double> water(s->ni, kWaterInit);
     CU(up(&s->water, water));
     CU(cudaMalloc(&s->Q, s->ni * sizeof(double))); CU(cudaMemset(s->Q, 0, s->ni * sizeof(double)));
@@ -370,8 +388,8 @@ extern "C" int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc)
     // heat_sim_3D, 3dFD.f90:101-214
     if (s->pulselength < s->delt) s->delt = s->pulselength / 100.;
     for (int p = 1; p <= s->loops; ++p) {
-        k_heat_step<<<gi, 256, 0, st>>>(n, s->temp, s->tn, s->kappa, s->density, s->heatcap, s->coeff, h->d_jmean, s->Q, s->dx,
-                                        s->dy, s->dz, s->delt, s->laserOn, s->volumeVoxel, s->massVoxel, s->QVapor, s->jscale, s->flags);
+        k_heat_step<<<gi, 256, 0, st>>>(n, s->temp, s->tn, s->kappa, s->density, s->heatcap, s->coeff, h->d_jmean, s->Q, 1. / (s->dx * s->dx),
+                                        1. / (s->dy * s->dy), 1. / (s->dz * s->dz), s->delt, s->laserOn, s->volumeVoxel, s->massVoxel, s->QVapor, s->jscale, s->flags);
         std::swap(s->temp, s->tn);                                                       // t0 = tn (both hold the same halo)
         if (s->pulseCount >= s->realPulseLength && s->laser_flag) {                      // :199-211
             s->laser_flag = false; s->laserOn = 0.; s->pulseCount = 0.; s->pulsesDone += 1; s->repetitionCount = 0.;
@@ -382,23 +400,30 @@ extern "C" int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc)
         s->repetitionCount += s->delt;
         s->time += s->delt;
     }
-    // arrhenius(temp, delt, tissue, ThresTime, 1, N, N), mcpolar.f90:180
-    k_arrhenius<<<gi, 256, 0, st>>>(n, s->temp, h->d_rhokap, s->tissue, s->thres, s->delt, s->time);
-    // setupThermalCoeff(temp, N, ablateTemp), mcpolar.f90:182
-    k_local<<<gi, 256, 0, st>>>(n, s->temp, h->d_rhokap, s->cand, s->water, s->Q, s->density, s->heatcap, s->kappa, s->coeff,
-                                s->QVapor, s->ablateTemp, s->delt);
+    // arrhenius(temp, delt, tissue, ThresTime, 1, N, N) and setupThermalCoeff(temp, N, ablateTemp), mcpolar.f90:180-182,
+    // in two fused passes; the new opacity goes to a second buffer that then becomes the resident rhokap
     double *cur = s->cand2, *nxt = s->cand3;       // iterates of the fixed point; their halo stays 0 like rhokap's
-    k_clamp<<<gi, 256, 0, st>>>(n, s->cand, cur);
-    for (int it = 0; it < 3 * n + 8; ++it) {
-        CU(cudaMemsetAsync(s->flags, 0, sizeof(int), st));
-        k_rule<<<gi, 256, 0, st>>>(n, s->cand, cur, nxt, h->d_rhokap, s->flags);
-        std::swap(cur, nxt);
-        int changed = 0;                            // one pass reproduces itself at the fixed point: normally the first
-        CU(cudaMemcpyAsync(&changed, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (!changed) break;
+    k_post<<<gi, 256, 0, st>>>(n, s->temp, h->d_rhokap, s->tissue, s->thres, s->cand, cur, s->water, s->Q, s->density, s->heatcap,
+                               s->kappa, s->coeff, s->QVapor, s->ablateTemp, s->delt, s->time);
+    CU(cudaMemsetAsync(s->flags, 0, sizeof(int), st));
+    k_rule_air<<<gi, 256, 0, st>>>(n, s->cand, cur, nxt, h->d_rhokap, s->temp, s->rk_new, s->density, s->heatcap, s->kappa,
+                                   s->alpha, s->coeff, s->delt, s->flags);
+    std::swap(cur, nxt);
+    int changed = 0;
+    CU(cudaMemcpyAsync(&changed, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (changed) {
+        // rare: the rule zeroed a voxel whose neighbours ahead of it now see a different value -- iterate to the fixed point
+        for (int it = 0; it < 3 * n + 8 && changed; ++it) {
+            CU(cudaMemsetAsync(s->flags, 0, sizeof(int), st));
+            k_rule<<<gi, 256, 0, st>>>(n, s->cand, cur, nxt, h->d_rhokap, s->flags);
+            std::swap(cur, nxt);
+            CU(cudaMemcpyAsync(&changed, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        k_air<<<gi, 256, 0, st>>>(n, cur, s->temp, s->rk_new, s->density, s->heatcap, s->kappa, s->alpha, s->coeff, s->delt);
     }
-    k_air<<<gi, 256, 0, st>>>(n, cur, s->temp, h->d_rhokap, s->density, s->heatcap, s->kappa, s->alpha, s->coeff, s->delt);
+    std::swap(h->d_rhokap, s->rk_new);              // both buffers keep a zero halo
     CU(cudaGetLastError());
     s->counter += 1;
     return TAMC_OK;
