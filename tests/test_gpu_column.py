@@ -1,0 +1,107 @@
+"""Column form of the shipped (stub) regime (csrc/tamc_column.cuh) through the C ABI.
+
+The column kernels tally each packet's final partial deposit plus a stop count, and reconstruct the full-voxel
+crossings as F * dcell * rhokap.  Same Philox streams and the same taurun accumulation as the step-by-step
+kernels, so against the oracle run on the same counter-based stream: counters bit-exact, grid to fp64 summation
+order (1e-10 relative, identical support).  Integer work (voxel-steps, fates) must be bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.util import compare_grids, make_oracle, make_transport
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261017
+
+
+def _check(t, o, n, first=0):
+    o.zero_jmean()
+    o.seed_philox(SEED, first)
+    want = o.run(n)["stats"]
+    t.set_option("variant", 1)                       # step-by-step persistent kernel
+    t.run_async(n, SEED, first)
+    base, sb = t.get_jmean().copy(), t.get_stats()
+    t.set_option("variant", 3)
+    for column in (1, 2):
+        t.set_option("column", column)
+        for rep in range(2):                        # twice: the stop counts must be all zero again after a call
+            t.run_async(n, SEED, first)
+            jm, st = t.get_jmean(), t.get_stats()
+            assert st["gpu_launches"] == (3 if column == 1 else 2)
+            for key in ("packets", "voxel_steps", "scatters", "absorbed", "exits"):
+                assert st[key] == want[key] == sb[key], (key, column, rep)
+            compare_grids(jm, o.jmean, rtol=1e-10)
+            compare_grids(jm, base, rtol=1e-10)
+    t.set_option("column", -1)
+
+
+def test_column_shipped_and_crater():
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["shipped80"]
+    t, o = make_transport(cfg), make_oracle(cfg)
+    _check(t, o, 125000)
+    _check(t, o, 30000, first=(1 << 32) - 10000)      # ids crossing 2^32
+    t.close()
+    # ablated crater (rhokap == 0 voxels are crossed with zero deposit) with a water-depleted rim
+    for rk in list(tamc.configs.crater_sequence(80, 6))[3:6]:
+        t, o = make_transport(cfg, rk), make_oracle(cfg, rk)
+        _check(t, o, 60000)
+        t.close()
+
+
+@pytest.mark.parametrize("n", [50, 63, 200])
+def test_column_homog_grids(n):
+    """nzg = 50 and 63 are not multiples of 4 (partial first 256-bit group); 200 is the bench grid."""
+    import tamc
+
+    cfg = tamc.configs.scaled("homog200", n)
+    t, o = make_transport(cfg), make_oracle(cfg)
+    _check(t, o, 80000)
+    t.close()
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (3, 5, 7), (17, 4, 33), (40, 24, 6)])
+def test_column_non_cubic_heterogeneous_with_transmission(dims):
+    """Heterogeneous opacity, non-cubic boxes, thin enough that a good fraction of the packets crosses every voxel and
+    leaves through the bottom face (plane 0 of the stop counts)."""
+    import tamc
+
+    nx, ny, nz = dims
+    xmax, ymax, zmax = 0.02, 0.03, 0.05
+    rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+    ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    rk[1:-1, 1:-1, 1:-1] = (3.0 + 4.0 * ((ii + 2 * jj + 3 * kk) % 5)) * ((ii + kk) % 7 != 0)     # some voxels empty
+    o = orc.Oracle(nx, ny, nz, xmax, ymax, zmax)
+    o.set_rhokap(rk)
+    o.set_optics(0.0, 0.9)
+    o.set_flags(0)
+    t = tamc.MCTransport(nx, ny, nz, xmax, ymax, zmax)
+    t.set_optics(rk, 0.0, 0.9)
+    _check(t, o, 50000)
+    st = t.get_stats()
+    assert st["exits"][4] > 1000 and st["absorbed"] > 1000
+    t.close()
+
+
+def test_column_is_the_default_for_large_calls_and_matches_the_step_kernel():
+    """>= 2^20 packets on the default variant take the column form (3 launches); its grid equals the step-by-step
+    kernel's to summation order, the counters exactly."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["homog200"]
+    n = 3_000_000
+    t = make_transport(cfg)
+    t.run_async(n, SEED, 0)
+    jm, st = t.get_jmean().copy(), t.get_stats()
+    assert st["gpu_launches"] == 3
+    t.set_option("column", 0)
+    t.run_async(n, SEED, 0)
+    jm0, st0 = t.get_jmean(), t.get_stats()
+    assert st0["gpu_launches"] == 1
+    for key in ("packets", "voxel_steps", "absorbed", "exits"):
+        assert st[key] == st0[key]
+    compare_grids(jm, jm0, rtol=1e-10)
+    assert abs(jm.sum() / n - 1.0) < 5 / np.sqrt(n)
+    t.close()

@@ -216,6 +216,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_cnt); cudaFree(h->d_flush);
+    cudaFree(h->colws.stops); cudaFree(h->colws.rkT);
     for (int i = 0; i < EV_N; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -324,7 +325,7 @@ extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int
     CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));   // zarray / jmean = 0. (mcpolar.f90:185)
     CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
-    CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches));
+    CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches, &h->colws));
     CU(cudaEventRecord(h->ev[EV_K1], h->stream));
     if (int rc = enqueue_reduce(h)) return rc;
     h->last_launches = launches;
@@ -534,6 +535,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "merge")) return &h->cfg.merge;
     if (!strcmp(name, "min_ctas")) return &h->cfg.min_ctas;
     if (!strcmp(name, "tile")) return &h->cfg.tile;
+    if (!strcmp(name, "column")) return &h->cfg.column;
     if (!strcmp(name, "reduce")) return &h->reduce;
     return nullptr;
 }
@@ -547,6 +549,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
     if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");
     if (slot == &h->cfg.min_ctas && (value < 2 || value > 3)) return fail(TAMC_EINVAL, "min_ctas must be 2 or 3");
+    if (slot == &h->cfg.column && (value < -1 || value > 2)) return fail(TAMC_EINVAL, "column must be -1 (auto), 0 (off), 1 or 2");
     if (slot == &h->cfg.ctas_per_sm && (value < 0 || value > 32)) return fail(TAMC_EINVAL, "ctas_per_sm must be in [0,32]");
     *slot = (int)value;
     return TAMC_OK;

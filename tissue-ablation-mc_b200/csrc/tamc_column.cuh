@@ -1,0 +1,204 @@
+// tamc_column.cuh -- shipped (stub) regime, column form: variant 3's kernel when the scatter loop is off.
+//
+// In the shipped regime (mcpolar.f90:166-169: a packet ends at its first interaction) sourcephCO2
+// (sourceph.f90:37-42) sends every packet straight down (nxp = nyp = 0, nzp = -1), so a flight never leaves
+// the voxel column it was launched into and tauint1 (inttau2.f90:37-63) degenerates to a walk down that
+// column.  Two consequences, both exact:
+//
+//   1. The wall distance of a FULL crossing of voxel k is the same number for every packet: the packet
+//      enters at zface(k+1) - delta (update_pos, inttau2.f90:163-166; the launch voxel is entered at zp0)
+//      and leaves through zface(k), so dcell(k) = -(zface(k) - (zface(k+1) - delta)) and the deposit
+//      dcell(k)*rhokap(i,j,k) (inttau2.f90:46) depends on the voxel only.  The tally of all full crossings
+//      is therefore  F(i,j,k) * dcell(k) * rhokap(i,j,k)  with F = the number of packets of the column that
+//      stopped below k.  The transport kernel records where each packet stopped (one u32 RED) and tallies
+//      only the final partial deposit tau - taurun (inttau2.f90:51-53, one fp64 RED); k_column_finish turns
+//      the stop counts into F by a running sum up the column and adds the full-crossing term.  Per packet
+//      that is 2 atomics instead of one per voxel-step.
+//   2. The opacities a packet reads are consecutive in z.  A z-fastest copy of the columns under the beam's
+//      bounding box (k_column_gather, refreshed every MC call: ~10 MB at 200^3) lets one 256-bit load
+//      (LDG.E.256) fetch four voxel-steps' worth of rhokap.
+//
+// The plain persistent kernel sits on the L1TEX address throughput (one uncoalesced rhokap load + one jmean
+// RED per voxel-step, profiles/); this form issues ~1.3 loads + <= 2 REDs per PACKET.  Same Philox streams,
+// same launch arithmetic (launch_fast), same taurun accumulation order, hence the same stop voxel and the
+// same partial deposit bit for bit; the grid differs from the step-by-step tally only by fp64 summation
+// order (F*d instead of d+d+...+d).
+#pragma once
+
+#include "tamc_fast.cuh"
+
+namespace tamc {
+
+struct ColGeom {
+    int i0, j0;        // first voxel (1-based) of the beam's bounding box in x and y
+    int tw, th;        // its extent
+    int nzp;           // column length of the z-fastest copy: nzg rounded up to a multiple of 4
+};
+
+// z-fastest copy of the bounding-box columns: rkT[(dj*tw + di)*nzp + (k-1)] = rhokap(i0+di, j0+dj, k).
+// 32 x 32 (x, z) tiles through shared memory: reads coalesced along x, writes coalesced along z.
+__global__ void __launch_bounds__(256) k_column_gather(const DevGrid g, const ColGeom cg, double *__restrict__ rkT)
+{
+    __shared__ double tile[32][33];
+    const int dj = blockIdx.y, di0 = blockIdx.x * 32, kz0 = blockIdx.z * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long rowj = (long long)g.sx * (cg.j0 + dj);
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int kz = kz0 + r + ty, di = di0 + tx;          // kz = k - 1
+        double v = 0.;
+        if (di < cg.tw && kz < g.nzg) v = g.rhokap[(cg.i0 + di) + rowj + g.sxy * (kz + 1)];
+        tile[r + ty][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int di = di0 + r + ty, kz = kz0 + tx;
+        if (di < cg.tw && kz < cg.nzp) rkT[((size_t)dj * cg.tw + di) * cg.nzp + kz] = tile[tx][r + ty];
+    }
+}
+
+__device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// dcell(k) for k = 1..nzp into shared memory (0 past the launch plane / the grid): the wall distance
+// voxel_step_fast computes for a straight-down flight, fmin(fmin(100000., 100000.), (fz - zcur) * inz) with inz = -1.
+__device__ __forceinline__ void stage_column_steps(const DevGrid &g, int nzp, double *s_dz)
+{
+    const double *zf = g.faces + (g.nxg + 1) + (g.nyg + 1);      // zface(1:nzg+1), 0-based here: zf[k-1] = zface(k)
+    for (int k = 1 + threadIdx.x; k <= nzp; k += blockDim.x) {
+        double d = 0.;
+        if (k <= g.cellk0 && k <= g.nzg) {
+            const double zcur = (k == g.cellk0) ? g.zcur0 : zf[k] - g.delta;
+            d = fmin(100000., (zf[k - 1] - zcur) * -1.);
+        }
+        s_dz[k - 1] = d;
+    }
+    __syncthreads();
+}
+
+// One packet per thread, grid-stride.  kGather: read the z-fastest copy with 256-bit loads; otherwise walk the
+// resident grid itself (one 8-byte load per voxel-step).
+template <bool kGather, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
+                                                             const ColGeom cg, const double *__restrict__ rkT,
+                                                             unsigned int *__restrict__ stops,
+                                                             unsigned long long *__restrict__ cnt)
+{
+    extern __shared__ double s_dz[];
+    stage_column_steps(g, cg.nzp, s_dz);
+    const int plane = g.nxg * g.nyg;
+    const int k0 = g.cellk0;
+    unsigned long long steps = 0ull;
+    unsigned int packets = 0u, absorbed = 0u, bottom = 0u;
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        PhiloxRng rng;
+        rng.seed(seed, first_id + (uint64_t)i);
+        double u[4];
+        rng.block(u);
+        const Launched L = launch_fast(g, u, false);
+        const double tau = L.tau;
+        double taurun = 0.;
+        int kstop = 0;                                   // voxel of the interaction; 0 = left through the bottom face
+        if (kGather) {
+            const int di = (L.cells & 0xffff) - cg.i0, dj = (L.cells >> 16) - cg.j0;
+            const double *col = rkT + ((size_t)dj * cg.tw + di) * cg.nzp;
+            int idx = k0 - 1;                            // k - 1 of the voxel the packet is in
+            while (idx >= 0) {
+                const int gb = idx & ~3;
+                double r0, r1, r2, r3;
+                ldg256(col + gb, r0, r1, r2, r3);
+                const double2 da = *reinterpret_cast<const double2 *>(s_dz + gb), db = *reinterpret_cast<const double2 *>(s_dz + gb + 2);
+                // dcell*rhokap, inttau2.f90:40 -- products and sums rounded separately (no FMA contraction), as the oracle does
+                const double tc3 = __dmul_rn(db.y, r3), tc2 = __dmul_rn(db.x, r2), tc1 = __dmul_rn(da.y, r1), tc0 = __dmul_rn(da.x, r0);
+                // the four voxel-steps of the group without a divergent branch: running sums in the packet's order
+                // (slot 3 = the highest voxel first), then the first slot whose sum reaches tau.  Slots above the launch
+                // voxel (first group when nzg is not a multiple of 4) hold dcell = 0 and rhokap = 0: taurun + 0 < tau passes.
+                const double t3 = __dadd_rn(taurun, tc3), t2 = __dadd_rn(t3, tc2), t1 = __dadd_rn(t2, tc1), t0 = __dadd_rn(t1, tc0);
+                const bool p3 = t3 < tau, p2 = t2 < tau, p1 = t1 < tau, p0 = t0 < tau;               // inttau2.f90:42
+                const int nstop = !p3 ? 4 : (!p2 ? 3 : (!p1 ? 2 : (!p0 ? 1 : 0)));
+                const double before = !p3 ? taurun : (!p2 ? t3 : (!p1 ? t2 : t1));
+                if (nstop) { kstop = gb + nstop; taurun = before; break; }
+                taurun = t0;
+                idx = gb - 1;
+            }
+        } else {
+            int ridx = L.ridx;
+            for (int k = k0; k >= 1; --k) {
+                const double taucell = __dmul_rn(s_dz[k - 1], __ldg(g.rhokap + ridx));
+                const double t = __dadd_rn(taurun, taucell);
+                if (t < tau) taurun = t; else { kstop = k; break; }
+                ridx -= (int)g.sxy;
+            }
+        }
+        ++packets;
+        if (kstop) {
+            const double rest = tau - taurun;            // inttau2.f90:51-53: dcell*rhokap = ((tau-taurun)/rhokap)*rhokap
+            const int j = L.jidx - (k0 - kstop) * plane;
+            if (rest != 0.) atomicAdd(g.jmean + j, rest);
+            // the stop count only feeds voxels above kstop: nothing to record for a stop in the top plane
+            if (kstop < g.nzg) atomicAdd(stops + (j + plane), 1u);
+            steps += (unsigned long long)(k0 - kstop + 1);
+            ++absorbed;
+        } else {
+            atomicAdd(stops + (L.jidx - (k0 - 1) * plane), 1u);      // plane 0 of the counts: crossed every voxel
+            steps += (unsigned long long)k0;
+            ++bottom;
+        }
+    }
+    unsigned long long v[4] = {packets, steps, absorbed, bottom};
+    const int slot[4] = {CNT_PACKETS, CNT_STEPS, CNT_ABSORBED, CNT_EXIT0 + 4};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned long long x = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(cnt + slot[q], x);
+    }
+}
+
+// Full-crossing deposits: one thread per bounding-box column walks up from the bottom, F = packets that stopped
+// below the voxel (stops plane k holds the packets that stopped in voxel k, plane 0 those that left through the
+// bottom face), jmean(i,j,k) += F * dcell(k) * rhokap(i,j,k).  Clears the counts it consumed, so the array is
+// all zero again for the next call.  Lanes run along x: every access is coalesced.
+__global__ void __launch_bounds__(128) k_column_finish(const DevGrid g, const ColGeom cg, unsigned int *__restrict__ stops)
+{
+    extern __shared__ double s_dz[];
+    stage_column_steps(g, cg.nzp, s_dz);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cg.tw * cg.th) return;
+    const int i = cg.i0 + t % cg.tw, j = cg.j0 + t / cg.tw;
+    const int plane = g.nxg * g.nyg;
+    const int c0 = (i - 1) + g.nxg * (j - 1);
+    long long r0 = (long long)i + (long long)g.sx * j;
+    unsigned long long F = stops[c0];
+    if (F) stops[c0] = 0u;
+    constexpr int kBatch = 8;
+    for (int kb = 1; kb <= g.nzg; kb += kBatch) {
+        unsigned int c[kBatch];
+        double rk[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const int k = kb + q;
+            c[q] = (k < g.nzg) ? stops[c0 + k * plane] : 0u;            // the top plane is never recorded
+            rk[q] = (k <= g.nzg) ? __ldg(g.rhokap + r0 + g.sxy * k) : 0.;
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const int k = kb + q;
+            if (k <= g.nzg) {
+                if (F) {
+                    const double d = (double)F * (s_dz[k - 1] * rk[q]);
+                    if (d != 0.) g.jmean[c0 + (k - 1) * plane] += d;
+                }
+                if (c[q]) { F += c[q]; stops[c0 + k * plane] = 0u; }
+            }
+        }
+    }
+}
+
+}  // namespace tamc

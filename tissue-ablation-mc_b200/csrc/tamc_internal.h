@@ -18,11 +18,23 @@ struct LaunchCfg {
     int merge;          // merge consecutive same-voxel deposits in registers (-1 = auto: on with TAMC_SCATTER)
     int min_ctas;       // scattering kernel: the __launch_bounds__ min-CTAs-per-SM build to use (2 or 3)
     int tile;           // stub regime: shared-memory tally tile; -1 = auto, 0 = off, k > 0 = at most k planes
+    int column;         // stub regime, column form (tamc_column.cuh): -1 = auto (variant 3, >= 2^20 packets), 0 = off,
+                        // 1 = on with the z-fastest copy of the beam's columns, 2 = on, reading the resident grid
+};
+
+// Device buffers of the column form, owned by the handle and grown on demand by launch_transport.
+struct ColumnWorkspace {
+    unsigned int *stops = nullptr;   // nxg*nyg*nzg stop counts (plane 0: packets that left through the bottom face); all zero between calls
+    size_t stops_elems = 0;
+    double *rkT = nullptr;           // z-fastest copy of rhokap under the beam's bounding box
+    size_t rkT_elems = 0;
 };
 
 // production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.
+// ws may be null (no column form).
 cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
-                             unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches);
+                             unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches,
+                             ColumnWorkspace *ws = nullptr);
 
 // trace replay (tamc_replay.cu, compiled with -fmad=false)
 cudaError_t launch_replay(const DevGrid &g, long long n, const long long *d_off, const double *d_draws,

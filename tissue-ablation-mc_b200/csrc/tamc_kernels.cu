@@ -17,6 +17,7 @@
 
 #include "tamc_fast.cuh"
 #include "tamc_internal.h"
+#include "tamc_column.cuh"
 #include "tamc_pool.cuh"
 #include "tamc_stub_tile.cuh"
 
@@ -379,8 +380,58 @@ static cudaError_t launch_sized(K kernel, const LaunchCfg &cfg, size_t smem, lon
     return cudaGetLastError();
 }
 
+// Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
+static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
+                                 unsigned long long *d_cnt, cudaStream_t s, int *launches, ColumnWorkspace *ws, bool gather)
+{
+    const double R = sqrt(g.spot_r2);
+    ColGeom cg;
+    cg.i0 = max(1, (int)((g.xmax - R) * g.inv_dx) + 1);
+    cg.j0 = max(1, (int)((g.ymax - R) * g.inv_dy) + 1);
+    cg.tw = min(g.nxg, (int)((g.xmax + R) * g.inv_dx) + 1) - cg.i0 + 1;
+    cg.th = min(g.nyg, (int)((g.ymax + R) * g.inv_dy) + 1) - cg.j0 + 1;
+    cg.nzp = (g.nzg + 3) & ~3;
+    if (cg.tw < 1 || cg.th < 1) return cudaErrorInvalidValue;
+    const size_t nstops = (size_t)g.nxg * g.nyg * g.nzg;
+    if (ws->stops_elems < nstops) {
+        cudaFree(ws->stops);
+        ws->stops = nullptr;
+        ws->stops_elems = 0;
+        cudaError_t e = cudaMalloc(&ws->stops, nstops * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(ws->stops, 0, nstops * sizeof(unsigned int), s);
+        if (e != cudaSuccess) return e;
+        ws->stops_elems = nstops;
+    }
+    const size_t smem = sizeof(double) * (size_t)cg.nzp;
+    if (gather) {
+        const size_t nrk = (size_t)cg.tw * cg.th * cg.nzp;
+        if (ws->rkT_elems < nrk) {
+            cudaFree(ws->rkT);
+            ws->rkT = nullptr;
+            ws->rkT_elems = 0;
+            cudaError_t e = cudaMalloc(&ws->rkT, nrk * sizeof(double));
+            if (e != cudaSuccess) return e;
+            ws->rkT_elems = nrk;
+        }
+        const dim3 gg((cg.tw + 31) / 32, cg.th, (cg.nzp + 31) / 32);
+        k_column_gather<<<gg, 256, 0, s>>>(g, cg, ws->rkT);
+        if (launches) *launches += 1;
+    }
+    LaunchCfg c2 = cfg;
+    c2.block = 256;
+    cudaError_t e;
+    if (!gather) e = launch_sized(k_transport_column<false, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)nullptr, ws->stops, d_cnt);
+    else if (cfg.min_ctas == 2) e = launch_sized(k_transport_column<true, 6>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
+    else e = launch_sized(k_transport_column<true, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
+    if (e != cudaSuccess) return e;
+    k_column_finish<<<(cg.tw * cg.th + 127) / 128, 128, smem, s>>>(g, cg, ws->stops);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long long n, uint64_t seed, uint64_t first_id,
-                             unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches)
+                             unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches,
+                             ColumnWorkspace *ws)
 {
     if (n <= 0) return cudaSuccess;
     LaunchCfg cfg = cfg_in;
@@ -388,6 +439,16 @@ cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long lon
     if (cfg.block <= 0) cfg.block = pool ? 128 : 256;       // auto
     const bool merge = cfg.merge < 0 ? (g.flags & TAMC_SCATTER) != 0 : cfg.merge != 0;
     const size_t smem = faces_bytes(g);
+    // shipped regime, default variant: the column form once the call is large enough to pay for its two small extra kernels
+    if (ws && !d_rec && cfg.variant == 3 && !(g.flags & (TAMC_SCATTER | TAMC_FRESNEL)) && cfg.column != 0) {
+        // auto: calls large enough to pay for the two small extra kernels, and a footprint of more than a few thousand
+        // columns -- under a narrow beam the partial-deposit REDs hit so few addresses that the L2 atomic unit
+        // serialises, and the shared-memory tile below is the better form (measured: profiles/README.md)
+        const double R = sqrt(g.spot_r2);
+        const double cols = (2. * R * g.inv_dx + 1.) * (2. * R * g.inv_dy + 1.);
+        if (cfg.column > 0 || (n >= (1ll << 20) && cols > 4096.))
+            return launch_column(g, cfg, n, seed, first_id, d_cnt, s, launches, ws, cfg.column != 2);
+    }
     if (launches) *launches += 1;
     tamc_packet_record *none = nullptr;
 
