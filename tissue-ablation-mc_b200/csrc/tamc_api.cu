@@ -95,7 +95,7 @@ static int check(tamc_handle h)
 
 static DevGrid make_grid(const tamc_context *c)
 {
-    DevGrid g;
+    DevGrid g{};
     g.nxg = c->nxg; g.nyg = c->nyg; g.nzg = c->nzg;
     g.sx = c->nxg + 2;
     g.sxy = (long long)(c->nxg + 2) * (c->nyg + 2);

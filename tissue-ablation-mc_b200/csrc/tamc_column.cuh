@@ -96,11 +96,8 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGri
 
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        PhiloxRng rng;
-        rng.seed(seed, first_id + (uint64_t)i);
-        double u[4];
-        rng.block(u);
-        const Launched L = launch_fast(g, u, false);
+        const uint64_t gid = first_id + (uint64_t)i;
+        const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), false);
         const double tau = L.tau;
         double taurun = 0.;
         int kstop = 0;                                   // voxel of the interaction; 0 = left through the bottom face

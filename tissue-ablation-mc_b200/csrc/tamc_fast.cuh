@@ -18,11 +18,31 @@
 // Philox stream, and statistically against the oracle on the reference's ran2 stream.
 #pragma once
 
+#include "tamc_math.cuh"
 #include "tamc_transport.cuh"
 
 namespace tamc {
 
 constexpr double kInvPi = 0.31830988618379067154;   // 1/pi (the true pi: only converts radians for sincospi)
+
+// Philox4x32-10 (the same function as philox4x32_10) with the round keys read from the kernel-parameter bank
+// (DevGrid::rk, filled per call by launch_transport): a LOP3 takes them as a direct operand instead of
+// re-deriving key + r*W in every block.
+__device__ __forceinline__ uint4 philox_block(const DevGrid &g, uint32_t id_lo, uint32_t id_hi, uint32_t blk)
+{
+    uint4 c = make_uint4(id_lo, id_hi, blk, 0u);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ g.rk[2 * r], lo1, hi0 ^ c.w ^ g.rk[2 * r + 1], lo0);
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 philox_block(const DevGrid &g, PhiloxRng &rng) { return philox_block(g, rng.id_lo, rng.id_hi, rng.blk++); }
+
+// u32_to_unit in one fused operation: x*2^-32 + 2^-33 is exact, the same number as (x + 0.5)*2^-32.
+__device__ __forceinline__ double unit_fast(uint32_t x) { return __fma_rn((double)x, 1.0 / 4294967296.0, 1.0 / 8589934592.0); }
 
 struct FastPhoton {
     double xcur, ycur, zcur;      // shifted frame, inttau2.f90:24-26
@@ -73,15 +93,15 @@ struct Launched {
     int ridx, jidx;   // linear indices of the launch voxel in rhokap / jmean
 };
 
-// sourceph.f90:28-47 + inttau2.f90:36.  u = (r, theta, phi, tau) draws in the reference's order.
-__device__ __forceinline__ Launched launch_fast(const DevGrid &g, const double u[4], bool need_azimuth)
+// sourceph.f90:28-47 + inttau2.f90:36.  w = one Philox block = the (r, theta, phi, tau) draws in the reference's order.
+__device__ __forceinline__ Launched launch_fast(const DevGrid &g, const uint4 w, bool need_azimuth)
 {
     Launched L;
-    const double r = u[0] * g.spot_r2;
-    const double theta = u[1] * kTWOPI;
+    const double r = unit_fast(w.x) * g.spot_r2;
+    const double theta = unit_fast(w.y) * kTWOPI;
     double s, c;
-    sincospi(theta * kInvPi, &s, &c);
-    const double sr = sqrt(r);
+    fm::sincospi_0_2(theta * kInvPi, &s, &c);
+    const double sr = (r > 1e-280) ? fm::sqrt_normal(r) : sqrt(r);   // (spot diameter 0: r = 0)
     L.xcur = sr * c + g.xmax;
     L.ycur = sr * s + g.ymax;
     const int celli = (int)(L.xcur * g.inv_dx) + 1;
@@ -91,8 +111,8 @@ __device__ __forceinline__ Launched launch_fast(const DevGrid &g, const double u
     L.jidx = (celli - 1) + g.nxg * ((cellj - 1) + g.nyg * (g.cellk0 - 1));
     L.cosp = 1.;
     L.sinp = 0.;
-    if (need_azimuth) sincospi(kTWOPI * u[2] * kInvPi, &L.sinp, &L.cosp);   // phi is first used by the first scattering
-    L.tau = -log(u[3]);
+    if (need_azimuth) fm::sincospi_0_2(kTWOPI * unit_fast(w.z) * kInvPi, &L.sinp, &L.cosp);   // phi is first used by the first scattering
+    L.tau = fm::neglog_u32(w.w);
     return L;
 }
 
@@ -172,14 +192,14 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
 }
 
 // stokes.f90:6-153 as a rotation of the direction vector (see the header comment).
-// u1 -> stokes.f90:24/:48, u2 -> :32/:64, u3 -> the next tauint1 draw (inttau2.f90:36).
+// u1 -> stokes.f90:24/:48, u2 -> :32/:64, tau = -log(u3) -> the next tauint1 draw (inttau2.f90:36).
 template <bool kSetDir = true>
 __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2);
 
-__device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double u3)
+__device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double tau)
 {
     p.taurun = 0.;
-    p.tau = -log(u3);
+    p.tau = tau;
     // the centred position round trip of inttau2.f90:65-67 / :24-26
     p.xcur = (p.xcur - g.xmax) + g.xmax;
     p.ycur = (p.ycur - g.ymax) + g.ymax;
@@ -197,7 +217,7 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
         const double cost = 2. * u1 - 1.;
         const double s2 = 1. - cost * cost;
         p.sint = (s2 <= 0.) ? 0. : sqrt(s2);
-        sincospi(kTWOPI * u2 * kInvPi, &p.sinp, &p.cosp);
+        fm::sincospi_0_2(kTWOPI * u2 * kInvPi, &p.sinp, &p.cosp);
         p.nxp = p.sint * p.cosp;
         p.nyp = p.sint * p.sinp;
         p.nzp = cost;
@@ -215,7 +235,7 @@ __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, dou
     const double ri1 = kTWOPI * u2;
     const bool upper = ri1 > kPI;
     double si, ci;
-    sincospi((upper ? kTWOPI - ri1 : ri1) * kInvPi, &si, &ci);   // sin/cos of the angle, argument reduced exactly
+    fm::sincospi_0_2((upper ? kTWOPI - ri1 : ri1) * kInvPi, &si, &ci);   // sin/cos of the angle, argument reduced exactly
     si = upper ? -si : si;
 
     const double costp = p.nzp, sintp = p.sint;

@@ -54,10 +54,8 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         PhiloxRng rng;
         rng.seed(seed, first_id + (uint64_t)i);
-        double u[4];
-        rng.block(u);
         FastPhoton p;
-        adopt(g, lc, p, launch_fast(g, u, scatter_on));
+        adopt(g, lc, p, launch_fast(g, philox_block(g, rng), scatter_on));
         tally.begin();
         int steps = 0, nscatt = 0, fate = 0, ndraws = 4, nb = 0;
         bool specular = false;
@@ -85,9 +83,9 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
                 break;
             }
             if (!scatter_on) break;                               // mcpolar.f90:166-169 stub
-            rng.block(u);
-            if (u[0] < g.albedo) {
-                scatter_fast(g, p, u[1], u[2], u[3]);
+            const uint4 w = philox_block(g, rng);
+            if (unit_fast(w.x) < g.albedo) {
+                scatter_fast(g, p, unit_fast(w.y), unit_fast(w.z), fm::neglog_u32(w.w));
                 ++nscatt;
                 ndraws += 4;
             } else {
@@ -186,7 +184,6 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
     int count = 0;                       // launched packets parked in the reservoir (warp-uniform)
     long long next = 0, end = 0;         // ids of the chunk this warp currently owns
     bool exhausted = false;
-    double u[4];
 
     for (;;) {
         const unsigned idle = __ballot_sync(full, mode == LANE_IDLE);
@@ -204,10 +201,7 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
                 const long long id = next + lane;
                 if (id < end) {
                     const uint64_t gid = first_id + (uint64_t)id;
-                    PhiloxRng lr;
-                    lr.seed(seed, gid);
-                    lr.block(u);
-                    const Launched L = launch_fast(g, u, kScatter);
+                    const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), kScatter);
                     const int s = count + (int)lane;
                     R.xcur[s] = L.xcur; R.ycur[s] = L.ycur; R.tau[s] = L.tau;
                     if (kScatter) {
@@ -255,9 +249,9 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
         const unsigned walking = __ballot_sync(full, mode == LANE_WALK);
         if (kScatter && waiting && (__popc(waiting) >= scatter_min || walking == 0u)) {
             if (mode == LANE_INTERACT) {
-                rng.block(u);
-                if (u[0] < g.albedo) {                    // draw < albedo ? stokes : absorbed
-                    scatter_fast(g, p, u[1], u[2], u[3]);
+                const uint4 w = philox_block(g, rng);
+                if (unit_fast(w.x) < g.albedo) {          // draw < albedo ? stokes : absorbed
+                    scatter_fast(g, p, unit_fast(w.y), unit_fast(w.z), fm::neglog_u32(w.w));
                     ++nscatt;
                     mode = LANE_WALK;
                 } else {
@@ -429,11 +423,16 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     return cudaGetLastError();
 }
 
-cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg_in, long long n, uint64_t seed, uint64_t first_id,
+cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long long n, uint64_t seed, uint64_t first_id,
                              unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches,
                              ColumnWorkspace *ws)
 {
     if (n <= 0) return cudaSuccess;
+    DevGrid g = g_in;
+    for (int r = 0; r < 10; ++r) {          // Philox4x32 key schedule (Random123): key + r * (W32_0, W32_1)
+        g.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        g.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     LaunchCfg cfg = cfg_in;
     const bool pool = cfg.variant == 3 && (g.flags & TAMC_SCATTER) && !d_rec;
     if (cfg.block <= 0) cfg.block = pool ? 128 : 256;       // auto

@@ -105,17 +105,17 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 int4 g4 = S.tau_ns_nb;
                 const int ns = g4.z;
                 const uint4 id = S.id;
-                const uint4 r = philox4x32_10(key, make_uint4(id.x, id.y, (uint32_t)ns + 1u, 0u));
-                if (u32_to_unit(r.x) < g.albedo) {            // draw < albedo ? stokes : absorbed
+                const uint4 r = philox_block(g, id.x, id.y, (uint32_t)ns + 1u);
+                if (unit_fast(r.x) < g.albedo) {            // draw < albedo ? stokes : absorbed
                     FastPhoton q;
                     const double2 a = S.nz_st, b = S.cp_sp;
                     q.nzp = a.x; q.sint = a.y; q.cosp = b.x; q.sinp = b.y;
                     q.nxp = q.sint * q.cosp; q.nyp = q.sint * q.sinp;
                     // the position stays parked in the slot; the walker re-derives reciprocals and indices
-                    scatter_dir<false>(g, q, u32_to_unit(r.y), u32_to_unit(r.z));
+                    scatter_dir<false>(g, q, unit_fast(r.y), unit_fast(r.z));
                     S.nz_st = make_double2(q.nzp, q.sint);
                     S.cp_sp = make_double2(q.cosp, q.sinp);
-                    const double tau = -log(u32_to_unit(r.w));
+                    const double tau = fm::neglog_u32(r.w);
                     g4.x = __double2loint(tau); g4.y = __double2hiint(tau); g4.z = ns + 1;
                     S.tau_ns_nb = g4;
                     survive = true;
@@ -154,11 +154,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 if (lane < k) {
                     const int s = P.fq[nf - 1 - lane];
                     const uint64_t gid = first_id + (uint64_t)(next + lane);
-                    PhiloxRng lr;
-                    lr.seed(seed, gid);
-                    double u[4];
-                    lr.block(u);
-                    const Launched L = launch_fast(g, u, true);
+                    const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), true);
                     PoolSlot &S = P.slot[s];
                     S.pos_xy = make_double2(L.xcur, L.ycur);
                     S.pz_pval = make_double2(lc.zcur0, 0.);

@@ -64,11 +64,8 @@ __global__ void __launch_bounds__(1024, 1) k_transport_stub_tiled(const DevGrid 
             if (!exhausted) {
                 const long long id = next + lane;
                 if (id < end) {
-                    PhiloxRng lr;
-                    lr.seed(seed, first_id + (uint64_t)id);
-                    double u[4];
-                    lr.block(u);
-                    const Launched L = launch_fast(g, u, false);
+                    const uint64_t gid = first_id + (uint64_t)id;
+                    const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), false);
                     R.xcur[lane] = L.xcur; R.ycur[lane] = L.ycur; R.tau[lane] = L.tau;
                 }
                 count = (int)min((long long)32, end - next);

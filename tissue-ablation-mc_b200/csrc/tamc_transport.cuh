@@ -54,6 +54,7 @@ struct DevGrid {
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
     const double *faces;  // xface(1:nxg+1) | yface(1:nyg+1) | zface(1:nzg+1)
+    uint32_t rk[20];      // Philox round keys of this call's seed: key + r*(0x9E3779B9, 0xBB67AE85), r = 0..9 (production kernels)
 };
 
 // ---------------------------------------------------------------------------------------------
