@@ -35,6 +35,8 @@ UNIT = "packets/s"
 SEED = 20261017
 BYTES_PER_VOXEL_STEP = 16          # 8 B rhokap read + 8 B jmean accumulate
 HBM_FALLBACK_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FORMS = {0: "k_transport_simple", 1: "k_transport_persistent", 2: "k_transport_exact", 3: "k_transport_pool",
+         4: "k_transport_stub_tiled", 5: "k_transport_column", 6: "k_transport_column"}
 
 
 def parse():
@@ -319,19 +321,32 @@ def run_ours(args, cfg, name):
     peak, peak_src = measured_hbm_peak()
     k_ms = res["local_kernel_ms"] / args.steps
     achieved = BYTES_PER_VOXEL_STEP * (res["local_voxel_steps"] / args.steps) / (k_ms * 1e-3) / 1e9
+    form = t.get_option("form")
+    kernel_name = FORMS.get(form, "k_transport_persistent")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(name), "peak_source": peak_src, "kernel": {0: "k_transport_simple", 2: "k_transport_exact"}.get(t.get_option("variant"), "k_transport_pool" if cfg["flags"] & 1 and t.get_option("variant") == 3 else "k_transport_persistent"),
+                "traffic": ncu_traffic(name + ":" + kernel_name) or ncu_traffic(name), "peak_source": peak_src, "kernel": kernel_name,
                 "kernel_ms": k_ms, "algorithmic_bytes_per_voxel_step": BYTES_PER_VOXEL_STEP,
-                "note": "random-walk + fp64 atomics: latency/ALU bound, see DESIGN.md; frac is against the HBM copy peak"}
-    probe = None
+                "note": "random walk over an L2-resident region with fp64 atomics: instruction-issue / L1TEX-address bound, not HBM "
+                        "bound (DESIGN.md section 3); frac is the algorithmic 16 B per voxel-step against the HBM copy peak"}
     if rank == 0 and not (cfg["flags"] & 1):
         try:
+            vs_rate = res["local_voxel_steps"] / args.steps / (k_ms * 1e-3)
+            t.set_option("probe_form", 0)
+            t.roofline_probe(packets, SEED)
             pms, psteps = t.roofline_probe(packets, SEED)
-            pms, psteps = t.roofline_probe(packets, SEED)
-            probe = {"voxel_steps_per_s": psteps / (pms * 1e-3), "ms": pms,
-                     "what": "L2-atomic / grid-lookup roofline: same address stream (column under the beam, geometric step count), one fp64 load of rhokap + one fp64 RED into jmean per voxel-step, no transport arithmetic"}
-            roofline["probe"] = probe
-            roofline["frac_of_probe"] = (res["local_voxel_steps"] / args.steps / (k_ms * 1e-3)) / probe["voxel_steps_per_s"]
+            roofline["probe"] = {"voxel_steps_per_s": psteps / (pms * 1e-3), "ms": pms,
+                                 "what": "L2-atomic / grid-lookup roofline of the step-by-step tally: same address stream (column under the beam, "
+                                         "geometric step count), one fp64 load of rhokap + one fp64 RED into jmean per voxel-step, no transport arithmetic"}
+            roofline["frac_of_probe"] = vs_rate / roofline["probe"]["voxel_steps_per_s"]
+            if form in (5, 6):
+                t.set_option("probe_form", 1)
+                t.roofline_probe(packets, SEED)
+                pms, psteps = t.roofline_probe(packets, SEED)
+                roofline["probe_column"] = {"voxel_steps_per_s": psteps / (pms * 1e-3), "ms": pms,
+                                            "what": "the same for the column form the kernel uses: per packet one 256-bit load of the z-fastest opacity copy per "
+                                                    "four voxels + one fp64 RED + at most one u32 RED, incl. the gather and finish kernels, no transport arithmetic"}
+                roofline["frac_of_probe_column"] = vs_rate / roofline["probe_column"]["voxel_steps_per_s"]
+            t.set_option("probe_form", -1)
         except Exception as e:  # the probe is context, never fatal
             roofline["probe_error"] = str(e)
 
@@ -399,7 +414,7 @@ def run_ours(args, cfg, name):
                        "parallelism": f"packets partitioned over {world} GPU(s), one Philox stream per packet, one ncclAllReduce(jmean) per step",
                        "l2": "flushed between timed steps (256 MiB device fill outside the timed events)",
                        "rng": "Philox4x32-10, key=seed, counter=(packet id, event)",
-                       "options": {k: t.get_option(k) for k in ("variant", "block", "ctas_per_sm", "chunk", "scatter_min", "merge", "min_ctas")}},
+                       "options": {k: t.get_option(k) for k in ("variant", "block", "ctas_per_sm", "chunk", "scatter_min", "merge", "min_ctas", "tile", "column")}},
             "voxel_steps_per_s": vsteps_per_s,
             "voxel_steps_per_packet": res["voxel_steps"] / total_packets,
             "breakdown_ms_per_step": {"kernel": res["kernel_ms"] / args.steps, "allreduce": res["allreduce_ms"] / args.steps,

@@ -148,12 +148,19 @@ double *tamc_rhokap_device(tamc_handle h); /* device opacity grid with halo */
 int tamc_pin_host(void *ptr, uint64_t bytes);
 int tamc_unpin_host(void *ptr);
 /* Tuning knobs: "variant" (0 thread-per-packet, 1 persistent warps, 2 exact arithmetic, 3 = default:
- * persistent warps + work-queue regrouping when scattering), "block" (0 = auto), "ctas_per_sm",
- * "chunk", "scatter_min", "merge", "min_ctas", "reduce" (0 = skip the all-reduce). */
+ * work-queue regrouping when scattering; in the shipped stub regime the column form for large calls
+ * under a wide beam, the shared-memory tally tile under a narrow one, persistent warps otherwise),
+ * "block" (0 = auto), "ctas_per_sm", "chunk", "scatter_min", "merge", "min_ctas",
+ * "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "reduce" (0 = skip the all-reduce),
+ * "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 = per-voxel-step
+ * address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the last MC call
+ * ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on the resident grid). */
 int tamc_set_option(tamc_handle h, const char *name, int64_t value);
 int64_t tamc_get_option(tamc_handle h, const char *name);
 /* Access-pattern-only kernel: the tally/grid address stream of `nphotons` straight-down packets
- * with no transport arithmetic; ms receives its device time, steps the voxel-steps issued. */
+ * with no transport arithmetic (per voxel-step one rhokap load + one jmean RED; in the column form
+ * per packet one 256-bit load per four voxels + at most two REDs); ms receives its device time,
+ * steps the voxel-steps it stands for. */
 int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *ms, int64_t *steps);
 /* Writes >= bytes of device memory to evict L2 between timed steps. */
 int tamc_flush_l2(tamc_handle h, uint64_t bytes);

@@ -118,3 +118,62 @@ def test_coupled_loop_two_ranks_equals_one_rank_with_all_packets(tmp_path):
     assert np.allclose(t.heat_array("temp"), a[0], rtol=1e-9, atol=0)
     assert np.array_equal(t.heat_array("rhokap") == 0, a[1] == 0)
     t.close()
+
+
+def _stub_worker(rank, world, port, out):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "tissue-ablation-mc_b200")]
+    import torch
+    import torch.distributed as dist
+
+    import tamc
+    from tamc import dist as tdist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = tamc.configs.CONFIGS["shipped80"]
+    t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=rank)
+    t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
+    t.comm_init(world, rank, tdist.broadcast_unique_id(tamc.comm_unique_id, dist))
+    grids = []
+    for column, box in ((0, 0), (0, -1), (1, -1), (1, 1), (2, 0)):
+        t.set_option("column", column)
+        t.set_option("box_reduce", box)
+        t.seek(0)
+        jm, st = t.run(60000, 7)
+        assert st["allreduce_ms"] > 0
+        grids.append(jm.copy())
+    np.save(f"{out}.{rank}.npy", np.stack(grids))
+    dist.barrier()
+    t.close()
+    dist.destroy_process_group()
+
+
+def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
+    """Shipped (stub) regime on two ranks: reducing only the columns under the beam equals reducing the whole grid, for
+    the step-by-step kernel and for the column form, and equals one GPU running all the ids."""
+    import torch
+
+    import tamc
+    from tests.util import compare_grids
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "stub")
+    mp.spawn(_stub_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = np.load(out + ".0.npy"), np.load(out + ".1.npy")
+    assert np.array_equal(a, b)
+    cfg = tamc.configs.CONFIGS["shipped80"]
+    t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=0)
+    t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
+    t.run_async(120000, 7, 0)
+    one = t.get_jmean()
+    t.close()
+    assert np.array_equal(a[0], a[1])                   # same kernel, box vs whole-grid reduction: same sums
+    for g in a:
+        compare_grids(g, one, rtol=1e-10)

@@ -216,7 +216,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_cnt); cudaFree(h->d_flush);
-    cudaFree(h->colws.stops); cudaFree(h->colws.rkT);
+    cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense);
     for (int i = 0; i < EV_N; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -302,7 +302,28 @@ static int enqueue_reduce(tamc_handle h)
     h->timed_reduce = false;
     if (h->comm && h->reduce && h->nranks > 1) {
         // mcpolar.f90:173: MPI_allREDUCE(jmean, jmeanGLOBAL, nxg*nyg*nzg, MPI_DOUBLE_PRECISION, MPI_SUM)
-        NC(nccl_api()->AllReduce(h->d_jmean, h->d_jmean, h->n_jmean, ncclDouble, ncclSum, h->comm, h->stream));
+        // Shipped regime (no scatter loop): every flight is straight down, so the tally is zero outside the columns under
+        // the beam's bounding box on every rank -- reduce only those.  The rule depends on the optics flags, the grid and
+        // the spot, which all ranks share, never on the packet count or the kernel a rank happened to run.
+        const DevGrid g = make_grid(h);
+        ColGeom cg;
+        const bool box = h->box_reduce != 0 && !(h->flags & (TAMC_SCATTER | TAMC_FRESNEL)) && beam_box(g, cg) &&
+                         (h->box_reduce > 0 || 2 * (size_t)cg.tw * cg.th <= (size_t)h->nxg * h->nyg);
+        if (box) {
+            const size_t cnt = (size_t)cg.tw * cg.th * h->nzg;
+            if (h->colws.dense_elems < cnt) {
+                cudaFree(h->colws.dense);
+                h->colws.dense = nullptr;
+                h->colws.dense_elems = 0;
+                CU(cudaMalloc(&h->colws.dense, cnt * sizeof(double)));
+                h->colws.dense_elems = cnt;
+            }
+            CU(launch_box_copy(g, cg, h->colws.dense, false, h->num_sms, h->stream));
+            NC(nccl_api()->AllReduce(h->colws.dense, h->colws.dense, cnt, ncclDouble, ncclSum, h->comm, h->stream));
+            CU(launch_box_copy(g, cg, h->colws.dense, true, h->num_sms, h->stream));
+        } else {
+            NC(nccl_api()->AllReduce(h->d_jmean, h->d_jmean, h->n_jmean, ncclDouble, ncclSum, h->comm, h->stream));
+        }
         h->timed_reduce = true;
     }
     CU(cudaEventRecord(h->ev[EV_AR1], h->stream));
@@ -325,7 +346,7 @@ extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int
     CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));   // zarray / jmean = 0. (mcpolar.f90:185)
     CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
-    CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches, &h->colws));
+    CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches, &h->colws, &h->form));
     CU(cudaEventRecord(h->ev[EV_K1], h->stream));
     if (int rc = enqueue_reduce(h)) return rc;
     h->last_launches = launches;
@@ -537,6 +558,9 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "tile")) return &h->cfg.tile;
     if (!strcmp(name, "column")) return &h->cfg.column;
     if (!strcmp(name, "reduce")) return &h->reduce;
+    if (!strcmp(name, "probe_form")) return &h->probe_form;
+    if (!strcmp(name, "box_reduce")) return &h->box_reduce;
+    if (!strcmp(name, "form")) return &h->form;
     return nullptr;
 }
 
@@ -544,6 +568,8 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
 {
     int *slot = option_slot(h, name);
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
+    if (slot == &h->form) return fail(TAMC_EINVAL, "form is read-only: the kernel the last MC call ran");
+    if (slot == &h->probe_form && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "probe_form must be -1, 0 or 1");
     if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");
     if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
@@ -569,7 +595,7 @@ extern "C" int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed
     CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));
     CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
-    CU(launch_probe(g, h->cfg, nphotons, (uint64_t)seed, h->d_cnt, h->stream));
+    CU(launch_probe(g, h->cfg, nphotons, (uint64_t)seed, h->d_cnt, h->stream, &h->colws, h->probe_form));
     CU(cudaEventRecord(h->ev[EV_K1], h->stream));
     CU(cudaStreamSynchronize(h->stream));
     float t = 0.f;

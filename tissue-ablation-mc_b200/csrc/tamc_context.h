@@ -37,6 +37,9 @@ struct tamc_context {
     tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1};
     tamc::ColumnWorkspace colws;
     int reduce = 1;
+    int box_reduce = -1;    // shipped regime: all-reduce only the columns under the beam (-1 = auto, 0 = off, 1 = on)
+    int form = -1;          // FORM_* of the last MC call
+    int probe_form = -1;    // tamc_roofline_probe: -1 = match the transport, 0 = per-voxel-step stream, 1 = column form
 
     tamc_heat *heat = nullptr;
 

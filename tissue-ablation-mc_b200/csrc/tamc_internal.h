@@ -22,27 +22,37 @@ struct LaunchCfg {
                         // 1 = on with the z-fastest copy of the beam's columns, 2 = on, reading the resident grid
 };
 
+// Which kernel an MC call ran ("form" read-only option of tamc_get_option)
+enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6 };
+
 // Device buffers of the column form, owned by the handle and grown on demand by launch_transport.
 struct ColumnWorkspace {
     unsigned int *stops = nullptr;   // nxg*nyg*nzg stop counts (plane 0: packets that left through the bottom face); all zero between calls
     size_t stops_elems = 0;
     double *rkT = nullptr;           // z-fastest copy of rhokap under the beam's bounding box
     size_t rkT_elems = 0;
+    double *dense = nullptr;         // (tw, th, nzg) staging of the tally under the box for the all-reduce
+    size_t dense_elems = 0;
 };
+
+// shipped regime: the columns every deposit lies in, and the copy between them and a dense buffer
+bool beam_box(const DevGrid &g, ColGeom &cg);
+cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s);
 
 // production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.
 // ws may be null (no column form).
 cudaError_t launch_transport(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
                              unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches,
-                             ColumnWorkspace *ws = nullptr);
+                             ColumnWorkspace *ws = nullptr, int *form = nullptr);
 
 // trace replay (tamc_replay.cu, compiled with -fmad=false)
 cudaError_t launch_replay(const DevGrid &g, long long n, const long long *d_off, const double *d_draws,
                           unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s);
 
-// access-pattern-only probe and utilities
+// access-pattern-only probe (probe_form: -1 = the form launch_transport would pick, 0 = per-voxel-step stream,
+// 1 = column form) and utilities
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,
-                         cudaStream_t s);
+                         cudaStream_t s, ColumnWorkspace *ws, int probe_form);
 cudaError_t launch_fill(double *p, size_t n, double v, int num_sms, cudaStream_t s);
 
 }  // namespace tamc

@@ -335,6 +335,49 @@ __global__ void __launch_bounds__(256) k_probe(const DevGrid g, long long n, uin
     if (keep == 123.456) cnt[CNT_N - 1] = 1ull;   // keeps the loads alive; never true for opacity sums
 }
 
+// The same for the column form (tamc_column.cuh): per packet one 256-bit load of the z-fastest opacity copy per
+// group of four voxels crossed, one fp64 RED (the partial deposit) and, unless the packet stops in the top plane, one
+// u32 RED (the stop count) -- and as little else as possible.
+__global__ void __launch_bounds__(256) k_probe_column(const DevGrid g, long long n, uint64_t seed, float disk_r_vox, const ColGeom cg,
+                                                      const double *__restrict__ rkT, unsigned int *__restrict__ stops,
+                                                      unsigned long long *__restrict__ cnt)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long steps = 0;
+    double keep = 0.;
+    const float cx = 0.5f * g.nxg, cy = 0.5f * g.nyg;
+    const double rk0 = __ldg(g.rhokap + ((long long)(g.nxg / 2) + (long long)g.sx * (g.nyg / 2) + g.sxy * g.nzg));
+    const float inv_logp = -1.f / ((float)rk0 * (float)(2. * g.zmax / g.nzg));
+    const int plane = g.nxg * g.nyg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1));
+        const float u0 = ((uint32_t)h & 0xffffffu) * 5.9604645e-8f, u1 = ((uint32_t)(h >> 24) & 0xffffffu) * 5.9604645e-8f;
+        const float u2 = ((uint32_t)(h >> 40) + 0.5f) * 5.9604645e-8f;
+        const float rr = disk_r_vox * __fsqrt_rn(u0);
+        float sn, cs;
+        __sincosf(6.2831853f * u1, &sn, &cs);
+        const int ci = min(cg.i0 + cg.tw - 1, max(cg.i0, (int)(cx + rr * cs) + 1));
+        const int cj = min(cg.j0 + cg.th - 1, max(cg.j0, (int)(cy + rr * sn) + 1));
+        int nst = 1 + (int)(__logf(u2) * inv_logp);                                   // geometric
+        nst = min(nst, g.nzg);
+        steps += (unsigned long long)nst;
+        const double *col = rkT + ((size_t)(cj - cg.j0) * cg.tw + (ci - cg.i0)) * cg.nzp;
+        const int kstop = g.nzg - nst + 1;
+        for (int gb = (g.nzg - 1) & ~3; gb >= ((kstop - 1) & ~3); gb -= 4) {
+            double a, b, c, d;
+            ldg256(col + gb, a, b, c, d);
+            keep += a + d;
+        }
+        const int j = (ci - 1) + g.nxg * ((cj - 1) + g.nyg * (kstop - 1));
+        atomicAdd(g.jmean + j, 1.0);
+        if (kstop < g.nzg) atomicAdd(stops + (j + plane), 1u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(cnt + CNT_STEPS, steps);
+    if (keep == 123.456) cnt[CNT_N - 1] = 1ull;
+}
+
 __global__ void __launch_bounds__(256) k_fill(double *__restrict__ p, size_t n, double v)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -375,17 +418,30 @@ static cudaError_t launch_sized(K kernel, const LaunchCfg &cfg, size_t smem, lon
 }
 
 // Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
-static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
-                                 unsigned long long *d_cnt, cudaStream_t s, int *launches, ColumnWorkspace *ws, bool gather)
+// Bounding box of the launch voxels: launch_fast computes celli = int(xcur*inv_dx) + 1 with |xcur - xmax| <= R, and
+// both the product and the truncation are monotonic, so the box below contains every launch voxel.
+bool beam_box(const DevGrid &g, ColGeom &cg)
 {
     const double R = sqrt(g.spot_r2);
-    ColGeom cg;
     cg.i0 = max(1, (int)((g.xmax - R) * g.inv_dx) + 1);
     cg.j0 = max(1, (int)((g.ymax - R) * g.inv_dy) + 1);
     cg.tw = min(g.nxg, (int)((g.xmax + R) * g.inv_dx) + 1) - cg.i0 + 1;
     cg.th = min(g.nyg, (int)((g.ymax + R) * g.inv_dy) + 1) - cg.j0 + 1;
     cg.nzp = (g.nzg + 3) & ~3;
-    if (cg.tw < 1 || cg.th < 1) return cudaErrorInvalidValue;
+    return cg.tw >= 1 && cg.th >= 1;
+}
+
+cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s)
+{
+    if (unpack) k_box_copy<true><<<num_sms * 8, 256, 0, s>>>(g, cg, dense);
+    else k_box_copy<false><<<num_sms * 8, 256, 0, s>>>(g, cg, dense);
+    return cudaGetLastError();
+}
+
+// the workspace of the column form (+ the z-fastest copy of the opacities under the box)
+static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gather, cudaStream_t s, ColGeom &cg)
+{
+    if (!beam_box(g, cg)) return cudaErrorInvalidValue;
     const size_t nstops = (size_t)g.nxg * g.nyg * g.nzg;
     if (ws->stops_elems < nstops) {
         cudaFree(ws->stops);
@@ -396,7 +452,6 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
         if (e != cudaSuccess) return e;
         ws->stops_elems = nstops;
     }
-    const size_t smem = sizeof(double) * (size_t)cg.nzp;
     if (gather) {
         const size_t nrk = (size_t)cg.tw * cg.th * cg.nzp;
         if (ws->rkT_elems < nrk) {
@@ -409,8 +464,31 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
         }
         const dim3 gg((cg.tw + 31) / 32, cg.th, (cg.nzp + 31) / 32);
         k_column_gather<<<gg, 256, 0, s>>>(g, cg, ws->rkT);
-        if (launches) *launches += 1;
     }
+    return cudaGetLastError();
+}
+
+// auto rule of the column form: calls large enough to pay for the two small extra kernels, and a footprint of more
+// than a few thousand columns -- under a narrow beam the partial-deposit REDs hit so few addresses that the L2
+// atomic unit serialises, and the shared-memory tile is the better form (measured: profiles/README.md)
+static bool column_wanted(const DevGrid &g, const LaunchCfg &cfg, long long n)
+{
+    if (cfg.variant != 3 || (g.flags & (TAMC_SCATTER | TAMC_FRESNEL)) || cfg.column == 0) return false;
+    if (cfg.column > 0) return true;
+    const double R = sqrt(g.spot_r2);
+    const double cols = (2. * R * g.inv_dx + 1.) * (2. * R * g.inv_dy + 1.);
+    return n >= (1ll << 20) && cols > 4096.;
+}
+
+// Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
+static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
+                                 unsigned long long *d_cnt, cudaStream_t s, int *launches, ColumnWorkspace *ws, bool gather)
+{
+    ColGeom cg;
+    cudaError_t e0 = column_setup(g, ws, gather, s, cg);
+    if (e0 != cudaSuccess) return e0;
+    if (launches && gather) *launches += 1;
+    const size_t smem = sizeof(double) * (size_t)cg.nzp;
     LaunchCfg c2 = cfg;
     c2.block = 256;
     cudaError_t e;
@@ -425,7 +503,7 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
 
 cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long long n, uint64_t seed, uint64_t first_id,
                              unsigned long long *d_cnt, tamc_packet_record *d_rec, cudaStream_t s, int *launches,
-                             ColumnWorkspace *ws)
+                             ColumnWorkspace *ws, int *form)
 {
     if (n <= 0) return cudaSuccess;
     DevGrid g = g_in;
@@ -439,18 +517,14 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     const bool merge = cfg.merge < 0 ? (g.flags & TAMC_SCATTER) != 0 : cfg.merge != 0;
     const size_t smem = faces_bytes(g);
     // shipped regime, default variant: the column form once the call is large enough to pay for its two small extra kernels
-    if (ws && !d_rec && cfg.variant == 3 && !(g.flags & (TAMC_SCATTER | TAMC_FRESNEL)) && cfg.column != 0) {
-        // auto: calls large enough to pay for the two small extra kernels, and a footprint of more than a few thousand
-        // columns -- under a narrow beam the partial-deposit REDs hit so few addresses that the L2 atomic unit
-        // serialises, and the shared-memory tile below is the better form (measured: profiles/README.md)
-        const double R = sqrt(g.spot_r2);
-        const double cols = (2. * R * g.inv_dx + 1.) * (2. * R * g.inv_dy + 1.);
-        if (cfg.column > 0 || (n >= (1ll << 20) && cols > 4096.))
-            return launch_column(g, cfg, n, seed, first_id, d_cnt, s, launches, ws, cfg.column != 2);
+    if (ws && !d_rec && column_wanted(g, cfg, n)) {
+        if (form) *form = cfg.column == 2 ? FORM_COLUMN_RESIDENT : FORM_COLUMN;
+        return launch_column(g, cfg, n, seed, first_id, d_cnt, s, launches, ws, cfg.column != 2);
     }
     if (launches) *launches += 1;
     tamc_packet_record *none = nullptr;
 
+    if (form) *form = cfg.variant == 2 ? FORM_EXACT : ((d_rec || cfg.variant == 0 || ((g.flags & TAMC_FRESNEL) && !(g.flags & TAMC_SCATTER))) ? FORM_SIMPLE : (pool ? FORM_POOL : FORM_PERSISTENT));
     if (cfg.variant == 2) {
         if (d_rec) {
             if (merge) return launch_sized(k_transport_exact<MergeTally, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
@@ -511,6 +585,7 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
             int chunk = cfg.chunk > 0 ? cfg.chunk : 1024;
             cudaError_t e = cudaFuncSetAttribute(k_transport_stub_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
             if (e != cudaSuccess) return e;
+            if (form) *form = FORM_TILE;
             k_transport_stub_tiled<<<cfg.num_sms, 1024, tsmem, s>>>(g, n, seed, first_id, chunk, tg, d_cnt);
             return cudaGetLastError();
         }
@@ -538,11 +613,22 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
 }
 
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,
-                         cudaStream_t s)
+                         cudaStream_t s, ColumnWorkspace *ws, int probe_form)
 {
     const float disk_r_vox = (float)(sqrt(g.spot_r2) * g.inv_dx);
     LaunchCfg c2 = cfg;
-    if (c2.block <= 0) c2.block = 256;
+    c2.block = 256;
+    const bool column = probe_form < 0 ? (ws && column_wanted(g, cfg, n)) : probe_form == 1;
+    if (column && ws) {
+        ColGeom cg;
+        cudaError_t e = column_setup(g, ws, true, s, cg);
+        if (e != cudaSuccess) return e;
+        e = launch_sized(k_probe_column, c2, 0, n, s, g, n, seed, disk_r_vox, cg, (const double *)ws->rkT, ws->stops, d_cnt);
+        if (e != cudaSuccess) return e;
+        const size_t smem = sizeof(double) * (size_t)cg.nzp;
+        k_column_finish<<<(cg.tw * cg.th + 127) / 128, 128, smem, s>>>(g, cg, ws->stops);
+        return cudaGetLastError();
+    }
     return launch_sized(k_probe, c2, 0, n, s, g, n, seed, disk_r_vox, d_cnt);
 }
 

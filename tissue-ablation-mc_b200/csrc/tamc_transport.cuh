@@ -57,6 +57,13 @@ struct DevGrid {
     uint32_t rk[20];      // Philox round keys of this call's seed: key + r*(0x9E3779B9, 0xBB67AE85), r = 0..9 (production kernels)
 };
 
+// Bounding box of the beam's footprint on the top face (shipped regime: every flight stays inside these columns).
+struct ColGeom {
+    int i0, j0;        // first voxel (1-based) of the box in x and y
+    int tw, th;        // its extent
+    int nzp;           // column length of the z-fastest opacity copy: nzg rounded up to a multiple of 4
+};
+
 // ---------------------------------------------------------------------------------------------
 // RNG: Philox4x32-10, key = run seed, counter = (packet id lo, hi, draw block, 0).
 // One block = 4 uniforms = exactly what one event consumes (launch: r, theta, phi, tau;
