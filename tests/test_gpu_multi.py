@@ -174,6 +174,6 @@ def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
     t.run_async(120000, 7, 0)
     one = t.get_jmean()
     t.close()
-    assert np.array_equal(a[0], a[1])                   # same kernel, box vs whole-grid reduction: same sums
+    compare_grids(a[0], a[1], rtol=1e-12)               # same kernel, box vs whole-grid reduction (atomics order differs)
     for g in a:
         compare_grids(g, one, rtol=1e-10)
