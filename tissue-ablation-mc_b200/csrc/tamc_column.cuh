@@ -152,43 +152,54 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGri
     }
 }
 
-// Full-crossing deposits: one thread per bounding-box column walks up from the bottom, F = packets that stopped
-// below the voxel (stops plane k holds the packets that stopped in voxel k, plane 0 those that left through the
-// bottom face), jmean(i,j,k) += F * dcell(k) * rhokap(i,j,k).  Clears the counts it consumed, so the array is
-// all zero again for the next call.  Lanes run along x: every access is coalesced.
-__global__ void __launch_bounds__(128) k_column_finish(const DevGrid g, const ColGeom cg, unsigned int *__restrict__ stops)
+// Full-crossing deposits.  F(i,j,k) = packets of the column that stopped below voxel k = the running sum of the stop
+// counts up the column (plane k of `stops` holds the packets that stopped in voxel k, plane 0 those that left through
+// the bottom face); jmean(i,j,k) += F * dcell(k) * rhokap(i,j,k).  A CTA takes 32 columns (lanes along x: coalesced)
+// times kFinishChunks z-chunks: every thread first sums the counts of its chunk, a scan over the chunks of a column
+// gives each thread its starting F, then it walks its chunk.  Clears the counts it consumed, so the array is all zero
+// again for the next call.
+constexpr int kFinishChunks = 32;
+
+__global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevGrid g, const ColGeom cg, unsigned int *__restrict__ stops)
 {
     extern __shared__ double s_dz[];
+    __shared__ unsigned long long s_sum[kFinishChunks][32];
     stage_column_steps(g, cg.nzp, s_dz);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= cg.tw * cg.th) return;
-    const int i = cg.i0 + t % cg.tw, j = cg.j0 + t / cg.tw;
+    const int lane = threadIdx.x & 31, chunk = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const bool live = t < cg.tw * cg.th;
+    const int i = cg.i0 + (live ? t % cg.tw : 0), j = cg.j0 + (live ? t / cg.tw : 0);
     const int plane = g.nxg * g.nyg;
     const int c0 = (i - 1) + g.nxg * (j - 1);
-    long long r0 = (long long)i + (long long)g.sx * j;
-    unsigned long long F = stops[c0];
-    if (F) stops[c0] = 0u;
-    constexpr int kBatch = 8;
-    for (int kb = 1; kb <= g.nzg; kb += kBatch) {
-        unsigned int c[kBatch];
-        double rk[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            const int k = kb + q;
-            c[q] = (k < g.nzg) ? stops[c0 + k * plane] : 0u;            // the top plane is never recorded
-            rk[q] = (k <= g.nzg) ? __ldg(g.rhokap + r0 + g.sxy * k) : 0.;
+    const long long r0 = (long long)i + (long long)g.sx * j;
+    const int len = (g.nzg + kFinishChunks - 1) / kFinishChunks;
+    const int klo = chunk * len + 1, khi = min(g.nzg, klo + len - 1);      // voxels of this chunk
+
+    // counts of planes klo .. khi (the top plane nzg is never recorded); chunk 0 also takes plane 0
+    unsigned long long a = 0ull;
+    if (live) {
+        if (chunk == 0) a = stops[c0];
+        for (int k = klo; k <= min(khi, g.nzg - 1); ++k) a += stops[c0 + k * plane];
+    }
+    s_sum[chunk][lane] = a;
+    __syncthreads();
+    if (!live) return;
+    // F of the first voxel of the chunk: plane 0 + every plane below klo
+    // (s_sum[c] covers planes c*len+1 .. (c+1)*len, plus plane 0 for c = 0: together exactly the planes <= klo - 1)
+    unsigned long long F = 0ull;
+    if (chunk == 0) {
+        F = stops[c0];
+        if (F) stops[c0] = 0u;
+    } else {
+        for (int c = 0; c < chunk; ++c) F += s_sum[c][lane];
+    }
+    for (int k = klo; k <= khi; ++k) {
+        const unsigned int c = (k < g.nzg) ? stops[c0 + k * plane] : 0u;
+        if (F) {
+            const double d = (double)F * (s_dz[k - 1] * __ldg(g.rhokap + r0 + g.sxy * k));
+            if (d != 0.) g.jmean[c0 + (k - 1) * plane] += d;
         }
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            const int k = kb + q;
-            if (k <= g.nzg) {
-                if (F) {
-                    const double d = (double)F * (s_dz[k - 1] * rk[q]);
-                    if (d != 0.) g.jmean[c0 + (k - 1) * plane] += d;
-                }
-                if (c[q]) { F += c[q]; stops[c0 + k * plane] = 0u; }
-            }
-        }
+        if (c) { F += c; stops[c0 + k * plane] = 0u; }
     }
 }
 

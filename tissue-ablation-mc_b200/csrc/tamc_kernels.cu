@@ -496,7 +496,7 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     else if (cfg.min_ctas == 2) e = launch_sized(k_transport_column<true, 6>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     else e = launch_sized(k_transport_column<true, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     if (e != cudaSuccess) return e;
-    k_column_finish<<<(cg.tw * cg.th + 127) / 128, 128, smem, s>>>(g, cg, ws->stops);
+    k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(g, cg, ws->stops);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
@@ -626,7 +626,7 @@ cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, ui
         e = launch_sized(k_probe_column, c2, 0, n, s, g, n, seed, disk_r_vox, cg, (const double *)ws->rkT, ws->stops, d_cnt);
         if (e != cudaSuccess) return e;
         const size_t smem = sizeof(double) * (size_t)cg.nzp;
-        k_column_finish<<<(cg.tw * cg.th + 127) / 128, 128, smem, s>>>(g, cg, ws->stops);
+        k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(g, cg, ws->stops);
         return cudaGetLastError();
     }
     return launch_sized(k_probe, c2, 0, n, s, g, n, seed, disk_r_vox, d_cnt);
