@@ -11,7 +11,7 @@ per GPU per step (weak scaling: every rank runs its own 1e8, like the reference'
   python bench.py --impl reference ...                     the reference's CPU path (oracle port, all host threads)
 
 One JSON line on stdout (rank 0).  `value` times the device-resident call (inputs already in HBM);
-`e2e` times tamc_set_optics + tamc_run with pinned HOST buffers, copies inside the timed region.
+`e2e` times tamc_run_optics (= tamc_set_optics + tamc_run) with pinned HOST buffers, copies inside the timed region.
 """
 from __future__ import annotations
 
@@ -295,16 +295,15 @@ def run_ours(args, cfg, name):
     jm = t.new_jmean()
     tamc.pin_host(jm)
     for _ in range(2):
-        t.set_optics(rk, cfg["albedo"], cfg["hgg"], flags=cfg["flags"])
-        t.run(packets, SEED, out=jm)
+        t.run_optics(rk, cfg["albedo"], cfg["hgg"], packets, SEED, flags=cfg["flags"], out=jm)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     e0 = time.perf_counter()
     e2e_parts = {"h2d_ms": 0.0, "d2h_ms": 0.0, "kernel_ms": 0.0, "allreduce_ms": 0.0}
     for _ in range(args.steps):
-        t.set_optics(rk, cfg["albedo"], cfg["hgg"], flags=cfg["flags"])      # H2D, as after every setupThermalCoeff
-        _, st = t.run(packets, SEED, out=jm)                                   # zero + transport + all-reduce + D2H
+        # H2D of rhokap (as after every setupThermalCoeff) + zero + transport + all-reduce + D2H of jmeanGLOBAL
+        _, st = t.run_optics(rk, cfg["albedo"], cfg["hgg"], packets, SEED, flags=cfg["flags"], out=jm)
         for k in e2e_parts:
             e2e_parts[k] += st[k] / args.steps
     torch.cuda.synchronize(dev)
@@ -422,7 +421,9 @@ def run_ours(args, cfg, name):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rk.nbytes), "d2h_bytes_per_step": int(jm.nbytes),
                     "ms_per_step": 1e3 * float(e2e_s.item()) / args.steps, "parts_ms": e2e_parts,
-                    "api": "tamc_set_optics(host rhokap) + tamc_run(host jmeanGLOBAL), pinned host arrays",
+                    "api": "tamc_run_optics(host rhokap -> host jmeanGLOBAL) = tamc_set_optics + tamc_run, pinned host arrays; io_form %d "
+                           "(bit0: jmeanGLOBAL written as zero fill beside the kernels + the beam's columns, bit1: the beam's columns of "
+                           "rhokap uploaded ahead of the full grid); parts_ms h2d/d2h time only the copies not hidden behind the transport" % t.get_option("io_form"),
                     "jmean_sum_per_packet": jm_sum / (packets * world)},
             "gpu_launches": int(res["launches"]), "clocks": clocks, "also": also,
         }

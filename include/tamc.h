@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TAMC_VERSION 101
+#define TAMC_VERSION 102
 
 enum {
     TAMC_OK = 0,
@@ -109,6 +109,20 @@ int tamc_set_optics(tamc_handle h, const double *rhokap, double albedo, double h
  * counter; ids are taken from the handle's cursor, which advances by nranks*nphotons per call so
  * repeated calls (the ablation loop) never reuse a stream.  Blocking.  stats may be NULL. */
 int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats);
+
+/* One pass of the ablation loop's MC side in a single call: tamc_set_optics(rhokap, ...) followed by
+ * tamc_run(...), i.e. mcpolar.f90:151-173 as it runs after every setupThermalCoeff (3dFD.f90:312-361).
+ * Same arguments, same results in jmean_global and on the device as the two calls; rhokap == NULL keeps
+ * the resident grid.  Having both arrays in one call lets the library overlap the PCIe copies with the
+ * transport when they are page-locked (tamc_pin_host) and the scatter loop is off: the tally is zero
+ * outside the columns under the beam, so jmean_global is written as a zero fill that runs beside the
+ * kernels plus a pitched copy of those columns, and the opacities of those columns are uploaded ahead
+ * of the full grid, which follows on a second stream.  Options "box_io" (-1 auto, 0 = plain copies in
+ * sequence) and read-only "io_form" (bit0: columns-only download, bit1: columns-first upload).
+ * tamc_run alone uses the same download.  In that mode stats->h2d_ms / d2h_ms time only the column copies
+ * that are not hidden behind the transport. */
+int tamc_run_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2, int flags,
+                    int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats);
 
 /* Same work, split so a driver can overlap it or keep the tally on the device:
  * enqueue tally clear + transport + all-reduce on the handle's stream; first_packet_id < 0 takes

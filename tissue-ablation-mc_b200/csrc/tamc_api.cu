@@ -217,6 +217,9 @@ extern "C" int tamc_finalize(tamc_handle h)
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_cnt); cudaFree(h->d_flush);
     cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense);
+    if (h->s_up) { cudaStreamSynchronize(h->s_up); cudaStreamDestroy(h->s_up); }
+    if (h->s_dn) { cudaStreamSynchronize(h->s_dn); cudaStreamDestroy(h->s_dn); }
+    cudaFree(h->d_zero); cudaFree(h->d_box_rk);
     for (int i = 0; i < EV_N; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -236,28 +239,42 @@ extern "C" int tamc_set_source_co2(tamc_handle h, double spot_diameter_cm)
     return TAMC_OK;
 }
 
+static int check_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2, int flags, const char *who)
+{
+    const std::string w(who);
+    if (!(albedo >= 0. && albedo <= 1.)) return fail(TAMC_EINVAL, w + ": albedo must be in [0,1]");
+    if (!(hgg > -1. && hgg < 1.)) return fail(TAMC_EINVAL, w + ": hgg must be in (-1,1)");
+    if (flags & ~(TAMC_SCATTER | TAMC_FRESNEL)) return fail(TAMC_EINVAL, w + ": unknown flag bits");
+    if ((flags & TAMC_FRESNEL) && !(n1 > 0. && n2 > 0.)) return fail(TAMC_EINVAL, w + ": TAMC_FRESNEL needs positive n1, n2");
+    if (!rhokap && !h->optics_set) return fail(TAMC_ESTATE, w + ": first call needs the rhokap grid");
+    return TAMC_OK;
+}
+
+// full-grid upload on the handle's stream, not synchronised
+static int enqueue_upload(tamc_handle h, const double *rhokap)
+{
+    CU(cudaEventRecord(h->ev[EV_H0], h->stream));
+    if (host_is_pinned(rhokap))
+        CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else {
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CU(cudaEventRecord(h->ev[EV_H1], h->stream));
+    h->timed_h2d = true;
+    return TAMC_OK;
+}
+
 extern "C" int tamc_set_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2,
                                int flags)
 {
     if (int rc = check(h)) return rc;
-    if (!(albedo >= 0. && albedo <= 1.)) return fail(TAMC_EINVAL, "tamc_set_optics: albedo must be in [0,1]");
-    if (!(hgg > -1. && hgg < 1.)) return fail(TAMC_EINVAL, "tamc_set_optics: hgg must be in (-1,1)");
-    if (flags & ~(TAMC_SCATTER | TAMC_FRESNEL)) return fail(TAMC_EINVAL, "tamc_set_optics: unknown flag bits");
-    if ((flags & TAMC_FRESNEL) && !(n1 > 0. && n2 > 0.)) return fail(TAMC_EINVAL, "tamc_set_optics: TAMC_FRESNEL needs positive n1, n2");
-    if (!rhokap && !h->optics_set) return fail(TAMC_ESTATE, "tamc_set_optics: first call needs the rhokap grid");
+    if (int rc = check_optics(h, rhokap, albedo, hgg, n1, n2, flags, "tamc_set_optics")) return rc;
     h->timed_h2d = false;
     if (rhokap) {
-        CU(cudaEventRecord(h->ev[EV_H0], h->stream));
-        if (host_is_pinned(rhokap))
-            CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        else {
-            CU(cudaStreamSynchronize(h->stream));
-            CU(cudaMemcpy(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice));
-        }
-        CU(cudaEventRecord(h->ev[EV_H1], h->stream));
+        if (int rc = enqueue_upload(h, rhokap)) return rc;
         // the caller may rewrite rhokap as soon as this returns (no host pointer is kept past the call)
         CU(cudaStreamSynchronize(h->stream));
-        h->timed_h2d = true;
     }
     h->albedo = albedo; h->hgg = hgg; h->n1 = n1; h->n2 = n2; h->flags = flags;
     h->optics_set = true;
@@ -330,9 +347,9 @@ static int enqueue_reduce(tamc_handle h)
     return TAMC_OK;
 }
 
-extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id)
+// tally clear + transport + all-reduce on the handle's stream
+static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id)
 {
-    if (int rc = check(h)) return rc;
     if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run: tamc_set_optics has not been called");
     if (nphotons < 0 || nphotons > ((int64_t)1 << 46)) return fail(TAMC_EINVAL, "tamc_run: nphotons out of range");
     int64_t first = first_packet_id;
@@ -353,6 +370,12 @@ extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int
     h->timed_d2h = false;
     h->ran = true;
     return TAMC_OK;
+}
+
+extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id)
+{
+    if (int rc = check(h)) return rc;
+    return enqueue_mc(h, nphotons, seed, first_packet_id);
 }
 
 extern "C" int tamc_sync(tamc_handle h)
@@ -400,6 +423,7 @@ extern "C" int tamc_get_stats(tamc_handle h, tamc_stats *st)
     CU(cudaEventElapsedTime(&ms, h->ev[EV_K0], h->ev[EV_K1])); st->kernel_ms = ms;
     if (h->timed_reduce) { CU(cudaEventElapsedTime(&ms, h->ev[EV_K1], h->ev[EV_AR1])); st->allreduce_ms = ms; }
     if (h->timed_h2d) { CU(cudaEventElapsedTime(&ms, h->ev[EV_H0], h->ev[EV_H1])); st->h2d_ms = ms; }
+    if (h->timed_h2d && (h->io_form & 2)) st->kernel_ms -= st->h2d_ms;     // k_column_gather over PCIe sits inside K0..K1
     if (h->timed_d2h) { CU(cudaEventElapsedTime(&ms, h->ev[EV_D0], h->ev[EV_D1])); st->d2h_ms = ms; }
     st->gpu_launches = h->last_launches;
     if (cnt[CNT_ERRORS])
@@ -414,14 +438,150 @@ extern "C" int tamc_seek(tamc_handle h, int64_t next_packet_id)
     return TAMC_OK;
 }
 
-extern "C" int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
+// ------------------------------------------------------------------------------------------------
+// The boundary with the host driver, overlapped (shipped regime).
+//
+// Without the scatter loop every flight is straight down (sourceph.f90:37-42, mcpolar.f90:166-169), so
+//   * the tally is zero outside the columns under the beam's bounding box -- jmeanGLOBAL is written as a zero fill
+//     (device zeros -> host, a DMA on its own stream WHILE the transport runs) followed by the box columns after the
+//     all-reduce (k_box_mirror stores them straight into the caller's array; long calls use one pitched 3-D DMA whose
+//     descriptors are submitted while the transport runs): the same bytes in host memory as the plain full-grid download;
+//   * the column form reads the opacities of those columns only -- in tamc_run_optics k_column_gather fetches them
+//     straight from the caller's array (each voxel once) and the DMA of the full grid, which later calls and the heat
+//     step read, follows on a second stream beside the transport.
+// The kernels access page-locked host memory over PCIe (zero-copy) in 256-byte row segments: no per-slice DMA
+// descriptors to submit (a pitched 3-D cudaMemcpy of the box costs ~0.3 ms of host time at 200^3) ahead of the transport.
+// PCIe is full duplex, so the step costs  box up + transport + box down  instead of  grid up + transport + grid down.
+// Needs page-locked host arrays (tamc_pin_host); anything else takes the plain sequential path.
+// ------------------------------------------------------------------------------------------------
+static int side_streams(tamc_handle h)
 {
-    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_run: jmean_global is null");
-    if (int rc = tamc_run_async(h, nphotons, seed, -1)) return rc;
-    if (int rc = tamc_get_jmean(h, jmean_global)) return rc;
+    if (!h->s_up) CU(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    if (!h->s_dn) CU(cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
+    if (!h->d_zero) {
+        CU(cudaMalloc(&h->d_zero, h->n_jmean * sizeof(double)));
+        CU(cudaMemsetAsync(h->d_zero, 0, h->n_jmean * sizeof(double), h->s_dn));
+    }
+    return TAMC_OK;
+}
+
+static bool box_io_wanted(tamc_handle h, int flags, ColGeom &cg)
+{
+    if (h->box_io == 0 || (flags & (TAMC_SCATTER | TAMC_FRESNEL))) return false;
+    const DevGrid g = make_grid(h);
+    return beam_box(g, cg) && 2 * (size_t)cg.tw * cg.th <= (size_t)h->nxg * h->nyg;
+}
+
+static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
+{
+    ColGeom cg{};
+    const DevGrid g = make_grid(h);
+    // device-visible addresses of the caller's page-locked arrays (cudaHostRegister / cudaHostAlloc memory is mapped)
+    double *jm_dev = nullptr;
+    const double *rk_dev = nullptr;
+    bool box_dn = box_io_wanted(h, h->flags, cg) && host_is_pinned(jmean_global);
+    if (box_dn && cudaHostGetDevicePointer((void **)&jm_dev, jmean_global, 0) != cudaSuccess) { cudaGetLastError(); box_dn = false; }
+    bool box_up = rhokap && box_dn && host_is_pinned(rhokap) && column_gather_selected(g, h->cfg, nphotons);
+    if (box_up && cudaHostGetDevicePointer((void **)&rk_dev, const_cast<double *>(rhokap), 0) != cudaSuccess) { cudaGetLastError(); box_up = false; }
+    h->io_form = (box_dn ? 1 : 0) | (box_up ? 2 : 0);
+    if (rhokap) h->timed_h2d = false;   // otherwise keep the upload time of the tamc_set_optics before this call
+
+    if (box_dn) {
+        if (int rc = side_streams(h)) return rc;
+        // nothing of this call may overtake work already queued on the handle's stream
+        CU(cudaEventRecord(h->ev[EV_FORK], h->stream));
+        CU(cudaStreamWaitEvent(h->s_dn, h->ev[EV_FORK], 0));
+        if (!box_up) {      // with a columns-first upload the fill starts behind it (below): measured, the two slow each other
+            CU(cudaMemcpyAsync(jmean_global, h->d_zero, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->s_dn));
+            CU(cudaEventRecord(h->ev[EV_DN], h->s_dn));
+        }
+    }
+    if (box_up) {
+        const size_t need = (size_t)cg.tw * cg.th * (size_t)h->nzg;
+        if (h->box_rk_elems < need) {
+            cudaFree(h->d_box_rk);
+            h->d_box_rk = nullptr;
+            h->box_rk_elems = 0;
+            CU(cudaMalloc(&h->d_box_rk, need * sizeof(double)));
+            h->box_rk_elems = need;
+        }
+        // k_column_gather reads the beam's columns straight from the caller's array and k_column_finish the copy it keeps
+        h->colws.gather_src = rk_dev;
+        h->colws.box_rk = h->d_box_rk;
+        h->colws.ev_gather0 = h->ev[EV_H0];
+        h->colws.ev_gather1 = h->ev[EV_H1];
+    } else if (rhokap) {
+        if (int rc = enqueue_upload(h, rhokap)) return rc;
+    }
+
+    const int rc_mc = enqueue_mc(h, nphotons, seed, -1);
+    h->colws.gather_src = nullptr;
+    h->colws.box_rk = nullptr;
+    h->colws.ev_gather0 = h->colws.ev_gather1 = nullptr;
+    if (rc_mc) {
+        cudaStreamSynchronize(h->stream);
+        if (box_dn) cudaStreamSynchronize(h->s_dn);
+        return rc_mc;
+    }
+    if (box_up) {
+        // the full grid, for every later reader of the resident rhokap: behind the column upload so the two do not share
+        // the link, beside the transport (which no longer reads the resident grid in this call)
+        h->timed_h2d = true;
+        CU(cudaStreamWaitEvent(h->s_dn, h->ev[EV_H1], 0));
+        CU(cudaMemcpyAsync(jmean_global, h->d_zero, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->s_dn));
+        CU(cudaEventRecord(h->ev[EV_DN], h->s_dn));
+        CU(cudaStreamWaitEvent(h->s_up, h->ev[EV_H1], 0));
+        CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
+        CU(cudaEventRecord(h->ev[EV_UP], h->s_up));
+    }
+
+    if (box_dn) {
+        CU(cudaStreamWaitEvent(h->stream, h->ev[EV_DN], 0));          // the zero fill lands first
+        CU(cudaEventRecord(h->ev[EV_D0], h->stream));
+        if (nphotons >= ((int64_t)1 << 22)) {
+            // long call: one pitched 3-D DMA (52 GB/s; its per-slice descriptors are submitted while the transport runs)
+            cudaMemcpy3DParms p{};
+            p.srcPtr = make_cudaPitchedPtr(h->d_jmean, (size_t)h->nxg * sizeof(double), (size_t)h->nxg, (size_t)h->nyg);
+            p.srcPos = make_cudaPos((size_t)(cg.i0 - 1) * sizeof(double), (size_t)(cg.j0 - 1), 0);
+            p.dstPtr = make_cudaPitchedPtr(jmean_global, (size_t)h->nxg * sizeof(double), (size_t)h->nxg, (size_t)h->nyg);
+            p.dstPos = p.srcPos;
+            p.extent = make_cudaExtent((size_t)cg.tw * sizeof(double), (size_t)cg.th, (size_t)h->nzg);
+            p.kind = cudaMemcpyDeviceToHost;
+            CU(cudaMemcpy3DAsync(&p, h->stream));
+        } else      // short call: posted writes from a kernel (41 GB/s, nothing to submit per slice)
+            CU(launch_box_mirror(g, cg, jm_dev, h->num_sms, h->stream));
+        CU(cudaEventRecord(h->ev[EV_D1], h->stream));
+        if (box_up) CU(cudaStreamWaitEvent(h->stream, h->ev[EV_UP], 0));
+        CU(cudaStreamSynchronize(h->stream));
+        h->timed_d2h = true;
+        if (nphotons < ((int64_t)1 << 22)) h->last_launches += 1;
+    } else {
+        if (int rc = tamc_get_jmean(h, jmean_global)) return rc;
+    }
     if (stats) return tamc_get_stats(h, stats);
     tamc_stats tmp;
     return tamc_get_stats(h, &tmp);   // surfaces transport errors even when the caller wants no stats
+}
+
+extern "C" int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
+{
+    if (int rc = check(h)) return rc;
+    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_run: jmean_global is null");
+    if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run: tamc_set_optics has not been called");
+    if (nphotons < 0 || nphotons > ((int64_t)1 << 46)) return fail(TAMC_EINVAL, "tamc_run: nphotons out of range");
+    return run_boundary(h, nullptr, nphotons, seed, jmean_global, stats);
+}
+
+extern "C" int tamc_run_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2, int flags,
+                               int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
+{
+    if (int rc = check(h)) return rc;
+    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_run_optics: jmean_global is null");
+    if (int rc = check_optics(h, rhokap, albedo, hgg, n1, n2, flags, "tamc_run_optics")) return rc;
+    if (nphotons < 0 || nphotons > ((int64_t)1 << 46)) return fail(TAMC_EINVAL, "tamc_run_optics: nphotons out of range");
+    h->albedo = albedo; h->hgg = hgg; h->n1 = n1; h->n2 = n2; h->flags = flags;
+    h->optics_set = true;
+    return run_boundary(h, rhokap, nphotons, seed, jmean_global, stats);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -561,6 +721,8 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "probe_form")) return &h->probe_form;
     if (!strcmp(name, "box_reduce")) return &h->box_reduce;
     if (!strcmp(name, "form")) return &h->form;
+    if (!strcmp(name, "box_io")) return &h->box_io;
+    if (!strcmp(name, "io_form")) return &h->io_form;
     return nullptr;
 }
 
@@ -569,6 +731,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     int *slot = option_slot(h, name);
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
     if (slot == &h->form) return fail(TAMC_EINVAL, "form is read-only: the kernel the last MC call ran");
+    if (slot == &h->io_form) return fail(TAMC_EINVAL, "io_form is read-only: how the last tamc_run moved its arrays");
     if (slot == &h->probe_form && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "probe_form must be -1, 0 or 1");
     if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");

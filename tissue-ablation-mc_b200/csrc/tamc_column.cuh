@@ -31,18 +31,30 @@ namespace tamc {
 
 // z-fastest copy of the bounding-box columns: rkT[(dj*tw + di)*nzp + (k-1)] = rhokap(i0+di, j0+dj, k).
 // 32 x 32 (x, z) tiles through shared memory: reads coalesced along x, writes coalesced along z.
-__global__ void __launch_bounds__(256) k_column_gather(const DevGrid g, const ColGeom cg, double *__restrict__ rkT)
+// `src` is the opacity grid in the reference's layout (halo included): the resident copy, or -- tamc_run_optics, the
+// columns-first upload -- the caller's page-locked host array read over PCIe (zero-copy; every voxel of the box is read
+// exactly once, in 256-byte row segments).  kBox: also keep the tile in x-fastest order, box[di + tw*(dj + th*(k-1))],
+// for k_column_finish, so nothing on this call's critical path waits for the full-grid upload.
+template <bool kBox>
+__global__ void __launch_bounds__(256) k_column_gather(const DevGrid g, const ColGeom cg, const double *__restrict__ src,
+                                                       double *__restrict__ rkT, double *__restrict__ box)
 {
     __shared__ double tile[32][33];
     const int dj = blockIdx.y, di0 = blockIdx.x * 32, kz0 = blockIdx.z * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long rowj = (long long)g.sx * (cg.j0 + dj);
+    double v[4];
 #pragma unroll
-    for (int r = 0; r < 32; r += 8) {
-        const int kz = kz0 + r + ty, di = di0 + tx;          // kz = k - 1
-        double v = 0.;
-        if (di < cg.tw && kz < g.nzg) v = g.rhokap[(cg.i0 + di) + rowj + g.sxy * (kz + 1)];
-        tile[r + ty][tx] = v;
+    for (int r = 0; r < 4; ++r) {                                // all four loads in flight before the first use
+        const int kz = kz0 + 8 * r + ty, di = di0 + tx;          // kz = k - 1
+        v[r] = 0.;
+        if (di < cg.tw && kz < g.nzg) v[r] = src[(cg.i0 + di) + rowj + g.sxy * (kz + 1)];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int kz = kz0 + 8 * r + ty, di = di0 + tx;
+        tile[8 * r + ty][tx] = v[r];
+        if (kBox && di < cg.tw && kz < g.nzg) box[di + (size_t)cg.tw * (dj + (size_t)cg.th * kz)] = v[r];
     }
     __syncthreads();
 #pragma unroll
@@ -218,6 +230,20 @@ __global__ void __launch_bounds__(256) k_box_copy(const DevGrid g, const ColGeom
         const size_t j = (size_t)(cg.i0 - 1 + di) + (size_t)g.nxg * ((size_t)(cg.j0 - 1 + dj) + (size_t)g.nyg * kz);
         if (kUnpack) g.jmean[j] = dense[t];
         else dense[t] = g.jmean[j];
+    }
+}
+
+// The tally under the beam's bounding box -> the same voxels of `dst`, an array in the tally's own layout: the caller's
+// page-locked jmeanGLOBAL, written over PCIe (posted writes, 256-byte row segments).  The rest of jmeanGLOBAL is zero
+// fill that travelled while the transport ran (tamc_api.cu).
+__global__ void __launch_bounds__(256) k_box_mirror(const DevGrid g, const ColGeom cg, double *__restrict__ dst)
+{
+    const int rows = cg.th * g.nzg;
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < rows; r += nwarps) {
+        const int dj = r % cg.th, kz = r / cg.th;
+        const size_t row = (size_t)(cg.i0 - 1) + (size_t)g.nxg * ((size_t)(cg.j0 - 1 + dj) + (size_t)g.nyg * kz);
+        for (int di = lane; di < cg.tw; di += 32) dst[row + di] = g.jmean[row + di];
     }
 }
 

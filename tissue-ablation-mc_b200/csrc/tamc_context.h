@@ -10,7 +10,7 @@
 
 struct tamc_heat;   // device-resident heat / ablation state (tamc_heat.cu)
 
-enum { EV_ZERO0 = 0, EV_K0, EV_K1, EV_AR1, EV_H0, EV_H1, EV_D0, EV_D1, EV_N };
+enum { EV_ZERO0 = 0, EV_K0, EV_K1, EV_AR1, EV_H0, EV_H1, EV_D0, EV_D1, EV_FORK, EV_UP, EV_DN, EV_N };
 
 struct tamc_context {
     // (members are documented where they are used in tamc_api.cu)
@@ -40,6 +40,15 @@ struct tamc_context {
     int box_reduce = -1;    // shipped regime: all-reduce only the columns under the beam (-1 = auto, 0 = off, 1 = on)
     int form = -1;          // FORM_* of the last MC call
     int probe_form = -1;    // tamc_roofline_probe: -1 = match the transport, 0 = per-voxel-step stream, 1 = column form
+
+    // overlapped boundary copies of the shipped regime (tamc_run / tamc_run_optics, tamc_api.cu)
+    int box_io = -1;        // -1 = auto, 0 = off: plain full-grid copies in sequence
+    int io_form = 0;        // read-only: bit0 = the last tamc_run downloaded zero fill + beam columns, bit1 = the last
+                            // tamc_run_optics uploaded the beam columns ahead of the grid
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    double *d_zero = nullptr;           // n_jmean zeros: the tally outside the beam's columns
+    double *d_box_rk = nullptr;         // (tw, th, nzg+2) opacities under the beam, uploaded ahead of the full grid
+    size_t box_rk_elems = 0;
 
     tamc_heat *heat = nullptr;
 

@@ -33,11 +33,21 @@ struct ColumnWorkspace {
     size_t rkT_elems = 0;
     double *dense = nullptr;         // (tw, th, nzg) staging of the tally under the box for the all-reduce
     size_t dense_elems = 0;
+    // columns-first upload (tamc_run_optics), set for one call: k_column_gather reads `gather_src` (device-visible
+    // address of the caller's page-locked rhokap) instead of the resident grid, keeps an x-fastest copy of the box in
+    // `box_rk` for k_column_finish, and is bracketed by the two events
+    const double *gather_src = nullptr;
+    double *box_rk = nullptr;
+    cudaEvent_t ev_gather0 = nullptr, ev_gather1 = nullptr;
 };
 
 // shipped regime: the columns every deposit lies in, and the copy between them and a dense buffer
 bool beam_box(const DevGrid &g, ColGeom &cg);
+// true when launch_transport would run the column form on the z-fastest copy (the only form that reads rhokap
+// solely through k_column_gather / k_column_finish)
+bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n);
 cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s);
+cudaError_t launch_box_mirror(const DevGrid &g, const ColGeom &cg, double *dst, int num_sms, cudaStream_t s);
 
 // production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.
 // ws may be null (no column form).

@@ -438,6 +438,12 @@ cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, 
     return cudaGetLastError();
 }
 
+cudaError_t launch_box_mirror(const DevGrid &g, const ColGeom &cg, double *dst, int num_sms, cudaStream_t s)
+{
+    k_box_mirror<<<num_sms * 8, 256, 0, s>>>(g, cg, dst);
+    return cudaGetLastError();
+}
+
 // the workspace of the column form (+ the z-fastest copy of the opacities under the box)
 static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gather, cudaStream_t s, ColGeom &cg)
 {
@@ -463,7 +469,13 @@ static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gath
             ws->rkT_elems = nrk;
         }
         const dim3 gg((cg.tw + 31) / 32, cg.th, (cg.nzp + 31) / 32);
-        k_column_gather<<<gg, 256, 0, s>>>(g, cg, ws->rkT);
+        if (ws->gather_src && ws->box_rk) {
+            if (ws->ev_gather0) cudaEventRecord(ws->ev_gather0, s);
+            k_column_gather<true><<<gg, 256, 0, s>>>(g, cg, ws->gather_src, ws->rkT, ws->box_rk);
+            if (ws->ev_gather1) cudaEventRecord(ws->ev_gather1, s);
+        } else {
+            k_column_gather<false><<<gg, 256, 0, s>>>(g, cg, g.rhokap, ws->rkT, nullptr);
+        }
     }
     return cudaGetLastError();
 }
@@ -478,6 +490,11 @@ static bool column_wanted(const DevGrid &g, const LaunchCfg &cfg, long long n)
     const double R = sqrt(g.spot_r2);
     const double cols = (2. * R * g.inv_dx + 1.) * (2. * R * g.inv_dy + 1.);
     return n >= (1ll << 20) && cols > 4096.;
+}
+
+bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n)
+{
+    return n > 0 && column_wanted(g, cfg, n) && cfg.column != 2;
 }
 
 // Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
@@ -496,7 +513,15 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     else if (cfg.min_ctas == 2) e = launch_sized(k_transport_column<true, 6>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     else e = launch_sized(k_transport_column<true, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     if (e != cudaSuccess) return e;
-    k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(g, cg, ws->stops);
+    DevGrid gf = g;
+    if (gather && ws->gather_src && ws->box_rk) {
+        // rhokap(i,j,k) = box[(i-i0) + tw*((j-j0) + th*(k-1))]: the resident index expression i + sx*j + sxy*k with
+        // sx = tw, sxy = tw*th and the origin moved
+        gf.sx = cg.tw;
+        gf.sxy = (long long)cg.tw * cg.th;
+        gf.rhokap = ws->box_rk - ((long long)cg.i0 + (long long)cg.tw * cg.j0 + gf.sxy);
+    }
+    k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(gf, cg, ws->stops);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

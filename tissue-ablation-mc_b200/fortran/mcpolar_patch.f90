@@ -35,12 +35,13 @@
       oflags = 0                           ! TAMC_SCATTER to run the albedo/stokes loop instead of the stub
 
 !--- (3) the hot path: REPLACES mcpolar.f90:151-173 (photon loop + MPI_allREDUCE) --------------------
-      !  rhokap was rewritten by setupThermalCoeff at the end of the previous iteration (mcpolar.f90:182)
-      ierr = tamc_set_optics(tamc, rhokap, albedo, hgg, n1, n2, oflags)
-      call tamc_check(ierr, 'tamc_set_optics')
-      !  nphotons packets on this rank, tally summed over all ranks, UNSCALED sum into jmeanGLOBAL
-      ierr = tamc_run(tamc, int(nphotons, c_int64_t), seed64, jmeanGLOBAL, c_null_ptr)
-      call tamc_check(ierr, 'tamc_run')
+      !  rhokap was rewritten by setupThermalCoeff at the end of the previous iteration (mcpolar.f90:182):
+      !  upload it, run nphotons packets on this rank, sum the tally over all ranks, UNSCALED sum into
+      !  jmeanGLOBAL.  One call, so the library can overlap the two PCIe copies with the transport
+      !  (equivalent to tamc_set_optics followed by tamc_run, which remain available).
+      ierr = tamc_run_optics(tamc, rhokap, albedo, hgg, n1, n2, oflags, int(nphotons, c_int64_t), seed64, &
+                             jmeanGLOBAL, c_null_ptr)
+      call tamc_check(ierr, 'tamc_run_optics')
       !  mcpolar.f90:174 (the power / packet-count / voxel-volume scaling) stays exactly as it is.
 
 !--- (4) before MPI_Finalize at mcpolar.f90:215 ------------------------------------------------------

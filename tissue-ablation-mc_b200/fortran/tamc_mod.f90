@@ -73,6 +73,20 @@ module tamc_mod
             type(c_ptr), value           :: stats        ! c_loc(a tamc_stats) or c_null_ptr
         end function tamc_run
 
+        !  tamc_set_optics + tamc_run in one call: what the time loop does once per iteration.  With rhokap and
+        !  jmean_global page-locked (tamc_pin_host) the PCIe copies overlap the transport.
+        integer(c_int) function tamc_run_optics(handle, rhokap, albedo, hgg, n1, n2, flags, nphotons, seed, &
+                                                jmean_global, stats) bind(C, name="tamc_run_optics")
+            import :: c_int, c_int64_t, c_double, c_ptr
+            type(c_ptr), value           :: handle
+            real(c_double), intent(in)   :: rhokap(*)
+            real(c_double), value        :: albedo, hgg, n1, n2
+            integer(c_int), value        :: flags
+            integer(c_int64_t), value    :: nphotons, seed
+            real(c_double), intent(out)  :: jmean_global(*)
+            type(c_ptr), value           :: stats        ! c_loc(a tamc_stats) or c_null_ptr
+        end function tamc_run_optics
+
         integer(c_int) function tamc_comm_unique_id(id128) bind(C, name="tamc_comm_unique_id")
             import :: c_int, c_char
             character(kind=c_char), intent(out) :: id128(128)

@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
         "tamc_set_source_co2": (i, [p, d]),
         "tamc_set_optics": (i, [p, p, d, d, d, d, i]),
         "tamc_run": (i, [p, i64, i64, p, C.POINTER(Stats)]),
+        "tamc_run_optics": (i, [p, p, d, d, d, d, i, i64, i64, p, C.POINTER(Stats)]),
         "tamc_run_async": (i, [p, i64, i64, i64]),
         "tamc_sync": (i, [p]),
         "tamc_get_jmean": (i, [p, p]),
@@ -122,7 +123,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = [
-    "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_optics", "tamc_run", "tamc_run_async",
+    "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_optics", "tamc_run", "tamc_run_optics", "tamc_run_async",
     "tamc_sync", "tamc_get_jmean", "tamc_get_stats", "tamc_seek", "tamc_run_replay", "tamc_run_records",
     "tamc_comm_unique_id", "tamc_comm_init", "tamc_stream", "tamc_jmean_device", "tamc_rhokap_device",
     "tamc_pin_host", "tamc_unpin_host", "tamc_set_option", "tamc_get_option", "tamc_roofline_probe",
@@ -230,6 +231,25 @@ class MCTransport:
         assert jm.flags.f_contiguous and jm.dtype == np.float64 and jm.shape == self.jmean_shape
         st = Stats()
         _ck(self.L.tamc_run(self.h, int(nphotons), int(seed), jm.ctypes.data, C.byref(st)))
+        return jm, st.as_dict()
+
+    def run_optics(self, rhokap, albedo, hgg, nphotons, seed, n1=1.0, n2=1.0, flags=0, out=None):
+        """tamc_run_optics: tamc_set_optics + tamc_run in one call (copies overlapped with the transport when the
+        arrays are page-locked and the scatter loop is off); returns (jmeanGLOBAL unscaled, stats dict)."""
+        ptr = None
+        if rhokap is not None:
+            rk = np.asarray(rhokap, dtype=np.float64)
+            if rk.shape != self.rhokap_shape:
+                raise ValueError(f"rhokap must have shape {self.rhokap_shape} (halo included)")
+            if not rk.flags.f_contiguous:
+                rk = np.asfortranarray(rk)
+            self._keep = rk
+            ptr = rk.ctypes.data
+        jm = out if out is not None else self.new_jmean()
+        assert jm.flags.f_contiguous and jm.dtype == np.float64 and jm.shape == self.jmean_shape
+        st = Stats()
+        _ck(self.L.tamc_run_optics(self.h, ptr, float(albedo), float(hgg), float(n1), float(n2), int(flags),
+                                   int(nphotons), int(seed), jm.ctypes.data, C.byref(st)))
         return jm, st.as_dict()
 
     def run_async(self, nphotons, seed, first_packet_id=-1):
