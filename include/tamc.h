@@ -162,13 +162,15 @@ double *tamc_rhokap_device(tamc_handle h); /* device opacity grid with halo */
 int tamc_pin_host(void *ptr, uint64_t bytes);
 int tamc_unpin_host(void *ptr);
 /* Tuning knobs: "variant" (0 thread-per-packet, 1 persistent warps, 2 exact arithmetic, 3 = default:
- * work-queue regrouping when scattering; in the shipped stub regime the column form for large calls
- * under a wide beam, the shared-memory tally tile under a narrow one, persistent warps otherwise),
- * "block" (0 = auto), "ctas_per_sm", "chunk", "scatter_min", "merge", "min_ctas",
- * "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "reduce" (0 = skip the all-reduce),
- * "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 = per-voxel-step
- * address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the last MC call
- * ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on the resident grid). */
+ * work-queue regrouping when scattering; in the shipped stub regime the column form for large calls,
+ * persistent warps otherwise), "block" (0 = auto), "ctas_per_sm", "chunk", "scatter_min", "merge",
+ * "min_ctas", "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "column_tile" (shared-memory
+ * tiles of the column form: -1 = auto, 0 = off, 10*ta + tb = ta planes of deposits and tb planes of
+ * stop counts), "reduce" (0 = skip the all-reduce), "box_reduce" / "box_io" (-1 = auto, 0 = move the
+ * whole grid), "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 =
+ * per-voxel-step address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the
+ * last MC call ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on
+ * the resident grid, 7 column with shared-memory tiles), "io_form" (see tamc_run_optics). */
 int tamc_set_option(tamc_handle h, const char *name, int64_t value);
 int64_t tamc_get_option(tamc_handle h, const char *name);
 /* Access-pattern-only kernel: the tally/grid address stream of `nphotons` straight-down packets

@@ -33,6 +33,17 @@ def _check(t, o, n, first=0):
                 assert st[key] == want[key] == sb[key], (key, column, rep)
             compare_grids(jm, o.jmean, rtol=1e-10)
             compare_grids(jm, base, rtol=1e-10)
+    # shared-memory tiles for the top planes (10*ta + tb): deposits only, counts only, both, deeper than the grid allows
+    t.set_option("column", 1)
+    for split in (10, 4, 23, 14):
+        t.set_option("column_tile", split)
+        for rep in range(2):
+            t.run_async(n, SEED, first)
+            jm, st = t.get_jmean(), t.get_stats()
+            for key in ("packets", "voxel_steps", "scatters", "absorbed", "exits"):
+                assert st[key] == want[key], (key, split, rep)
+            compare_grids(jm, o.jmean, rtol=1e-10)
+    t.set_option("column_tile", -1)
     t.set_option("column", -1)
 
 
@@ -104,4 +115,34 @@ def test_column_is_the_default_for_large_calls_and_matches_the_step_kernel():
         assert st[key] == st0[key]
     compare_grids(jm, jm0, rtol=1e-10)
     assert abs(jm.sum() / n - 1.0) < 5 / np.sqrt(n)
+    t.close()
+
+
+@pytest.mark.parametrize("name,n,split", [("homog200", 12_000_000, (0, 1)), ("shipped80", 20_000_000, (1, 2))])
+def test_auto_tiles_for_calls_that_amortise_the_flush(name, n, split):
+    """Large calls take the column form with shared-memory tiles (form 7): one plane of stop counts under a wide beam,
+    the top plane of deposits + two planes of counts under a narrow one.  Same counters, grid to summation order; the
+    probe follows the same shape."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS[name]
+    t = make_transport(cfg)
+    t.run_async(n, SEED, 0)
+    jm, st = t.get_jmean().copy(), t.get_stats()
+    assert t.get_option("form") == 7 and st["gpu_launches"] == 3
+    t.set_option("column", 1)
+    t.set_option("column_tile", 0)
+    t.run_async(n, SEED, 0)
+    jm0, st0 = t.get_jmean().copy(), t.get_stats()
+    assert t.get_option("form") == 5
+    for key in ("packets", "voxel_steps", "absorbed", "exits"):
+        assert st[key] == st0[key]
+    compare_grids(jm, jm0, rtol=1e-10)
+    assert abs(jm.sum() / n - 1.0) < 5 / np.sqrt(n)
+    t.set_option("column", -1)
+    t.set_option("column_tile", -1)
+    ms, steps = t.roofline_probe(n, 3)
+    assert ms > 0 and abs(steps / st["voxel_steps"] - 1.0) < 0.02
+    t.run_async(1000, SEED, 0)                         # the probe leaves the stop counts clean
+    assert t.get_option("form") == 1 and abs(t.get_jmean().sum() / 1000 - 1.0) < 0.2
     t.close()

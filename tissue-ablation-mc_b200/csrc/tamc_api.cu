@@ -717,6 +717,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "min_ctas")) return &h->cfg.min_ctas;
     if (!strcmp(name, "tile")) return &h->cfg.tile;
     if (!strcmp(name, "column")) return &h->cfg.column;
+    if (!strcmp(name, "column_tile")) return &h->cfg.column_tile;
     if (!strcmp(name, "reduce")) return &h->reduce;
     if (!strcmp(name, "probe_form")) return &h->probe_form;
     if (!strcmp(name, "box_reduce")) return &h->box_reduce;
@@ -739,6 +740,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");
     if (slot == &h->cfg.min_ctas && (value < 2 || value > 3)) return fail(TAMC_EINVAL, "min_ctas must be 2 or 3");
     if (slot == &h->cfg.column && (value < -1 || value > 2)) return fail(TAMC_EINVAL, "column must be -1 (auto), 0 (off), 1 or 2");
+    if (slot == &h->cfg.column_tile && (value < -1 || value > 99)) return fail(TAMC_EINVAL, "column_tile must be -1 (auto), 0 (off) or 10*ta + tb");
     if (slot == &h->cfg.ctas_per_sm && (value < 0 || value > 32)) return fail(TAMC_EINVAL, "ctas_per_sm must be in [0,32]");
     *slot = (int)value;
     return TAMC_OK;

@@ -20,10 +20,12 @@ struct LaunchCfg {
     int tile;           // stub regime: shared-memory tally tile; -1 = auto, 0 = off, k > 0 = at most k planes
     int column;         // stub regime, column form (tamc_column.cuh): -1 = auto (variant 3, >= 2^20 packets), 0 = off,
                         // 1 = on with the z-fastest copy of the beam's columns, 2 = on, reading the resident grid
+    int column_tile;    // column form: shared-memory tiles for the top planes of the deposits / stop counts; -1 = auto
+                        // (column_plan in tamc_kernels.cu), 0 = off, 10*ta + tb = force that split
 };
 
 // Which kernel an MC call ran ("form" read-only option of tamc_get_option)
-enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6 };
+enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6, FORM_COLUMN_TILED = 7 };
 
 // Device buffers of the column form, owned by the handle and grown on demand by launch_transport.
 struct ColumnWorkspace {

@@ -338,10 +338,20 @@ __global__ void __launch_bounds__(256) k_probe(const DevGrid g, long long n, uin
 // The same for the column form (tamc_column.cuh): per packet one 256-bit load of the z-fastest opacity copy per
 // group of four voxels crossed, one fp64 RED (the partial deposit) and, unless the packet stops in the top plane, one
 // u32 RED (the stop count) -- and as little else as possible.
-__global__ void __launch_bounds__(256) k_probe_column(const DevGrid g, long long n, uint64_t seed, float disk_r_vox, const ColGeom cg,
+template <bool kTiled>
+__global__ void __launch_bounds__(kTiled ? 1024 : 256) k_probe_column(const DevGrid g, long long n, uint64_t seed, float disk_r_vox, const ColGeom cg,
                                                       const double *__restrict__ rkT, unsigned int *__restrict__ stops,
-                                                      unsigned long long *__restrict__ cnt)
+                                                      unsigned long long *__restrict__ cnt, int ta, int tb)
 {
+    extern __shared__ double s_tiles[];
+    const int cols = cg.tw * cg.th;
+    double *s_dep = s_tiles;
+    unsigned int *s_stop = reinterpret_cast<unsigned int *>(s_dep + (size_t)ta * cols);
+    if (kTiled) {
+        for (int i = threadIdx.x; i < ta * cols; i += blockDim.x) s_dep[i] = 0.;
+        for (int i = threadIdx.x; i < tb * cols; i += blockDim.x) s_stop[i] = 0u;
+        __syncthreads();
+    }
     const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned long long steps = 0;
     double keep = 0.;
@@ -361,7 +371,8 @@ __global__ void __launch_bounds__(256) k_probe_column(const DevGrid g, long long
         int nst = 1 + (int)(__logf(u2) * inv_logp);                                   // geometric
         nst = min(nst, g.nzg);
         steps += (unsigned long long)nst;
-        const double *col = rkT + ((size_t)(cj - cg.j0) * cg.tw + (ci - cg.i0)) * cg.nzp;
+        const int col_id = (cj - cg.j0) * cg.tw + (ci - cg.i0);
+        const double *col = rkT + (size_t)col_id * cg.nzp;
         const int kstop = g.nzg - nst + 1;
         for (int gb = (g.nzg - 1) & ~3; gb >= ((kstop - 1) & ~3); gb -= 4) {
             double a, b, c, d;
@@ -369,8 +380,28 @@ __global__ void __launch_bounds__(256) k_probe_column(const DevGrid g, long long
             keep += a + d;
         }
         const int j = (ci - 1) + g.nxg * ((cj - 1) + g.nyg * (kstop - 1));
-        atomicAdd(g.jmean + j, 1.0);
-        if (kstop < g.nzg) atomicAdd(stops + (j + plane), 1u);
+        const int d = nst - 1;
+        if (kTiled && d < ta) smem_add_f64(s_dep + d * cols + col_id, 1.0);
+        else atomicAdd(g.jmean + j, 1.0);
+        if (kTiled && d >= 1 && d <= tb) atomicAdd(s_stop + (d - 1) * cols + col_id, 1u);
+        else if (kstop < g.nzg) atomicAdd(stops + (j + plane), 1u);
+    }
+    if (kTiled) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ta * cols; i += blockDim.x) {
+            const double v = s_dep[i];
+            if (v != 0.) {
+                const int d = i / cols, c = i - d * cols, dj = c / cg.tw, di = c - dj * cg.tw;
+                atomicAdd(g.jmean + ((cg.i0 - 1 + di) + g.nxg * ((cg.j0 - 1 + dj) + g.nyg * (g.nzg - d - 1))), v);
+            }
+        }
+        for (int i = threadIdx.x; i < tb * cols; i += blockDim.x) {
+            const unsigned int v = s_stop[i];
+            if (v) {
+                const int d = i / cols + 1, c = i - (d - 1) * cols, dj = c / cg.tw, di = c - dj * cg.tw;
+                atomicAdd(stops + ((cg.i0 - 1 + di) + g.nxg * ((cg.j0 - 1 + dj) + g.nyg * (g.nzg - d))), v);
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
@@ -480,26 +511,52 @@ static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gath
     return cudaGetLastError();
 }
 
-// auto rule of the column form: calls large enough to pay for the two small extra kernels, and a footprint of more
-// than a few thousand columns -- under a narrow beam the partial-deposit REDs hit so few addresses that the L2
-// atomic unit serialises, and the shared-memory tile is the better form (measured: profiles/README.md)
-static bool column_wanted(const DevGrid &g, const LaunchCfg &cfg, long long n)
+// Plan of the column form for a call of n packets: whether to use it, and the shared-memory tile split (tamc_column.cuh:
+// ta planes of partial deposits, tb planes of stop counts per CTA).  Measured rules (profiles/README.md, tools/tile_sweep.py):
+//   * wide beam (> 4096 columns): the global REDs are not contended; one plane of stop counts and one 1024-thread CTA
+//     per SM is the fastest shape (deeper tiles only add flush work);
+//   * narrow beam: the same few thousand tally addresses are hit so often that the L2 atomic unit serialises -- keep the
+//     top plane of the deposits and two planes of counts in shared memory;
+//   * tiles only when the call amortises their flush (148 CTAs x columns x planes REDs), the column form itself only for
+//     calls that pay for its two small extra kernels (>= 2^20 packets).
+struct ColumnPlan {
+    bool use;
+    int ta, tb;
+};
+
+static ColumnPlan column_plan(const DevGrid &g, const LaunchCfg &cfg, long long n)
 {
-    if (cfg.variant != 3 || (g.flags & (TAMC_SCATTER | TAMC_FRESNEL)) || cfg.column == 0) return false;
-    if (cfg.column > 0) return true;
-    const double R = sqrt(g.spot_r2);
-    const double cols = (2. * R * g.inv_dx + 1.) * (2. * R * g.inv_dy + 1.);
-    return n >= (1ll << 20) && cols > 4096.;
+    ColumnPlan p{false, 0, 0};
+    ColGeom cg;
+    if (cfg.variant != 3 || (g.flags & (TAMC_SCATTER | TAMC_FRESNEL)) || cfg.column == 0 || n <= 0 || !beam_box(g, cg)) return p;
+    const long long cols = (long long)cg.tw * cg.th;
+    const bool wide = cols > 4096;
+    if (cfg.column != 2 && cfg.column_tile != 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const long long avail = (long long)optin - 8ll * cg.nzp - 1024;
+        int ta = wide ? 0 : 1, tb = wide ? 1 : 2;
+        if (cfg.column_tile > 0) { ta = cfg.column_tile / 10; tb = cfg.column_tile % 10; }       // forced split
+        ta = ta < g.nzg ? ta : g.nzg;
+        tb = tb < g.nzg ? tb : g.nzg;
+        const bool fits = cols * (8ll * ta + 4ll * tb) <= avail;
+        const bool pays = n >= 8ll * cfg.num_sms * cols * (ta + tb);
+        if (ta + tb > 0 && fits && (cfg.column_tile > 0 || pays)) { p.ta = ta; p.tb = tb; }
+    }
+    p.use = cfg.column > 0 || (n >= (1ll << 20) && (wide || p.ta + p.tb > 0));
+    return p;
 }
 
 bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n)
 {
-    return n > 0 && column_wanted(g, cfg, n) && cfg.column != 2;
+    return column_plan(g, cfg, n).use && cfg.column != 2;
 }
 
 // Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
 static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
-                                 unsigned long long *d_cnt, cudaStream_t s, int *launches, ColumnWorkspace *ws, bool gather)
+                                 unsigned long long *d_cnt, cudaStream_t s, int *launches, ColumnWorkspace *ws, bool gather,
+                                 const ColumnPlan &plan)
 {
     ColGeom cg;
     cudaError_t e0 = column_setup(g, ws, gather, s, cg);
@@ -509,6 +566,16 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     LaunchCfg c2 = cfg;
     c2.block = 256;
     cudaError_t e;
+    const int ta = gather ? plan.ta : 0, tb = gather ? plan.tb : 0;
+    if (ta + tb > 0) {
+        const size_t tsmem = smem + (size_t)cg.tw * cg.th * (8 * (size_t)ta + 4 * (size_t)tb);
+        e = cudaFuncSetAttribute(k_transport_column_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+        if (e != cudaSuccess) return e;
+        const long long want = (n + 1023) / 1024;
+        const int grid = (int)(want < cfg.num_sms ? want : cfg.num_sms);
+        k_transport_column_tiled<<<grid, 1024, tsmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
+        e = cudaGetLastError();
+    } else
     if (!gather) e = launch_sized(k_transport_column<false, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)nullptr, ws->stops, d_cnt);
     else if (cfg.min_ctas == 2) e = launch_sized(k_transport_column<true, 6>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     else e = launch_sized(k_transport_column<true, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
@@ -542,9 +609,10 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     const bool merge = cfg.merge < 0 ? (g.flags & TAMC_SCATTER) != 0 : cfg.merge != 0;
     const size_t smem = faces_bytes(g);
     // shipped regime, default variant: the column form once the call is large enough to pay for its two small extra kernels
-    if (ws && !d_rec && column_wanted(g, cfg, n)) {
-        if (form) *form = cfg.column == 2 ? FORM_COLUMN_RESIDENT : FORM_COLUMN;
-        return launch_column(g, cfg, n, seed, first_id, d_cnt, s, launches, ws, cfg.column != 2);
+    const ColumnPlan plan = (ws && !d_rec) ? column_plan(g, cfg, n) : ColumnPlan{false, 0, 0};
+    if (plan.use) {
+        if (form) *form = cfg.column == 2 ? FORM_COLUMN_RESIDENT : (plan.ta + plan.tb > 0 ? FORM_COLUMN_TILED : FORM_COLUMN);
+        return launch_column(g, cfg, n, seed, first_id, d_cnt, s, launches, ws, cfg.column != 2, plan);
     }
     if (launches) *launches += 1;
     tamc_packet_record *none = nullptr;
@@ -643,12 +711,25 @@ cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, ui
     const float disk_r_vox = (float)(sqrt(g.spot_r2) * g.inv_dx);
     LaunchCfg c2 = cfg;
     c2.block = 256;
-    const bool column = probe_form < 0 ? (ws && column_wanted(g, cfg, n)) : probe_form == 1;
+    LaunchCfg cp = cfg;
+    if (probe_form == 1 && cp.column <= 0) cp.column = 1;
+    const ColumnPlan plan = ws ? column_plan(g, cp, n) : ColumnPlan{false, 0, 0};
+    const bool column = probe_form < 0 ? plan.use : probe_form == 1;
     if (column && ws) {
         ColGeom cg;
         cudaError_t e = column_setup(g, ws, true, s, cg);
         if (e != cudaSuccess) return e;
-        e = launch_sized(k_probe_column, c2, 0, n, s, g, n, seed, disk_r_vox, cg, (const double *)ws->rkT, ws->stops, d_cnt);
+        if (plan.ta + plan.tb > 0) {       // the transport's shape: one 1024-thread CTA per SM with its tiles
+            const size_t tsmem = (size_t)cg.tw * cg.th * (8 * (size_t)plan.ta + 4 * (size_t)plan.tb);
+            e = cudaFuncSetAttribute(k_probe_column<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+            if (e != cudaSuccess) return e;
+            const long long want = (n + 1023) / 1024;
+            k_probe_column<true><<<(int)(want < cfg.num_sms ? want : cfg.num_sms), 1024, tsmem, s>>>(
+                g, n, seed, disk_r_vox, cg, (const double *)ws->rkT, ws->stops, d_cnt, plan.ta, plan.tb);
+            e = cudaGetLastError();
+        } else {
+            e = launch_sized(k_probe_column<false>, c2, 0, n, s, g, n, seed, disk_r_vox, cg, (const double *)ws->rkT, ws->stops, d_cnt, 0, 0);
+        }
         if (e != cudaSuccess) return e;
         const size_t smem = sizeof(double) * (size_t)cg.nzp;
         k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(g, cg, ws->stops);
