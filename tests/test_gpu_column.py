@@ -35,15 +35,18 @@ def _check(t, o, n, first=0):
             compare_grids(jm, base, rtol=1e-10)
     # shared-memory tiles for the top planes (10*ta + tb): deposits only, counts only, both, deeper than the grid allows
     t.set_option("column", 1)
-    for split in (10, 4, 23, 14):
+    # ... each with the column walk regrouped through the per-warp park queues (default) and without
+    for split, park in ((10, 1), (4, 1), (23, 1), (14, 1), (14, 0), (4, 0)):
         t.set_option("column_tile", split)
+        t.set_option("column_park", park)
         for rep in range(2):
             t.run_async(n, SEED, first)
             jm, st = t.get_jmean(), t.get_stats()
             for key in ("packets", "voxel_steps", "scatters", "absorbed", "exits"):
-                assert st[key] == want[key], (key, split, rep)
+                assert st[key] == want[key], (key, split, park, rep)
             compare_grids(jm, o.jmean, rtol=1e-10)
     t.set_option("column_tile", -1)
+    t.set_option("column_park", -1)
     t.set_option("column", -1)
 
 

@@ -413,6 +413,9 @@ extern "C" int tamc_get_stats(tamc_handle h, tamc_stats *st)
     CU(cudaMemcpy(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
     st->packets = (int64_t)cnt[CNT_PACKETS];
     st->voxel_steps = (int64_t)cnt[CNT_STEPS];
+    // feeds the launch plan of the next stub-regime call (LaunchCfg::column_park)
+    if (!(h->flags & (TAMC_SCATTER | TAMC_FRESNEL)) && cnt[CNT_PACKETS] >= 10000)
+        h->cfg.steps_hint = (double)cnt[CNT_STEPS] / (double)cnt[CNT_PACKETS];
     st->scatters = (int64_t)cnt[CNT_SCATTERS];
     st->absorbed = (int64_t)cnt[CNT_ABSORBED];
     for (int f = 0; f < 6; ++f) st->exits[f] = (int64_t)cnt[CNT_EXIT0 + f];
@@ -718,6 +721,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "tile")) return &h->cfg.tile;
     if (!strcmp(name, "column")) return &h->cfg.column;
     if (!strcmp(name, "column_tile")) return &h->cfg.column_tile;
+    if (!strcmp(name, "column_park")) return &h->cfg.column_park;
     if (!strcmp(name, "reduce")) return &h->reduce;
     if (!strcmp(name, "probe_form")) return &h->probe_form;
     if (!strcmp(name, "box_reduce")) return &h->box_reduce;

@@ -274,6 +274,162 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_tiled(const DevGri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same with the column walk regrouped (default for tiled calls).
+//
+// In k_transport_column(_tiled) a lane loops over four-voxel groups until its packet stops; most packets stop in the
+// first group (1 - q^4), so the later passes of that loop run with a handful of lanes (ncu: 13 of 32 on average, and
+// the loop is half of all instructions).  Here every warp does ONE group per packet and parks the unfinished packets
+// (column, next group, tau, taurun, tally index: 28 bytes) in a 64-entry queue of its own in shared memory; whenever 32
+// are parked the warp takes them out and gives each its next group with all lanes busy.  The launch arithmetic (the
+// other half of the instructions) always runs with 32 lanes, as before.  Same per-packet arithmetic in the same order.
+// ---------------------------------------------------------------------------------------------------------------
+struct ParkQueue {                 // one per warp
+    double tau[64], taurun[64];
+    int col[64], idx[64], jidx[64];
+};
+
+// one four-voxel group of a packet's walk (inttau2.f90:37-63 for a straight-down flight); returns the stop voxel
+// (1-based k), 0 = left through the bottom face, -1 = goes on with the group below (idx, taurun advanced)
+__device__ __forceinline__ int column_group(const double *__restrict__ col, const double *s_dz, int &idx, double tau, double &taurun)
+{
+    const int gb = idx & ~3;
+    double r0, r1, r2, r3;
+    ldg256(col + gb, r0, r1, r2, r3);
+    const double2 da = *reinterpret_cast<const double2 *>(s_dz + gb), db = *reinterpret_cast<const double2 *>(s_dz + gb + 2);
+    const double tc3 = __dmul_rn(db.y, r3), tc2 = __dmul_rn(db.x, r2), tc1 = __dmul_rn(da.y, r1), tc0 = __dmul_rn(da.x, r0);
+    const double t3 = __dadd_rn(taurun, tc3), t2 = __dadd_rn(t3, tc2), t1 = __dadd_rn(t2, tc1), t0 = __dadd_rn(t1, tc0);
+    const bool p3 = t3 < tau, p2 = t2 < tau, p1 = t1 < tau, p0 = t0 < tau;
+    const int nstop = !p3 ? 4 : (!p2 ? 3 : (!p1 ? 2 : (!p0 ? 1 : 0)));
+    if (nstop) {
+        taurun = !p3 ? taurun : (!p2 ? t3 : (!p1 ? t2 : t1));
+        return gb + nstop;
+    }
+    taurun = t0;
+    idx = gb - 1;
+    return idx >= 0 ? -1 : 0;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_transport_column_parked(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
+                                                                     const ColGeom cg, const double *__restrict__ rkT,
+                                                                     unsigned int *__restrict__ stops,
+                                                                     unsigned long long *__restrict__ cnt, int ta, int tb)
+{
+    extern __shared__ double s_dz[];
+    const int cols = cg.tw * cg.th;
+    double *s_dep = s_dz + cg.nzp;                                             // [ta][cols]
+    unsigned int *s_stop = reinterpret_cast<unsigned int *>(s_dep + (size_t)ta * cols);   // [tb][cols], depth 1 first
+    ParkQueue *queues = reinterpret_cast<ParkQueue *>(s_dep + (size_t)ta * cols + (((size_t)tb * cols + 1) >> 1));
+    for (int i = threadIdx.x; i < ta * cols; i += blockDim.x) s_dep[i] = 0.;
+    for (int i = threadIdx.x; i < tb * cols; i += blockDim.x) s_stop[i] = 0u;
+    stage_column_steps(g, cg.nzp, s_dz);                                        // ends with __syncthreads()
+    const int plane = g.nxg * g.nyg;
+    const int k0 = g.cellk0;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    ParkQueue &Q = queues[threadIdx.x >> 5];
+    int qn = 0;                                                                 // parked packets of this warp (warp-uniform)
+    unsigned long long steps = 0ull;
+    unsigned int packets = 0u, absorbed = 0u, bottom = 0u;
+
+    // a packet that stopped in voxel kstop (> 0) or left through the bottom face (0): the two tallies
+    auto tally = [&](int kstop, int col_id, int jidx, double tau, double taurun) {
+        if (kstop) {
+            const double rest = tau - taurun;                                  // inttau2.f90:51-53
+            const int d = k0 - kstop;
+            const int j = jidx - d * plane;
+            if (rest != 0.) {
+                if (d < ta) smem_add_f64(s_dep + d * cols + col_id, rest);
+                else atomicAdd(g.jmean + j, rest);
+            }
+            if (d >= 1 && d <= tb) atomicAdd(s_stop + (d - 1) * cols + col_id, 1u);
+            else if (kstop < g.nzg) atomicAdd(stops + (j + plane), 1u);
+            steps += (unsigned long long)(d + 1);
+            ++absorbed;
+        } else {
+            atomicAdd(stops + (jidx - (k0 - 1) * plane), 1u);
+            steps += (unsigned long long)k0;
+            ++bottom;
+        }
+    };
+    // one group for the packet in this lane's registers; parks it if it goes on
+    auto advance = [&](bool live, int col_id, int idx, int jidx, double tau, double taurun) {
+        int r = 1;
+        if (live) {
+            r = column_group(rkT + (size_t)col_id * cg.nzp, s_dz, idx, tau, taurun);
+            if (r >= 0) tally(r, col_id, jidx, tau, taurun);
+        }
+        const bool park = live && r < 0;
+        const unsigned pm = __ballot_sync(0xffffffffu, park);
+        if (park) {
+            const int s = qn + __popc(pm & lt_mask);
+            Q.tau[s] = tau; Q.taurun[s] = taurun; Q.col[s] = col_id; Q.idx[s] = idx; Q.jidx[s] = jidx;
+        }
+        qn += __popc(pm);
+        __syncwarp();
+    };
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < n; wbase += stride) {
+        const long long i = wbase + lane;
+        const bool live = i < n;
+        const uint64_t gid = first_id + (uint64_t)i;
+        const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), false);
+        const int di = (L.cells & 0xffff) - cg.i0, dj = (L.cells >> 16) - cg.j0;
+        if (live) ++packets;
+        advance(live, dj * cg.tw + di, k0 - 1, L.jidx, L.tau, 0.);
+        while (qn >= 32) {                                                     // a full warp of parked packets: their next group
+            const int s = qn - 32 + lane;
+            const double tau = Q.tau[s], taurun = Q.taurun[s];
+            const int col_id = Q.col[s], idx = Q.idx[s], jidx = Q.jidx[s];
+            qn -= 32;
+            __syncwarp();
+            advance(true, col_id, idx, jidx, tau, taurun);
+        }
+    }
+    // what is still parked when the ids run out: to completion, one packet per lane
+    while (qn > 0) {
+        const int take = qn < 32 ? qn : 32;
+        const int s = qn - take + lane;
+        const bool live = lane < take;
+        double tau = 0., taurun = 0.;
+        int col_id = 0, idx = 0, jidx = 0;
+        if (live) { tau = Q.tau[s]; taurun = Q.taurun[s]; col_id = Q.col[s]; idx = Q.idx[s]; jidx = Q.jidx[s]; }
+        qn -= take;
+        __syncwarp();
+        if (live) {
+            int r;
+            do r = column_group(rkT + (size_t)col_id * cg.nzp, s_dz, idx, tau, taurun); while (r < 0);
+            tally(r, col_id, jidx, tau, taurun);
+        }
+    }
+    __syncthreads();
+    // flush: lanes along x, coalesced REDs; k = k0 - depth
+    for (int i = threadIdx.x; i < ta * cols; i += blockDim.x) {
+        const double v = s_dep[i];
+        if (v != 0.) {
+            const int d = i / cols, c = i - d * cols, dj = c / cg.tw, di = c - dj * cg.tw;
+            atomicAdd(g.jmean + ((cg.i0 - 1 + di) + g.nxg * ((cg.j0 - 1 + dj) + g.nyg * (k0 - d - 1))), v);
+        }
+    }
+    for (int i = threadIdx.x; i < tb * cols; i += blockDim.x) {
+        const unsigned int v = s_stop[i];
+        if (v) {
+            const int d = i / cols + 1, c = i - (d - 1) * cols, dj = c / cg.tw, di = c - dj * cg.tw;
+            atomicAdd(stops + ((cg.i0 - 1 + di) + g.nxg * ((cg.j0 - 1 + dj) + g.nyg * (k0 - d))), v);
+        }
+    }
+    unsigned long long v[4] = {packets, steps, absorbed, bottom};
+    const int slot[4] = {CNT_PACKETS, CNT_STEPS, CNT_ABSORBED, CNT_EXIT0 + 4};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned long long x = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(cnt + slot[q], x);
+    }
+}
+
 // Full-crossing deposits.  F(i,j,k) = packets of the column that stopped below voxel k = the running sum of the stop
 // counts up the column (plane k of `stops` holds the packets that stopped in voxel k, plane 0 those that left through
 // the bottom face); jmean(i,j,k) += F * dcell(k) * rhokap(i,j,k).  A CTA takes 32 columns (lanes along x: coalesced)

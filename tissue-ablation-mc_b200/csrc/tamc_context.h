@@ -34,7 +34,7 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1};
+    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0.};
     tamc::ColumnWorkspace colws;
     int reduce = 1;
     int box_reduce = -1;    // shipped regime: all-reduce only the columns under the beam (-1 = auto, 0 = off, 1 = on)

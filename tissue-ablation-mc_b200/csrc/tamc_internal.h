@@ -22,6 +22,11 @@ struct LaunchCfg {
                         // 1 = on with the z-fastest copy of the beam's columns, 2 = on, reading the resident grid
     int column_tile;    // column form: shared-memory tiles for the top planes of the deposits / stop counts; -1 = auto
                         // (column_plan in tamc_kernels.cu), 0 = off, 10*ta + tb = force that split
+    int column_park;    // tiled column form: regroup the column walk through per-warp queues; 1 = on, 0 = off, -1 = auto:
+                        // on when the previous stub-regime call on this handle averaged >= 2.25 voxel-steps per packet
+                        // (measured: +7 % at 2.98 steps per packet, -11 % at 1.56, where nearly every packet stops in
+                        // its first four-voxel group and there is nothing to regroup)
+    double steps_hint;  // voxel-steps per packet of the previous stub-regime call (0 = none yet)
 };
 
 // Which kernel an MC call ran ("form" read-only option of tamc_get_option)

@@ -535,7 +535,7 @@ static ColumnPlan column_plan(const DevGrid &g, const LaunchCfg &cfg, long long 
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        const long long avail = (long long)optin - 8ll * cg.nzp - 1024;
+        const long long avail = (long long)optin - 8ll * cg.nzp - 1024 - 32ll * (long long)sizeof(ParkQueue);
         int ta = wide ? 0 : 1, tb = wide ? 1 : 2;
         if (cfg.column_tile > 0) { ta = cfg.column_tile / 10; tb = cfg.column_tile % 10; }       // forced split
         ta = ta < g.nzg ? ta : g.nzg;
@@ -573,7 +573,15 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
         if (e != cudaSuccess) return e;
         const long long want = (n + 1023) / 1024;
         const int grid = (int)(want < cfg.num_sms ? want : cfg.num_sms);
-        k_transport_column_tiled<<<grid, 1024, tsmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
+        if (cfg.column_park > 0 || (cfg.column_park < 0 && cfg.steps_hint >= 2.25)) {
+            // tiles, then (8-byte aligned) one ParkQueue per warp
+            const size_t psmem = smem + 8 * ((size_t)cg.tw * cg.th * (size_t)ta + (((size_t)cg.tw * cg.th * (size_t)tb + 1) >> 1)) + 32 * sizeof(ParkQueue);
+            e = cudaFuncSetAttribute(k_transport_column_parked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            if (e != cudaSuccess) return e;
+            k_transport_column_parked<<<grid, 1024, psmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
+        } else {
+            k_transport_column_tiled<<<grid, 1024, tsmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
+        }
         e = cudaGetLastError();
     } else
     if (!gather) e = launch_sized(k_transport_column<false, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)nullptr, ws->stops, d_cnt);
