@@ -53,6 +53,7 @@ struct FastPhoton {
     int celli, cellj, cellk;      // 1-based voxel
     int ridx, jidx;               // linear indices into rhokap (halo layout) and jmean
     int dflags;                   // bit0-2: cosine < 0 (x,y,z); bit3-5: cosine == 0
+    double rk;                    // kAhead kernels: rhokap of the voxel the packet is in, fetched when it entered
 };
 
 __device__ __forceinline__ void set_direction(FastPhoton &p)
@@ -141,7 +142,11 @@ __device__ __forceinline__ double flip_sign(double v, int neg)
 // kNeedPos = false (shipped stub regime: the packet ends at its first interaction) drops the final
 // position update and its division: the last deposit dcell*rhokap = ((tau-taurun)/rhokap)*rhokap is
 // tallied as tau-taurun.
-template <bool kNeedPos, class Tally>
+// kAhead: the opacity is read from p.rk, loaded as soon as the packet's voxel was known (on adoption / at the end of
+// the previous step), so the load's latency runs beside the loop's bookkeeping instead of at the head of the step --
+// what matters when the grids exceed L2 (400^3: ncu long-scoreboard 3.5 per issue); a scattering that leaves the
+// packet in its voxel re-uses the value.
+template <bool kNeedPos, class Tally, bool kAhead = false>
 __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *xf, const double *yf, const double *zf,
                                                FastPhoton &p, Tally &tally)
 {
@@ -152,7 +157,7 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     const double dy = (f & 16) ? 100000. : (fy - p.ycur) * p.iny;
     const double dz = (f & 32) ? 100000. : (fz - p.zcur) * p.inz;
     const double dwall = fmin(fmin(dx, dy), dz);
-    const double rk = __ldg(g.rhokap + p.ridx);
+    const double rk = kAhead ? p.rk : __ldg(g.rhokap + p.ridx);
     const double taucell = dwall * rk;
     const bool wall = p.taurun + taucell < p.tau;                    // inttau2.f90:42
     const double rest = p.tau - p.taurun;
@@ -185,6 +190,7 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
     p.cellk += sz;
     p.ridx += sx + sy * g.sx + sz * (int)g.sxy;
     p.jidx += sx + sy * g.nxg + sz * (g.nxg * g.nyg);
+    if (kAhead && wall) p.rk = __ldg(g.rhokap + p.ridx);          // the halo keeps this in bounds when the packet has left
     if (!wall) return STEP_INTERACT;
     const bool out = ((unsigned)(p.celli - 1) >= (unsigned)g.nxg) | ((unsigned)(p.cellj - 1) >= (unsigned)g.nyg) |
                      ((unsigned)(p.cellk - 1) >= (unsigned)g.nzg);

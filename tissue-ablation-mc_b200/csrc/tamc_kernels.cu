@@ -652,6 +652,14 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
             const size_t qsmem = ((smem + 15) & ~(size_t)15) + 4 * sizeof(WarpPool);
             if (g.flags & TAMC_FRESNEL)
                 return launch_sized(k_transport_pool<128, 5, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+            // grids beyond L2 (400^3: 1 GB): the walk waits on DRAM for every opacity (ncu: long scoreboard 3.5 per issue) --
+            // fetch it one loop pass early (+8 % on phantom400; -1 % when the grids sit in L2, so only there)
+            int dev = 0, l2 = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+            const double grid_bytes = 8. * ((double)g.sxy * (g.nzg + 2) + (double)g.nxg * g.nyg * g.nzg);
+            if (grid_bytes > 2. * (double)l2)
+                return launch_sized(k_transport_pool<128, 5, false, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
             return launch_sized(k_transport_pool<128, 5, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
         }
         LaunchCfg c2 = cfg;

@@ -48,11 +48,15 @@ struct alignas(16) WarpPool {
 };
 
 // kFresnel compiles the boundary-optics extension in (TAMC_FRESNEL); the default build carries none of it.
-template <int kBlock, int kMinCtas, bool kFresnel>
+template <int kBlock, int kMinCtas, bool kFresnel, bool kAhead = false>
 __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                                   int chunk, int scatter_min,
                                                                   unsigned long long *__restrict__ cnt)
 {
+    // kAhead: opacity of the next voxel fetched one loop pass early (voxel_step_fast).  Never with kFresnel: a reflection
+    // moves the packet back into the grid after the step.
+    static_assert(!(kAhead && kFresnel), "kAhead and kFresnel are exclusive");
+
     extern __shared__ double s_faces[];
     const double *xf, *yf, *zf;
     stage_faces(g, s_faces, xf, yf, zf);
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 p.celli = g5.z & 0xffff; p.cellj = g5.z >> 16; p.cellk = g5.w;
                 p.ridx = p.celli + g.sx * (p.cellj + (g.nyg + 2) * p.cellk);
                 p.jidx = (p.celli - 1) + g.nxg * ((p.cellj - 1) + g.nyg * (p.cellk - 1));
+                if (kAhead) p.rk = __ldg(g.rhokap + p.ridx);
                 tally.pidx = g5.x; tally.pval = g1.y;
                 steps = g5.y;
                 if (kFresnel) nb = g4.w;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
             atomicAdd(&P.cnt[CNT_EXIT0 + 5], 1ull);
             atomicAdd(&P.cnt[CNT_SPECULAR], 1ull);
         } else if (walking) {
-            int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
+            int r = voxel_step_fast<true, decltype(tally), kAhead>(g, xf, yf, zf, p, tally);
             ++steps;
             if (fresnel && r == STEP_EXIT && fresnel_reflect_fast(g, xf, yf, zf, p, key, P.slot[slot].id.x, P.slot[slot].id.y, nb)) {
                 atomicAdd(&P.cnt[CNT_REFLECT], 1ull);
