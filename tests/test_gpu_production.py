@@ -346,3 +346,28 @@ def test_chi_square_full_size_layered_skin_200():
     assert (np.abs(z) > 3).mean() < 0.02 and abs(z.mean()) < 5 / np.sqrt(z.size)
     assert abs(steps / ref["stats"]["voxel_steps"] - 1) < 0.01 and abs(scat / ref["stats"]["scatters"] - 1) < 0.01
     assert abs(s1.sum() / ref["jmean"].sum() - 1) < 0.01
+
+
+def test_pool_kernel_with_early_opacity_fetch_at_400_cubed():
+    """Grids beyond L2 (phantom400: BASELINE config 4) take the pool kernel that fetches the next voxel's opacity one
+    loop pass early.  Same production arithmetic, so against the persistent kernel on the same packet ids the
+    counters are equal and the grid agrees to summation order."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["phantom400"]
+    t = make_transport(cfg)
+    n = 4000
+    res = {}
+    for variant in (3, 1):
+        t.set_option("variant", variant)
+        t.run_async(n, SEED, 0)
+        res[variant] = (t.get_jmean().copy(), t.get_stats(), t.get_option("form"))
+    assert res[3][2] == 3 and res[1][2] == 1
+    for key in ("packets", "voxel_steps", "scatters", "absorbed", "exits"):
+        assert res[3][1][key] == res[1][1][key], key
+    a, b = res[3][0], res[1][0]
+    assert np.array_equal(a != 0, b != 0)
+    nz = b != 0
+    assert np.abs(a[nz] - b[nz]).max() <= 1e-9 * np.abs(b[nz]).max()
+    assert res[3][1]["scatters"] > 100 * n
+    t.close()
