@@ -613,7 +613,8 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     }
     LaunchCfg cfg = cfg_in;
     const bool pool = cfg.variant == 3 && (g.flags & TAMC_SCATTER) && !d_rec;
-    if (cfg.block <= 0) cfg.block = pool ? 128 : 256;       // auto
+    const bool auto_block = cfg.block <= 0;
+    if (auto_block) cfg.block = pool ? 128 : 256;
     const bool merge = cfg.merge < 0 ? (g.flags & TAMC_SCATTER) != 0 : cfg.merge != 0;
     const size_t smem = faces_bytes(g);
     // shipped regime, default variant: the column form once the call is large enough to pay for its two small extra kernels
@@ -646,27 +647,27 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     if (pool) {
         // work-queue regrouping: faces + one 64-packet pool per warp in shared memory
         int chunk = cfg.chunk > 0 ? cfg.chunk : 64;
-        if (cfg.block <= 128) {   // 0 = auto: 128 threads, 5 CTAs per SM
+        // grids beyond L2 (400^3: 1 GB): the walk waits on DRAM for every opacity (ncu: long scoreboard 3.5 per issue) --
+        // fetch it one loop pass early (kAhead), and 256-thread CTAs (measured on phantom400: 128 x 5: 58.7 ms per 2e6
+        // packets, with kAhead 54.5; 256 x 2: 51.6; when the grids sit in L2 kAhead costs 1 %, so only there)
+        int dev = 0, l2 = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        const bool beyond_l2 = 8. * ((double)g.sxy * (g.nzg + 2) + (double)g.nxg * g.nyg * g.nzg) > 2. * (double)l2;
+        const bool fres = (g.flags & TAMC_FRESNEL) != 0;
+        if (auto_block ? !beyond_l2 : cfg.block <= 128) {       // auto: 128 threads, 5 CTAs per SM while the grids fit L2
             LaunchCfg c2 = cfg;
             c2.block = 128;
             const size_t qsmem = ((smem + 15) & ~(size_t)15) + 4 * sizeof(WarpPool);
-            if (g.flags & TAMC_FRESNEL)
-                return launch_sized(k_transport_pool<128, 5, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
-            // grids beyond L2 (400^3: 1 GB): the walk waits on DRAM for every opacity (ncu: long scoreboard 3.5 per issue) --
-            // fetch it one loop pass early (+8 % on phantom400; -1 % when the grids sit in L2, so only there)
-            int dev = 0, l2 = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
-            const double grid_bytes = 8. * ((double)g.sxy * (g.nzg + 2) + (double)g.nxg * g.nyg * g.nzg);
-            if (grid_bytes > 2. * (double)l2)
-                return launch_sized(k_transport_pool<128, 5, false, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+            if (fres) return launch_sized(k_transport_pool<128, 5, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+            if (beyond_l2) return launch_sized(k_transport_pool<128, 5, false, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
             return launch_sized(k_transport_pool<128, 5, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
         }
         LaunchCfg c2 = cfg;
         c2.block = 256;
         const size_t qsmem = ((smem + 15) & ~(size_t)15) + 8 * sizeof(WarpPool);
-        if (g.flags & TAMC_FRESNEL)
-            return launch_sized(k_transport_pool<256, 2, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        if (fres) return launch_sized(k_transport_pool<256, 2, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
+        if (beyond_l2) return launch_sized(k_transport_pool<256, 2, false, true>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
         return launch_sized(k_transport_pool<256, 2, false>, c2, qsmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
     }
     // shipped (stub) regime with enough packets to pay for zeroing and flushing a tile per SM: privatise the
