@@ -169,3 +169,44 @@ def test_shipped_configuration_coupled_trace_matches_oracle_fixture():
     assert first == {"boil": gold["first_boil_iteration"], "ablate": gold["first_ablation_iteration"],
                      "diverged": gold["diverged_iteration"]}
     t.close()
+
+
+@pytest.mark.parametrize("air_fraction,seed", [(0.5, 1), (0.75, 2), (0.9, 3)])
+def test_neighbour_rule_single_pass_equals_the_sequential_sweep(air_fraction, seed):
+    """The "six neighbours ablated" rule (3dFD.f90:347-353) runs upstream inside the k,j,i sweep; the device evaluates
+    it in one data-parallel pass (argument in csrc/tamc_heat.cu).  Hand-made air pockets -- isolated voxels, pairs,
+    chains along every axis, voxels against the halo -- against the sequential oracle, several calls in a row."""
+    n, npk = 16, 20000
+    t, h = _pair(n, zmax=0.06, pulsetype="tophat", power=5.0, energyPerPixel=4000.0, ablateTemp=150.0, loops=1)
+    rng = np.random.default_rng(seed)
+    rk = h.array("rhokap")                                # writable view of the oracle's array
+    hole = rng.uniform(size=(n, n, n)) < air_fraction
+    rk[1:-1, 1:-1, 1:-1][hole] = 0.0
+    # explicit chains of tissue through an air block, along each axis and ending at the halo
+    rk[2:9, 2:9, 2:9] = 0.0
+    rk[3:8, 5, 5] = 680.0
+    rk[5, 3:8, 3] = 680.0
+    rk[3, 3, 3:8] = 680.0
+    rk[1, 1, 1] = 680.0
+    rk[n, n, n] = 680.0
+    t.heat_upload("rhokap", np.asfortranarray(rk.copy()))
+    before = rk[1:-1, 1:-1, 1:-1].copy()
+    zeroed_by_rule = 0
+    for it in range(4):
+        t.run_async(npk, 77)
+        jm = t.get_jmean()
+        h.scale_jmean(jm, npk)
+        h.sim_3d(jm, it)
+        h.arrhenius()
+        h.setup_thermal_coeff(150.0)
+        t.heat_step(npk)
+        if not np.isfinite(h.array("temp")).all():
+            break
+        a, b = t.heat_array("rhokap"), h.array("rhokap")
+        assert np.array_equal(a == 0, b == 0), f"call {it}: the set of ablated voxels differs"
+        _compare(t, h)
+        now = b[1:-1, 1:-1, 1:-1]
+        zeroed_by_rule += int(((before != 0) & (now == 0)).sum())
+        before = now.copy()
+    assert zeroed_by_rule > 0                            # the rule really removed isolated tissue
+    t.close()

@@ -46,9 +46,9 @@ struct tamc_heat {
     int loops = 1, pulsesToDo = 1, pulsesDone = 0, pulsetype = 1, counter = 0;
     // device arrays
     double *coeff = nullptr, *kappa = nullptr, *density = nullptr, *heatcap = nullptr, *alpha = nullptr;   // (0:n+1)^3
-    double *temp = nullptr, *tn = nullptr, *cand = nullptr, *cand2 = nullptr, *cand3 = nullptr, *rk_new = nullptr;  // (0:n+1)^3
+    double *temp = nullptr, *tn = nullptr, *cand = nullptr, *cand2 = nullptr, *rk_new = nullptr;  // (0:n+1)^3
     double *water = nullptr, *Q = nullptr, *tissue = nullptr, *thres = nullptr;                              // n^3 (thres: 3 n^3)
-    int *flags = nullptr;                                                                                     // [0] changed, [1] negative temperature
+    int *flags = nullptr;                                                                                     // [1] negative temperature (sticky)
 };
 
 namespace {
@@ -125,46 +125,15 @@ __global__ void __launch_bounds__(256) k_heat_step(int n, const double *__restri
 
 // The "remove tissue whose six neighbours are ablated" rule (3dFD.f90:347-353) is evaluated upstream
 // inside the k,j,i sweep, so a voxel sees FINAL values of the neighbours behind the sweep (i-1, j-1, k-1)
-// and PREVIOUS-CALL values of those ahead (i+1, j+1, k+1).  final(v) = clamp(rule(local(v),
-// final(behind), old(ahead))) is a triangular system; iterating it from final = clamp(local) converges
-// to its unique solution, which is the sequential result.  One iteration = one launch; `changed` tells
-// the host when the fixed point is reached (normally after the first or second pass).
-__global__ void __launch_bounds__(256) k_rule(int n, const double *__restrict__ local, const double *__restrict__ cur,
-                                              double *__restrict__ next, const double *__restrict__ old, int *__restrict__ flags)
-{
-    int i, j, k;
-    if (!voxel_of_thread(n, i, j, k)) return;
-    const size_t c = h3(n, i, j, k), sy = (size_t)(n + 2), sz = (size_t)(n + 2) * (n + 2);
-    double v = local[c];
-    // same summation order as the Fortran: k+1, j+1, i+1, k-1, j-1, i-1
-    const double summ = old[c + sz] + old[c + sy] + old[c + 1] + cur[c - sz] + cur[c - sy] + cur[c - 1];
-    if (summ == 0.) v = 0.;
-    if (v <= 0.01) v = 0.;
-    if (v != cur[c]) flags[0] = 1;
-    next[c] = v;
-}
-
-// setupThermalCoeff, last part (3dFD.f90:350-357): store the final opacity; air properties where it is zero
-__global__ void __launch_bounds__(256) k_air(int n, const double *__restrict__ fin, const double *__restrict__ temp,
-                                             double *__restrict__ rhokap, double *__restrict__ density, double *__restrict__ heatcap,
-                                             double *__restrict__ kappa, double *__restrict__ alpha, double *__restrict__ coeff, double delt)
-{
-    int i, j, k;
-    if (!voxel_of_thread(n, i, j, k)) return;
-    const size_t c = h3(n, i, j, k);
-    const double v = fin[c];
-    rhokap[c] = v;
-    if (v <= 0.01) {
-        const double T = temp[c];
-        const double rho = airDensity(T);
-        density[c] = rho;
-        heatcap[c] = 1.006e3;
-        const double kap = airThermalCond(T);
-        kappa[c] = kap;
-        alpha[c] = kap / (rho * 1.006e3);
-        coeff[c] = delt / (airDensity(T) * 1.006e3);
-    }
-}
+// and PREVIOUS-CALL values of those ahead (i+1, j+1, k+1):
+//     final(v) = clamp(rule(local(v), final(behind), old(ahead))).
+// One data-parallel pass that reads clamp(local) for the neighbours behind gives exactly that sequential result.
+// Proof: the two can differ at a voxel Y only if a neighbour X behind it has final(X) = 0 != clamp(local(X)), i.e. X
+// was zeroed by the rule itself.  That needs all six terms of X's sum to vanish, among them old(Y) -- Y is one of
+// X's neighbours AHEAD.  But opacity never grows back: old(Y) = 0 makes local(Y) = 0 (the property update only
+// rescales rhokap > 0, 3dFD.f90:334-345), so final(Y) = 0 whatever X became.  Hence no host round trip and no
+// iteration: the whole time loop is enqueued ahead of the GPU.  (tests/test_gpu_heat.py compares the opacity with the
+// sequential oracle after every call, through boiling, ablation and hand-made air pockets.)
 
 // ---- fused passes (the common path of tamc_heat_step) --------------------------------------------------------
 // k_post = Arrhenius + the voxel-local half of setupThermalCoeff + clamp: one read of temp / rhokap / Q per voxel.
@@ -211,16 +180,14 @@ __global__ void __launch_bounds__(256) k_post(int n, const double *__restrict__ 
     cur[c] = rk <= 0.01 ? 0. : rk;
 }
 
-// k_rule_air = the first pass of the neighbour rule + the air-property block, writing the new opacity to a second
-// buffer (the rule still needs last call's values ahead of the sweep).  The set of air voxels only grows in later
-// passes, so the air properties written here never have to be undone; `changed` tells the host whether the rare
-// extra passes (k_rule ... k_air) are needed.
+// k_rule_air = the neighbour rule (see above) + the air-property block, writing the new opacity to a second buffer
+// (the rule still needs last call's values ahead of the sweep).
 __global__ void __launch_bounds__(256) k_rule_air(int n, const double *__restrict__ local, const double *__restrict__ cur,
-                                                  double *__restrict__ next, const double *__restrict__ old,
+                                                  const double *__restrict__ old,
                                                   const double *__restrict__ temp, double *__restrict__ rk_new,
                                                   double *__restrict__ density, double *__restrict__ heatcap,
                                                   double *__restrict__ kappa, double *__restrict__ alpha, double *__restrict__ coeff,
-                                                  double delt, int *__restrict__ flags)
+                                                  double delt)
 {
     int i, j, k;
     if (!voxel_of_thread(n, i, j, k)) return;
@@ -229,8 +196,6 @@ __global__ void __launch_bounds__(256) k_rule_air(int n, const double *__restric
     const double summ = old[c + sz] + old[c + sy] + old[c + 1] + cur[c - sz] + cur[c - sy] + cur[c - 1];
     if (summ == 0.) v = 0.;
     if (v <= 0.01) v = 0.;
-    if (v != cur[c]) flags[0] = 1;
-    next[c] = v;
     rk_new[c] = v;
     if (v <= 0.01) {
         const double T = temp[c];
@@ -271,7 +236,7 @@ void tamc_heat_release_(tamc_context *c)
 {
     tamc_heat *s = c->heat;
     if (!s) return;
-    double *arrs[] = {s->coeff, s->kappa, s->density, s->heatcap, s->alpha, s->temp, s->tn, s->cand, s->cand2, s->cand3, s->rk_new,
+    double *arrs[] = {s->coeff, s->kappa, s->density, s->heatcap, s->alpha, s->temp, s->tn, s->cand, s->cand2, s->rk_new,
                       s->water, s->Q, s->tissue, s->thres};
     for (double *p : arrs) cudaFree(p);
     cudaFree(s->flags);
@@ -347,9 +312,7 @@ extern "C" int tamc_heat_init(tamc_handle h, const tamc_heat_params *p, double *
     CU(up(&s->alpha, alpha)); CU(up(&s->kappa, kappa)); CU(up(&s->density, density)); CU(up(&s->heatcap, heatcap));
     CU(up(&s->coeff, coeff)); CU(up(&s->temp, temp)); CU(up(&s->tn, temp));
     CU(cudaMalloc(&s->cand, s->nh * sizeof(double))); CU(cudaMalloc(&s->cand2, s->nh * sizeof(double)));
-    CU(cudaMalloc(&s->cand3, s->nh * sizeof(double)));
     CU(cudaMemset(s->cand, 0, s->nh * sizeof(double))); CU(cudaMemset(s->cand2, 0, s->nh * sizeof(double)));
-    CU(cudaMemset(s->cand3, 0, s->nh * sizeof(double)));
     CU(cudaMalloc(&s->rk_new, s->nh * sizeof(double)));
     CU(cudaMemset(s->rk_new, 0, s->nh * sizeof(double)));
     std::vector<double> water(s->ni, kWaterInit);
@@ -402,27 +365,11 @@ extern "C" int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc)
     }
     // arrhenius(temp, delt, tissue, ThresTime, 1, N, N) and setupThermalCoeff(temp, N, ablateTemp), mcpolar.f90:180-182,
     // in two fused passes; the new opacity goes to a second buffer that then becomes the resident rhokap
-    double *cur = s->cand2, *nxt = s->cand3;       // iterates of the fixed point; their halo stays 0 like rhokap's
+    double *cur = s->cand2;                        // clamp(local); its halo stays 0 like rhokap's
     k_post<<<gi, 256, 0, st>>>(n, s->temp, h->d_rhokap, s->tissue, s->thres, s->cand, cur, s->water, s->Q, s->density, s->heatcap,
                                s->kappa, s->coeff, s->QVapor, s->ablateTemp, s->delt, s->time);
-    CU(cudaMemsetAsync(s->flags, 0, sizeof(int), st));
-    k_rule_air<<<gi, 256, 0, st>>>(n, s->cand, cur, nxt, h->d_rhokap, s->temp, s->rk_new, s->density, s->heatcap, s->kappa,
-                                   s->alpha, s->coeff, s->delt, s->flags);
-    std::swap(cur, nxt);
-    int changed = 0;
-    CU(cudaMemcpyAsync(&changed, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (changed) {
-        // rare: the rule zeroed a voxel whose neighbours ahead of it now see a different value -- iterate to the fixed point
-        for (int it = 0; it < 3 * n + 8 && changed; ++it) {
-            CU(cudaMemsetAsync(s->flags, 0, sizeof(int), st));
-            k_rule<<<gi, 256, 0, st>>>(n, s->cand, cur, nxt, h->d_rhokap, s->flags);
-            std::swap(cur, nxt);
-            CU(cudaMemcpyAsync(&changed, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-        }
-        k_air<<<gi, 256, 0, st>>>(n, cur, s->temp, s->rk_new, s->density, s->heatcap, s->kappa, s->alpha, s->coeff, s->delt);
-    }
+    k_rule_air<<<gi, 256, 0, st>>>(n, s->cand, cur, h->d_rhokap, s->temp, s->rk_new, s->density, s->heatcap, s->kappa,
+                                   s->alpha, s->coeff, s->delt);
     std::swap(h->d_rhokap, s->rk_new);              // both buffers keep a zero halo
     CU(cudaGetLastError());
     s->counter += 1;

@@ -10,7 +10,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tissue-ablation-mc_b200")]
 import tamc  # noqa: E402
 
 # algorithmic bytes per voxel of one tamc_heat_step call with loops = 1
-BYTES = {"k_heat_step": 72, "k_post": 128, "k_rule_air": 48}
+BYTES = {"k_heat_step": 72, "k_post": 128, "k_rule_air": 40}
 out = {}
 for n, calls in ((80, 400), (200, 60)):
     t = tamc.MCTransport(n, n, n, 0.03, 0.03, 0.06)
