@@ -196,9 +196,10 @@ extern "C" int tamc_init(int device, int nxg, int nyg, int nzg, double xmax, dou
     CUI(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_N; ++i) CUI(cudaEventCreate(&c->ev[i]));
     CUI(cudaMalloc(&c->d_rhokap, c->n_rhokap * sizeof(double)));
-    CUI(cudaMalloc(&c->d_jmean, c->n_jmean * sizeof(double)));
+    // the tally and, right behind it, the call's counters: one clear per MC call covers both
+    CUI(cudaMalloc(&c->d_jmean, (c->n_jmean + CNT_N) * sizeof(double)));
+    c->d_cnt = reinterpret_cast<unsigned long long *>(c->d_jmean + c->n_jmean);
     CUI(cudaMalloc(&c->d_faces, faces.size() * sizeof(double)));
-    CUI(cudaMalloc(&c->d_cnt, CNT_N * sizeof(unsigned long long)));
     CUI(cudaMemcpy(c->d_faces, faces.data(), faces.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUI(cudaMemset(c->d_rhokap, 0, c->n_rhokap * sizeof(double)));
     CUI(cudaMemset(c->d_jmean, 0, c->n_jmean * sizeof(double)));
@@ -215,7 +216,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     tamc_heat_release_(h);
-    cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_cnt); cudaFree(h->d_flush);
+    cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_flush);
     cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense);
     if (h->s_up) { cudaStreamSynchronize(h->s_up); cudaStreamDestroy(h->s_up); }
     if (h->s_dn) { cudaStreamSynchronize(h->s_dn); cudaStreamDestroy(h->s_dn); }
@@ -360,8 +361,8 @@ static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t fir
     const DevGrid g = make_grid(h);
     int launches = 0;
     CU(cudaEventRecord(h->ev[EV_ZERO0], h->stream));
-    CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));   // zarray / jmean = 0. (mcpolar.f90:185)
-    CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
+    static_assert(sizeof(unsigned long long) == sizeof(double), "the counters sit behind the tally in one allocation");
+    CU(cudaMemsetAsync(h->d_jmean, 0, (h->n_jmean + CNT_N) * sizeof(double), h->stream));   // zarray / jmean = 0. (mcpolar.f90:185) + counters
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
     CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches, &h->colws, &h->form));
     CU(cudaEventRecord(h->ev[EV_K1], h->stream));
