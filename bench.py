@@ -36,7 +36,7 @@ SEED = 20261017
 BYTES_PER_VOXEL_STEP = 16          # 8 B rhokap read + 8 B jmean accumulate
 HBM_FALLBACK_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 FORMS = {0: "k_transport_simple", 1: "k_transport_persistent", 2: "k_transport_exact", 3: "k_transport_pool",
-         4: "k_transport_stub_tiled", 5: "k_transport_column", 6: "k_transport_column", 7: "k_transport_column_tiled"}
+         4: "k_transport_stub_tiled", 5: "k_transport_column", 6: "k_transport_column", 7: "k_transport_column_tiled", 8: "k_transport_column_parked"}
 
 
 def parse():
@@ -337,13 +337,13 @@ def run_ours(args, cfg, name):
                                  "what": "L2-atomic / grid-lookup roofline of the step-by-step tally: same address stream (column under the beam, "
                                          "geometric step count), one fp64 load of rhokap + one fp64 RED into jmean per voxel-step, no transport arithmetic"}
             roofline["frac_of_probe"] = vs_rate / roofline["probe"]["voxel_steps_per_s"]
-            if form in (5, 6, 7):
+            if form in (5, 6, 7, 8):
                 t.set_option("probe_form", 1)
                 t.roofline_probe(packets, SEED)
                 pms, psteps = t.roofline_probe(packets, SEED)
                 roofline["probe_column"] = {"voxel_steps_per_s": psteps / (pms * 1e-3), "ms": pms,
                                             "what": "the same for the column form the kernel uses: per packet one 256-bit load of the z-fastest opacity copy per "
-                                                    "four voxels + one fp64 RED + at most one u32 RED (form 7: the top planes in the same shared-memory "
+                                                    "four voxels + one fp64 RED + at most one u32 RED (forms 7, 8: the top planes in the same shared-memory "
                                                     "tiles, same launch shape), incl. the gather and finish kernels, no transport arithmetic"}
                 roofline["frac_of_probe_column"] = vs_rate / roofline["probe_column"]["voxel_steps_per_s"]
             t.set_option("probe_form", -1)

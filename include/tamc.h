@@ -166,11 +166,12 @@ int tamc_unpin_host(void *ptr);
  * persistent warps otherwise), "block" (0 = auto), "ctas_per_sm", "chunk", "scatter_min", "merge",
  * "min_ctas", "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "column_tile" (shared-memory
  * tiles of the column form: -1 = auto, 0 = off, 10*ta + tb = ta planes of deposits and tb planes of
- * stop counts), "reduce" (0 = skip the all-reduce), "box_reduce" / "box_io" (-1 = auto, 0 = move the
+ * stop counts), "column_park" (regrouped column walk of a tiled call: -1 = auto from the previous call's
+ * voxel-steps per packet, 0 = off, 1 = on), "reduce" (0 = skip the all-reduce), "box_reduce" / "box_io" (-1 = auto, 0 = move the
  * whole grid), "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 =
  * per-voxel-step address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the
  * last MC call ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on
- * the resident grid, 7 column with shared-memory tiles), "io_form" (see tamc_run_optics). */
+ * the resident grid, 7 column with shared-memory tiles, 8 the same with the regrouped walk), "io_form" (see tamc_run_optics). */
 int tamc_set_option(tamc_handle h, const char *name, int64_t value);
 int64_t tamc_get_option(tamc_handle h, const char *name);
 /* Access-pattern-only kernel: the tally/grid address stream of `nphotons` straight-down packets

@@ -132,7 +132,7 @@ def test_auto_tiles_for_calls_that_amortise_the_flush(name, n, split):
     t = make_transport(cfg)
     t.run_async(n, SEED, 0)
     jm, st = t.get_jmean().copy(), t.get_stats()
-    assert t.get_option("form") == 7 and st["gpu_launches"] == 3
+    assert t.get_option("form") in (7, 8) and st["gpu_launches"] == 3
     t.set_option("column", 1)
     t.set_option("column_tile", 0)
     t.run_async(n, SEED, 0)

@@ -30,7 +30,7 @@ struct LaunchCfg {
 };
 
 // Which kernel an MC call ran ("form" read-only option of tamc_get_option)
-enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6, FORM_COLUMN_TILED = 7 };
+enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6, FORM_COLUMN_TILED = 7, FORM_COLUMN_PARKED = 8 };
 
 // Device buffers of the column form, owned by the handle and grown on demand by launch_transport.
 struct ColumnWorkspace {

@@ -548,6 +548,9 @@ static ColumnPlan column_plan(const DevGrid &g, const LaunchCfg &cfg, long long 
     return p;
 }
 
+// regrouped column walk (k_transport_column_parked) for a tiled call? -- LaunchCfg::column_park
+static bool column_parked(const LaunchCfg &cfg) { return cfg.column_park > 0 || (cfg.column_park < 0 && cfg.steps_hint >= 2.25); }
+
 bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n)
 {
     return column_plan(g, cfg, n).use && cfg.column != 2;
@@ -573,7 +576,7 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
         if (e != cudaSuccess) return e;
         const long long want = (n + 1023) / 1024;
         const int grid = (int)(want < cfg.num_sms ? want : cfg.num_sms);
-        if (cfg.column_park > 0 || (cfg.column_park < 0 && cfg.steps_hint >= 2.25)) {
+        if (column_parked(cfg)) {
             // tiles, then (8-byte aligned) one ParkQueue per warp
             const size_t psmem = smem + 8 * ((size_t)cg.tw * cg.th * (size_t)ta + (((size_t)cg.tw * cg.th * (size_t)tb + 1) >> 1)) + 32 * sizeof(ParkQueue);
             e = cudaFuncSetAttribute(k_transport_column_parked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
@@ -620,7 +623,8 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     // shipped regime, default variant: the column form once the call is large enough to pay for its two small extra kernels
     const ColumnPlan plan = (ws && !d_rec) ? column_plan(g, cfg, n) : ColumnPlan{false, 0, 0};
     if (plan.use) {
-        if (form) *form = cfg.column == 2 ? FORM_COLUMN_RESIDENT : (plan.ta + plan.tb > 0 ? FORM_COLUMN_TILED : FORM_COLUMN);
+        const bool parked = plan.ta + plan.tb > 0 && cfg.column != 2 && column_parked(cfg);
+        if (form) *form = cfg.column == 2 ? FORM_COLUMN_RESIDENT : (parked ? FORM_COLUMN_PARKED : (plan.ta + plan.tb > 0 ? FORM_COLUMN_TILED : FORM_COLUMN));
         return launch_column(g, cfg, n, seed, first_id, d_cnt, s, launches, ws, cfg.column != 2, plan);
     }
     if (launches) *launches += 1;
