@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 FLAG_SCATTER = 1
 FLAG_FRESNEL = 2
+FLAG_PERIODIC = 4
 
 RECORD_DTYPE = np.dtype(
     [
@@ -42,6 +43,7 @@ class Stats(C.Structure):
         ("deposit_sum", C.c_double),
         ("specular", C.c_int64),
         ("internal_reflections", C.c_int64),
+        ("wraps", C.c_int64),
     ]
 
     def as_dict(self):
@@ -49,7 +51,7 @@ class Stats(C.Structure):
             "packets": self.packets, "voxel_steps": self.voxel_steps, "scatters": self.scatters,
             "absorbed": self.absorbed, "exits": list(self.exits), "draws": self.draws,
             "deposit_sum": self.deposit_sum, "specular": self.specular,
-            "internal_reflections": self.internal_reflections,
+            "internal_reflections": self.internal_reflections, "wraps": self.wraps,
         }
 
 
@@ -90,6 +92,7 @@ def _bind(path: str) -> C.CDLL:
     lib.orc_init_opt1.argtypes = [p]
     lib.orc_set_optics.argtypes = [p, d, d]
     lib.orc_set_spot.argtypes = [p, d]
+    lib.orc_set_source_gaussian.argtypes = [p, d]
     lib.orc_set_indices.argtypes = [p, d, d]
     lib.orc_set_flags.argtypes = [p, i]
     lib.orc_zero_jmean.argtypes = [p]
@@ -211,6 +214,10 @@ class Oracle:
 
     def set_spot(self, diameter: float):
         self.lib.orc_set_spot(self.h, float(diameter))
+
+    def set_source_gaussian(self, sigma: float):
+        """Gaussian beam through rang() (sourceph.f90:73-101); sigma <= 0 = back to the CO2 disk."""
+        self.lib.orc_set_source_gaussian(self.h, float(sigma))
 
     def set_flags(self, flags: int):
         self.lib.orc_set_flags(self.h, int(flags))

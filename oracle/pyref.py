@@ -90,10 +90,23 @@ def find(val: float, a) -> int:
     return lo
 
 
+def rang(avg: float, sigma: float, rng) -> float:
+    """sourceph.f90:73-101 (Marsaglia polar method) over ranu, :52-70."""
+    while True:
+        u = -1.0 + rng() * (1.0 - -1.0)
+        s = -1.0 + rng() * (1.0 - -1.0)
+        s = s * s + u * u
+        if not s >= 1.0:
+            break
+    return avg + sigma * (u * math.sqrt(-2.0 * math.log(s) / s))
+
+
 def photon_loop(nphotons, nxg, nyg, nzg, xmax, ymax, zmax, rhokap, rng, albedo=0.0, hgg=0.9,
-                scatter=False, spot=250e-4):
+                scatter=False, spot=250e-4, gauss_sigma=0.0, periodic=False):
     """mcpolar.f90:151-170.  rhokap(i,j,k) is a callable on 1-based interior indices.
 
+    gauss_sigma > 0: launch point from rang() (sourceph.f90:73-101), redrawn while off the top face -- builder-defined
+    use of upstream dead code.  periodic: repeat_bounds (inttau2.f90:242-279, dead code upstream) on lateral exits.
     Returns (tally dict {(i,j,k): value}, list of per-packet dicts)."""
     xf, yf, zf = make_faces(nxg, xmax), make_faces(nyg, ymax), make_faces(nzg, zmax)
     delta = 1.0e-8 * (2.0 * zmax / nzg)                     # mcpolar.f90:112
@@ -104,10 +117,18 @@ def photon_loop(nphotons, nxg, nyg, nzg, xmax, ymax, zmax, rhokap, rng, albedo=0
     for _ in range(nphotons):
         n0 = rng.count
         # ---- sourceph.f90:28-47
-        r = rng() * ((spot / 2.0) * (spot / 2.0))
-        theta = rng() * TWOPI
-        pos = [math.sqrt(r) * math.cos(theta), math.sqrt(r) * math.sin(theta),
-               zmax - (1.0e-8 * (2.0 * zmax / nzg))]
+        if gauss_sigma > 0.0:
+            pos = [0.0, 0.0, zmax - (1.0e-8 * (2.0 * zmax / nzg))]
+            for ax, lim in ((0, xmax), (1, ymax)):
+                v = rang(0.0, gauss_sigma, rng)
+                while not abs(v) < lim:
+                    v = rang(0.0, gauss_sigma, rng)
+                pos[ax] = v
+        else:
+            r = rng() * ((spot / 2.0) * (spot / 2.0))
+            theta = rng() * TWOPI
+            pos = [math.sqrt(r) * math.cos(theta), math.sqrt(r) * math.sin(theta),
+                   zmax - (1.0e-8 * (2.0 * zmax / nzg))]
         phi = TWOPI * rng()
         cosp, sinp = math.cos(phi), math.sin(phi)
         sint, cost = 0.0, -1.0
@@ -115,7 +136,11 @@ def photon_loop(nphotons, nxg, nyg, nzg, xmax, ymax, zmax, rhokap, rng, albedo=0
         cell = [int(nxg * (pos[0] + xmax) / (2.0 * xmax)) + 1,
                 int(nyg * (pos[1] + ymax) / (2.0 * ymax)) + 1,
                 int(nzg * (pos[2] + zmax) / (2.0 * zmax)) + 1]
+        if gauss_sigma > 0.0:
+            cell[0], cell[1] = min(cell[0], nxg), min(cell[1], nyg)
         info = {"steps": 0, "deposit": 0.0, "nscatt": 0}
+        if periodic:
+            info["wraps"] = 0
 
         def tauint1():
             """inttau2.f90:7-72; returns True when the packet left the grid."""
@@ -158,6 +183,15 @@ def photon_loop(nphotons, nxg, nyg, nzg, xmax, ymax, zmax, rhokap, rng, albedo=0
                             cur[ax] = cur[ax] + n[ax] * dcell
                     for ax in range(3):                   # update_voxels, inttau2.f90:201-203
                         cell[ax] = find(cur[ax], faces[ax])
+                    if periodic:                          # repeat_bounds, inttau2.f90:242-279
+                        for ax, lim, ng in ((0, xmax, nxg), (1, ymax, nyg)):
+                            if cell[ax] == -1:
+                                if cur[ax] < delta:
+                                    cur[ax], cell[ax] = 2.0 * lim - delta, ng
+                                    info["wraps"] += 1
+                                elif cur[ax] > 2.0 * lim - delta:
+                                    cur[ax], cell[ax] = delta, 1
+                                    info["wraps"] += 1
                 else:
                     dcell = (tau - taurun) / rk
                     tally[key] = tally.get(key, 0.0) + dcell * rk
@@ -272,10 +306,35 @@ def golden():
     return out
 
 
+def golden_next():
+    """Known answers for the SURVEY 8(f)-2 options built on upstream dead code (rang, repeat_bounds)."""
+    out = {"source": "oracle/pyref.py golden_next() (independent Python transliteration; builder-defined call sites)"}
+    # Gaussian beam, shipped stub regime on a coarse grid; sigma comparable to the half-width so redraws happen
+    tally, pk = photon_loop(24, 20, 20, 20, 0.03, 0.03, 0.06, lambda i, j, k: 680.0, Ran2(2), gauss_sigma=0.02)
+    out["gauss_stub_first24"] = pk
+    out["gauss_stub_first24_tally"] = [[list(k), v] for k, v in sorted(tally.items())]
+    # periodic lateral boundaries, thin turbid slab (most packets cross a lateral face several times)
+    tally, pk = photon_loop(16, 8, 8, 24, 0.01, 0.01, 0.06, lambda i, j, k: 90.0 if k > 6 else 40.0, Ran2(4),
+                            albedo=0.95, hgg=0.8, scatter=True, spot=0.01, periodic=True)
+    out["periodic_first16"] = pk
+    out["periodic_first16_tally"] = [[list(k), v] for k, v in sorted(tally.items())]
+    # both at once
+    tally, pk = photon_loop(12, 10, 12, 14, 0.02, 0.024, 0.03, lambda i, j, k: 120.0, Ran2(6), albedo=0.9, hgg=0.0,
+                            scatter=True, gauss_sigma=0.015, periodic=True)
+    out["gauss_periodic_first12"] = pk
+    out["gauss_periodic_first12_tally"] = [[list(k), v] for k, v in sorted(tally.items())]
+    return out
+
+
 if __name__ == "__main__":
-    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "oracle_kat.json")
+    here = os.path.dirname(os.path.abspath(__file__))
+    dst = os.path.join(here, "..", "tests", "golden", "oracle_kat.json")
     if len(sys.argv) > 1:
         dst = sys.argv[1]
     with open(dst, "w") as f:
         json.dump(golden(), f, indent=1)
     print("wrote", os.path.normpath(dst))
+    dst2 = os.path.join(os.path.dirname(dst), "oracle_kat_next.json")
+    with open(dst2, "w") as f:
+        json.dump(golden_next(), f, indent=1)
+    print("wrote", os.path.normpath(dst2))

@@ -43,11 +43,14 @@ struct orc_state {
     int iv[32], iy, idum2;
     /* sourceph.f90:23 */
     double spotSize;
+    double gauss_sigma;         /* > 0: Gaussian beam through rang() instead of the CO2 disk */
     /* oracle plumbing */
     int flags;
     int rng_mode;
     uint64_t ph_seed, ph_packet;
     uint32_t ph_block[4];
+    int64_t ph_block_idx;       /* which block of the packet's main stream ph_block holds (-1 = none) */
+    int64_t pkt_sdraws;         /* source-stream draws consumed by the current packet (Philox: counter word 3 = 2) */
     int64_t pkt_draws;          /* draws consumed by the current packet */
     double *draw_log;
     int64_t draw_cap, draw_n;
@@ -57,6 +60,7 @@ struct orc_state {
     double deposit;
     int64_t pkt_bdraws;         /* boundary-stream draws consumed by the current packet */
     int64_t internal_reflections;
+    int64_t wraps;              /* ORC_FLAG_PERIODIC: lateral re-entries */
 };
 
 #define RHOKAP(o, i, j, k) ((o)->rhokap[(size_t)(i) + (size_t)((o)->nxg + 2) * ((size_t)(j) + (size_t)((o)->nyg + 2) * (size_t)(k))])
@@ -142,6 +146,7 @@ void orc_set_optics(orc_state *o, double albedo, double hgg)
 }
 
 void orc_set_spot(orc_state *o, double d) { o->spotSize = d; }
+void orc_set_source_gaussian(orc_state *o, double sigma) { o->gauss_sigma = sigma > 0. ? sigma : 0.; }
 void orc_set_indices(orc_state *o, double n1, double n2) { o->n1 = n1; o->n2 = n2; }
 void orc_set_flags(orc_state *o, int flags) { o->flags = flags; }
 void orc_zero_jmean(orc_state *o) { memset(o->jmean, 0, sizeof(double) * (size_t)o->nxg * o->nyg * o->nzg); }
@@ -228,9 +233,11 @@ static double draw(orc_state *o)
         r = ran2(o, &o->iseed);
     } else {
         int lane = (int)(o->pkt_draws & 3);
-        if (lane == 0)
+        if (o->ph_block_idx != (o->pkt_draws >> 2)) {
+            o->ph_block_idx = o->pkt_draws >> 2;
             orc_philox4x32_10((uint32_t)o->ph_seed, (uint32_t)(o->ph_seed >> 32), (uint32_t)o->ph_packet,
-                              (uint32_t)(o->ph_packet >> 32), (uint32_t)(o->pkt_draws >> 2), 0u, o->ph_block);
+                              (uint32_t)(o->ph_packet >> 32), (uint32_t)o->ph_block_idx, 0u, o->ph_block);
+        }
         r = ((double)o->ph_block[lane] + 0.5) * (1.0 / 4294967296.0);
     }
     o->pkt_draws++;
@@ -307,6 +314,71 @@ static void sourcephCO2(orc_state *o, double xmax, double ymax, double zmax, int
     *xcell = (int)((double)o->nxg * (o->xp + xmax) / (2. * xmax)) + 1;
     *ycell = (int)((double)o->nyg * (o->yp + ymax) / (2. * ymax)) + 1;
     *zcell = (int)((double)o->nzg * (o->zp + zmax) / (2. * zmax)) + 1;
+}
+
+/* Draws of the Gaussian source.  ran2: the one sequential generator (logged, so replay sees them in order).
+ * Philox: a stream of their own (counter word 3 = 2, draw index / 4 in word 2) because the polar method consumes a
+ * variable number of draws, and the packet's main stream keeps its fixed layout of one block per event. */
+static double draw_source(orc_state *o)
+{
+    if (o->rng_mode == ORC_RNG_RAN2) return draw(o);
+    {
+        uint32_t b[4];
+        orc_philox4x32_10((uint32_t)o->ph_seed, (uint32_t)(o->ph_seed >> 32), (uint32_t)o->ph_packet,
+                          (uint32_t)(o->ph_packet >> 32), (uint32_t)(o->pkt_sdraws >> 2), 2u, b);
+        return ((double)b[o->pkt_sdraws++ & 3] + 0.5) * (1.0 / 4294967296.0);
+    }
+}
+
+/* sourceph.f90:52-70 */
+static double ranu(orc_state *o, double a, double b)
+{
+    return a + draw_source(o) * (b - a);
+}
+
+/* sourceph.f90:73-101 (Marsaglia polar method; only the first variate of the pair is used) */
+static double rang(orc_state *o, double avg, double sigma)
+{
+    double u = 0., s, tmp;
+
+    s = 1.;
+    while (s >= 1.) {
+        u = ranu(o, -1., 1.);
+        s = ranu(o, -1., 1.);
+        s = s * s + u * u;       /* s**2. + u**2. */
+    }
+    tmp = u * sqrt(-2. * log(s) / s);
+
+    return avg + sigma * tmp;
+}
+
+/* Builder-defined launch on top of rang() -- the reference defines rang and never calls it.  Everything but the
+ * entry point is sourcephCO2 (sourceph.f90:32-47); a variate that misses the top face is redrawn, so every packet
+ * enters the grid and the cell formula stays in range. */
+static void sourcephGauss(orc_state *o, double xmax, double ymax, double zmax, int *xcell, int *ycell, int *zcell)
+{
+    const double sigma = o->gauss_sigma;
+
+    do { o->xp = rang(o, 0., sigma); } while (!(fabs(o->xp) < xmax));
+    do { o->yp = rang(o, 0., sigma); } while (!(fabs(o->yp) < ymax));
+    o->zp = zmax - (1.e-8 * (2. * zmax / (double)o->nzg));
+
+    if (o->rng_mode == ORC_RNG_PHILOX) o->pkt_draws = 2;   /* phi and tau stay words 2 and 3 of the packet's block 0 */
+    o->phi = TWOPI * draw(o);
+    o->cosp = cos(o->phi);
+    o->sinp = sin(o->phi);
+    o->sint = 0.;
+    o->cost = -1.;
+
+    o->nxp = o->sint * o->cosp;
+    o->nyp = o->sint * o->sinp;
+    o->nzp = o->cost;
+
+    *xcell = (int)((double)o->nxg * (o->xp + xmax) / (2. * xmax)) + 1;
+    *ycell = (int)((double)o->nyg * (o->yp + ymax) / (2. * ymax)) + 1;
+    *zcell = (int)((double)o->nzg * (o->zp + zmax) / (2. * zmax)) + 1;
+    if (*xcell > o->nxg) *xcell = o->nxg;   /* (xp + xmax) rounded up to 2 xmax: one ulp from the edge */
+    if (*ycell > o->nyg) *ycell = o->nyg;
 }
 
 /* ------------------------------------------------------------------ tauint1 and helpers */
@@ -390,6 +462,35 @@ static void update_pos(orc_state *o, double *xcur, double *ycur, double *zcur, i
     if (wall_flag) update_voxels(o, *xcur, *ycur, *zcur, celli, cellj, cellk);
 }
 
+/* inttau2.f90:242-279.  Returns 0, or -1 where the Fortran prints 'Error in Repeat_bounds...' and stops. */
+static int repeat_bounds(int *cella, int *cellb, double *acur, double *bcur, double amax, double bmax, int nag, int nbg,
+                         double delta)
+{
+    if (*cella == -1) {
+        if (*acur < delta) {
+            *acur = 2. * amax - delta;
+            *cella = nag;
+        } else if (*acur > 2. * amax - delta) {
+            *acur = delta;
+            *cella = 1;
+        } else {
+            return -1;
+        }
+    }
+    if (*cellb == -1) {
+        if (*bcur < delta) {
+            *bcur = 2. * bmax - delta;
+            *cellb = nbg;
+        } else if (*bcur > 2. * bmax - delta) {
+            *bcur = delta;
+            *cellb = 1;
+        } else {
+            return -1;
+        }
+    }
+    return 0;
+}
+
 /* inttau2.f90:7-72 */
 static void tauint1(orc_state *o, double xmax, double ymax, double zmax, int *xcell, int *ycell, int *zcell,
                     int *tflag, double delta)
@@ -424,6 +525,11 @@ static void tauint1(orc_state *o, double xmax, double ymax, double zmax, int *xc
             {
                 const int pi = celli, pj = cellj, pk = cellk;
                 update_pos(o, &xcur, &ycur, &zcur, &celli, &cellj, &cellk, dcell, 1, dir, delta);
+                /* ORC_FLAG_PERIODIC: the call site repeat_bounds never got upstream -- a packet that left through a
+                 * lateral face re-enters on the opposite side and the optical-depth integration continues */
+                if ((o->flags & ORC_FLAG_PERIODIC) && (celli == -1 || cellj == -1)) {
+                    if (repeat_bounds(&celli, &cellj, &xcur, &ycur, xmax, ymax, o->nxg, o->nyg, delta) == 0) o->wraps++;
+                }
                 if ((o->flags & ORC_FLAG_FRESNEL) && (celli == -1 || cellj == -1 || cellk == -1)) {
                     /* extension: the crossed face is an outer face of the grid */
                     const int a = dir[0] ? 0 : (dir[1] ? 1 : 2);
@@ -610,6 +716,7 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
     o->draw_overflow = 0;
 
     o->internal_reflections = 0;
+    o->wraps = 0;
     for (j = 1; j <= nphotons; j++) {
         int absorbed = 0, specular = 0;
         tflag = 0;
@@ -620,7 +727,10 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
         if (offsets) offsets[j - 1] = o->draw_n;
 
         o->pkt_bdraws = 0;
-        sourcephCO2(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell);
+        o->pkt_sdraws = 0;
+        o->ph_block_idx = -1;
+        if (o->gauss_sigma > 0.) sourcephGauss(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell);
+        else sourcephCO2(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell);
         if (o->flags & ORC_FLAG_FRESNEL) {
             /* extension: specular reflection at the top surface, normal incidence */
             const double r0 = (o->n1 - o->n2) / (o->n1 + o->n2);
@@ -674,6 +784,7 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
     }
     if (offsets) offsets[nphotons] = o->draw_n;
     st.internal_reflections = o->internal_reflections;
+    st.wraps = o->wraps;
     if (stats) *stats = st;
     o->draw_log = NULL;
     return o->draw_overflow ? -1 : 0;
@@ -757,6 +868,7 @@ int orc_run_ranks(int nranks, int nxg, int nyg, int nzg, double xmax, double yma
             stats->deposit_sum += rstats[r].deposit_sum;
             stats->specular += rstats[r].specular;
             stats->internal_reflections += rstats[r].internal_reflections;
+            stats->wraps += rstats[r].wraps;
             for (f = 0; f < 6; f++) stats->exits[f] += rstats[r].exits[f];
         }
     }

@@ -48,12 +48,14 @@ typedef struct {
     double  deposit_sum;
     int64_t specular;       /* ORC_FLAG_FRESNEL: reflected at the top surface before entering (also counted in exits[5]) */
     int64_t internal_reflections;
+    int64_t wraps;          /* ORC_FLAG_PERIODIC: lateral re-entries (repeat_bounds) */
 } orc_stats;
 
 typedef struct orc_state orc_state;
 
 enum { ORC_RNG_RAN2 = 0, ORC_RNG_PHILOX = 1 };
-enum { ORC_FLAG_SCATTER = 1, ORC_FLAG_FRESNEL = 2 };
+enum { ORC_FLAG_SCATTER = 1, ORC_FLAG_FRESNEL = 2,
+       ORC_FLAG_PERIODIC = 4 /* repeat_bounds (inttau2.f90:242-279, never called upstream) applied to lateral exits */ };
 
 /* Allocate module state for an nxg*nyg*nzg grid and build the face arrays
  * (gridset.f90:23-31); rhokap and jmean start at zero. */
@@ -77,6 +79,11 @@ void orc_set_optics(orc_state *o, double albedo, double hgg);
  * for ORC_FLAG_FRESNEL -- specular reflection at launch, Fresnel reflection or escape at the six outer faces. */
 void orc_set_indices(orc_state *o, double n1, double n2);
 void orc_set_spot(orc_state *o, double spot_diameter);   /* sourceph.f90:23, default 250d-4 */
+/* Gaussian beam built on rang() (sourceph.f90:73-101: Marsaglia polar method over ranu, :52-70; dead code
+ * upstream, so the launch that uses it is builder-defined): xp = rang(0, sigma), yp = rang(0, sigma), each
+ * redrawn while it falls off the top face (|xp| >= xmax); everything else as sourcephCO2.  sigma <= 0
+ * switches back to the CO2 disk. */
+void orc_set_source_gaussian(orc_state *o, double sigma);
 void orc_set_flags(orc_state *o, int flags);
 void orc_zero_jmean(orc_state *o);
 

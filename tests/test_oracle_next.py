@@ -1,0 +1,172 @@
+"""SURVEY 8(f)-2 options built on upstream dead code -- the Gaussian beam through rang() (sourceph.f90:73-101) and
+periodic lateral boundaries through repeat_bounds (inttau2.f90:242-279): the C oracle against the committed known
+answers of the independent Python transliteration (tests/golden/oracle_kat_next.json, oracle/pyref.py golden_next())
+and against analytic properties.  The call sites are builder-defined (the reference defines both routines and never
+calls them); parity is unpinned by the reference itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import pyref
+from tests.test_oracle_kat import _check_packets, _check_tally
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden_next():
+    with open(os.path.join(HERE, "golden", "oracle_kat_next.json")) as f:
+        return json.load(f)
+
+
+def test_gaussian_stub_known_answers(golden_next):
+    o = orc.Oracle(20, 20, 20, 0.03, 0.03, 0.06)
+    o.gridset_uniform(680.0)
+    o.set_source_gaussian(0.02)
+    o.seed_ran2(2)
+    out = o.run(24, records=True, draws_cap=4096)
+    _check_packets(out["records"], out["offsets"], golden_next["gauss_stub_first24"])
+    _check_tally(o.jmean, golden_next["gauss_stub_first24_tally"])
+
+
+def test_periodic_known_answers(golden_next):
+    o = orc.Oracle(8, 8, 24, 0.01, 0.01, 0.06)
+    rk = np.zeros((10, 10, 26), order="F")
+    rk[1:-1, 1:-1, 1:-1] = 90.0
+    rk[1:-1, 1:-1, 1:7] = 40.0
+    o.set_rhokap(rk)
+    o.set_optics(0.95, 0.8)
+    o.set_spot(0.01)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_ran2(4)
+    out = o.run(16, records=True, draws_cap=1 << 16)
+    pk = golden_next["periodic_first16"]
+    _check_packets(out["records"], out["offsets"], pk)
+    _check_tally(o.jmean, golden_next["periodic_first16_tally"])
+    assert out["stats"]["wraps"] == sum(p["wraps"] for p in pk) > 0
+    assert out["stats"]["exits"][:4] == [0, 0, 0, 0]              # nothing leaves through a lateral face
+
+
+def test_gaussian_periodic_known_answers(golden_next):
+    o = orc.Oracle(10, 12, 14, 0.02, 0.024, 0.03)
+    o.gridset_uniform(120.0)
+    o.set_optics(0.9, 0.0)
+    o.set_source_gaussian(0.015)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_ran2(6)
+    out = o.run(12, records=True, draws_cap=1 << 16)
+    _check_packets(out["records"], out["offsets"], golden_next["gauss_periodic_first12"])
+    _check_tally(o.jmean, golden_next["gauss_periodic_first12_tally"])
+
+
+def test_pyref_live_agrees_periodic_fresh_case():
+    nx, ny, nz = 9, 7, 11
+    o = orc.Oracle(nx, ny, nz, 0.015, 0.012, 0.03)
+    rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+    ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    rk[1:-1, 1:-1, 1:-1] = 60.0 + 9.0 * ((ii + 3 * jj + 2 * kk) % 5)
+    o.set_rhokap(rk)
+    o.set_optics(0.93, 0.6)
+    o.set_source_gaussian(0.02)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_ran2(9)
+    out = o.run(30, records=True, draws_cap=1 << 16)
+    tally, pk = pyref.photon_loop(30, nx, ny, nz, 0.015, 0.012, 0.03, lambda i, j, k: float(rk[i, j, k]),
+                                  pyref.Ran2(9), albedo=0.93, hgg=0.6, scatter=True, gauss_sigma=0.02, periodic=True)
+    _check_packets(out["records"], out["offsets"], pk)
+    _check_tally(o.jmean, [[list(k), v] for k, v in tally.items()])
+    assert out["stats"]["wraps"] == sum(p["wraps"] for p in pk) > 0
+
+
+def test_gaussian_beam_moments():
+    """rang() gives N(0, sigma^2): with sigma well inside the face the launch points have that mean and variance,
+    the tally summed over z is the binned Gaussian, and the stub-regime invariants (deposit = tau) still hold."""
+    n, xmax, sigma, npk = 40, 0.05, 0.008, 200000
+    o = orc.Oracle(n, n, n, xmax, xmax, 0.06)
+    o.gridset_uniform(680.0)
+    o.set_source_gaussian(sigma)
+    o.seed_ran2(1)
+    out = o.run(npk, records=True)
+    rec, st = out["records"], out["stats"]
+    se = sigma / np.sqrt(npk)
+    assert abs(rec["xp"].mean()) < 4 * se and abs(rec["yp"].mean()) < 4 * se
+    assert rec["xp"].std() == pytest.approx(sigma, rel=0.01) and rec["yp"].std() == pytest.approx(sigma, rel=0.01)
+    assert abs(np.corrcoef(rec["xp"], rec["yp"])[0, 1]) < 0.01
+    assert st["absorbed"] == npk and st["deposit_sum"] / npk == pytest.approx(1.0, rel=0.01)   # E[tau] = 1
+    # polar method: acceptance pi/4 per pair -> 2 * 2 * 4/pi source draws + phi + tau per packet
+    assert st["draws"] / npk == pytest.approx(2 + 16 / np.pi, rel=0.01)
+    col = o.jmean.sum(axis=2).sum(axis=1) / o.jmean.sum()           # marginal in x
+    from math import erf, sqrt
+    edges = np.array(pyref.make_faces(n, xmax)) - xmax
+    want = np.array([0.5 * (erf(b / (sigma * sqrt(2))) - erf(a / (sigma * sqrt(2)))) for a, b in zip(edges[:-1], edges[1:])])
+    assert np.abs(col - want).max() < 5 * np.sqrt(want.max() / npk)
+
+
+def test_gaussian_truncation_keeps_packets_on_the_face():
+    n, xmax = 16, 0.01
+    o = orc.Oracle(n, n, n, xmax, xmax, 0.02)
+    o.gridset_uniform(300.0)
+    o.set_source_gaussian(3 * xmax)                                  # most variates miss the face and are redrawn
+    o.seed_ran2(3)
+    out = o.run(20000, records=True)
+    rec = out["records"]
+    assert np.all(np.abs(rec["xp"]) < xmax) and np.all(np.abs(rec["yp"]) < xmax)
+    assert rec["xcell"].min() >= 1 and rec["xcell"].max() <= n and rec["ycell"].min() >= 1 and rec["ycell"].max() <= n
+    assert out["stats"]["draws"] / 20000 > 2 + 16 / np.pi + 4          # the redraws show up in the draw count
+
+
+def test_periodic_equals_infinite_slab():
+    """With periodic lateral boundaries a laterally uniform slab is the infinite slab: nothing leaves sideways, the
+    depth profile of the tally does not depend on the lateral size of the grid, and energy is conserved."""
+    prof = []
+    for nxy, xmax in ((6, 0.006), (24, 0.024)):
+        o = orc.Oracle(nxy, nxy, 30, xmax, xmax, 0.03)
+        o.gridset_uniform(150.0)
+        o.set_optics(0.9, 0.7)
+        o.set_spot(0.004)
+        o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+        o.seed_ran2(5)
+        st = o.run(40000)["stats"]
+        assert st["exits"][:4] == [0, 0, 0, 0]
+        assert st["absorbed"] + st["exits"][4] + st["exits"][5] == 40000
+        prof.append((o.jmean.sum(axis=(0, 1)) / 40000, st["exits"][4] / 40000, st["exits"][5] / 40000, st["wraps"]))
+    (p0, t0, r0, w0), (p1, t1, r1, w1) = prof
+    assert w0 > 4 * w1 > 0                                          # the narrow grid wraps far more often
+    # same physics, different random paths: agree within Monte-Carlo error
+    assert np.abs(p0 - p1).max() < 6 * np.sqrt(p0.max() / 40000)
+    assert abs(t0 - t1) < 6 * np.sqrt(max(t0, 1e-4) / 40000) and abs(r0 - r1) < 6 * np.sqrt(max(r0, 1e-4) / 40000)
+
+
+def test_periodic_off_is_bit_identical_to_before():
+    """The flag changes nothing for packets that never reach a lateral face (the shipped stub regime)."""
+    out = []
+    for flags in (0, orc.FLAG_PERIODIC):
+        o = orc.Oracle(80, 80, 80, 0.03, 0.03, 0.06)
+        o.gridset_uniform(o.init_opt1())
+        o.set_flags(flags)
+        o.seed_ran2(0)
+        r = o.run(2000, records=True)
+        out.append((r["records"].copy(), o.jmean.copy(), r["stats"]))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[1][2]["wraps"] == 0
+
+
+def test_philox_mode_source_stream_is_separate():
+    """Philox: the polar method draws from its own stream (counter word 3 = 2); phi and tau stay words 2 and 3 of the
+    packet's block 0, so ndraws stays 4 per launch and the packet's later events are unchanged by the source."""
+    o = orc.Oracle(20, 20, 20, 0.03, 0.03, 0.06)
+    o.gridset_uniform(680.0)
+    o.seed_philox(77, 5)
+    a = o.run(50, records=True)["records"].copy()
+    o.zero_jmean()
+    o.set_source_gaussian(0.01)
+    o.seed_philox(77, 5)
+    b = o.run(50, records=True)["records"].copy()
+    assert np.all(a["ndraws"] == 4) and np.all(b["ndraws"] == 4)
+    assert np.array_equal(a["deposit"] > 0, b["deposit"] > 0)
+    # same tau (word 3 of block 0) -> same total deposit per packet in the uniform stub regime
+    assert np.allclose(a["deposit"], b["deposit"], rtol=1e-12)
+    assert not np.allclose(a["xp"], b["xp"])
