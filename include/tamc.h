@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TAMC_VERSION 102
+#define TAMC_VERSION 103
 
 enum {
     TAMC_OK = 0,
@@ -42,10 +42,16 @@ enum {
 enum {
     TAMC_SCATTER = 1,    /* run the albedo test + stokes() loop the driver's shell implies
                             (mcpolar.f90:165-169, stokes.f90:6-153) instead of the shipped stub */
-    TAMC_FRESNEL = 2     /* EXTENSION, no upstream semantics (the reference reads n1, n2 and never uses them,
+    TAMC_FRESNEL = 2,    /* EXTENSION, no upstream semantics (the reference reads n1, n2 and never uses them,
                             mcpolar.f90:84-85, inttau2.f90:125): specular reflection at launch with probability
                             ((n1-n2)/(n1+n2))^2, and unpolarised Fresnel reflection / escape (n2 inside, n1 outside,
                             total internal reflection past the critical angle) at the six outer faces of the grid */
+    TAMC_PERIODIC = 4    /* periodic lateral boundaries: repeat_bounds (inttau2.f90:242-279) applied where tauint1 finds
+                            xcell or ycell == -1 after a wall crossing (inttau2.f90:57-61) -- the packet re-enters at
+                            `delta` / `2*max - delta` on the opposite side and the optical-depth integration goes on;
+                            only the top and bottom faces end a flight.  Upstream defines the routine and never calls
+                            it, so the call site is this library's.  No effect in the shipped stub
+                            regime, whose packets fly straight down.  Replayable (it draws nothing). */
 };
 
 typedef struct tamc_context *tamc_handle;
@@ -91,6 +97,16 @@ int tamc_finalize(tamc_handle h);
 
 /* sourceph.f90:23 spotSize (cm).  Default 250d-4. */
 int tamc_set_source_co2(tamc_handle h, double spot_diameter_cm);
+
+/* Gaussian beam in place of the CO2 disk: xp = rang(0., sigma), yp = rang(0., sigma) with sourceph.f90:73-101's
+ * Marsaglia polar method over ranu (:52-70), each variate redrawn while it misses the top face (|xp| >= xmax);
+ * everything else as sourcephCO2 (sourceph.f90:32-47).  Upstream defines rang and never calls it, so this launch is
+ * the library's own, checked against the oracle's sourcephGauss.  Production runs take rang's
+ * draws from a Philox stream of their own (counter word 3 = 2); trace replay consumes them from the packet's draw
+ * list in the reference's order (rang's pairs for x, for y, then phi, then tau).  sigma_cm must be positive;
+ * tamc_set_source_co2 switches back to the disk.  The column / tile forms and the beam-box copies of the shipped
+ * regime need the disk's bounded footprint and are not used with this source. */
+int tamc_set_source_gaussian(tamc_handle h, double sigma_cm);
 
 /* Uploads iarray::rhokap exactly as Fortran holds it -- (0:nxg+1,0:nyg+1,0:nzg+1), column-major,
  * halo included, i.e. pass rhokap(0,0,0) -- plus opt_prop's scalars.  Called once after gridset

@@ -19,6 +19,8 @@ def make_oracle(cfg, rhokap=None):
     o.set_indices(cfg.get("n1", 1.0), cfg.get("n2", 1.0))
     if "spot" in cfg:
         o.set_spot(cfg["spot"])
+    if cfg.get("gauss_sigma", 0.0) > 0.0:
+        o.set_source_gaussian(cfg["gauss_sigma"])
     return o
 
 
@@ -29,6 +31,8 @@ def make_transport(cfg, rhokap=None, device=0):
     t = tamc.MCTransport(n, n, n, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=device)
     if "spot" in cfg:
         t.set_source_co2(cfg["spot"])
+    if cfg.get("gauss_sigma", 0.0) > 0.0:
+        t.set_source_gaussian(cfg["gauss_sigma"])
     t.set_optics(rhokap if rhokap is not None else cfg["rhokap"](), cfg["albedo"], cfg["hgg"], n1=cfg.get("n1", 1.0),
                  n2=cfg.get("n2", 1.0), flags=cfg["flags"])
     return t

@@ -111,6 +111,7 @@ static DevGrid make_grid(const tamc_context *c)
     g.flags = c->flags;
     g.n1 = c->n1; g.n2 = c->n2;
     g.r0sq = ((c->n1 - c->n2) / (c->n1 + c->n2)) * ((c->n1 - c->n2) / (c->n1 + c->n2));
+    g.gauss_sigma = c->gauss_sigma;
     g.sc.one_m_g2 = 1. - g.g2;                                         // stokes.f90:48
     g.sc.one_p_g2 = 1. + g.g2;
     g.sc.one_m_g = 1. - g.hgg;
@@ -237,6 +238,18 @@ extern "C" int tamc_set_source_co2(tamc_handle h, double spot_diameter_cm)
     if (spot_diameter_cm / 2. >= h->xmax || spot_diameter_cm / 2. >= h->ymax)
         return fail(TAMC_EINVAL, "tamc_set_source_co2: spot does not fit on the top face");
     h->spot = spot_diameter_cm;
+    h->gauss_sigma = 0.;
+    return TAMC_OK;
+}
+
+extern "C" int tamc_set_source_gaussian(tamc_handle h, double sigma_cm)
+{
+    if (int rc = check(h)) return rc;
+    if (!(sigma_cm > 0.) || !(sigma_cm < 1e300)) return fail(TAMC_EINVAL, "tamc_set_source_gaussian: sigma must be positive and finite");
+    // each variate is redrawn while it misses the top face: keep the acceptance sane (sigma = 20 half-widths accepts ~4 %)
+    if (sigma_cm > 20. * h->xmax || sigma_cm > 20. * h->ymax)
+        return fail(TAMC_EINVAL, "tamc_set_source_gaussian: sigma beyond 20 half-widths of the top face");
+    h->gauss_sigma = sigma_cm;
     return TAMC_OK;
 }
 
@@ -245,7 +258,7 @@ static int check_optics(tamc_handle h, const double *rhokap, double albedo, doub
     const std::string w(who);
     if (!(albedo >= 0. && albedo <= 1.)) return fail(TAMC_EINVAL, w + ": albedo must be in [0,1]");
     if (!(hgg > -1. && hgg < 1.)) return fail(TAMC_EINVAL, w + ": hgg must be in (-1,1)");
-    if (flags & ~(TAMC_SCATTER | TAMC_FRESNEL)) return fail(TAMC_EINVAL, w + ": unknown flag bits");
+    if (flags & ~(TAMC_SCATTER | TAMC_FRESNEL | TAMC_PERIODIC)) return fail(TAMC_EINVAL, w + ": unknown flag bits");
     if ((flags & TAMC_FRESNEL) && !(n1 > 0. && n2 > 0.)) return fail(TAMC_EINVAL, w + ": TAMC_FRESNEL needs positive n1, n2");
     if (!rhokap && !h->optics_set) return fail(TAMC_ESTATE, w + ": first call needs the rhokap grid");
     return TAMC_OK;

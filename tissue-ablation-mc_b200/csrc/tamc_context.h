@@ -19,6 +19,7 @@ struct tamc_context {
     int nxg = 0, nyg = 0, nzg = 0;
     double xmax = 0, ymax = 0, zmax = 0, delta = 0;
     double spot = 250e-4;               // sourceph.f90:23
+    double gauss_sigma = 0.;            // > 0: Gaussian beam (tamc_set_source_gaussian) instead of the CO2 disk
     double albedo = 0, hgg = 0.9, n1 = 1, n2 = 1;
     int flags = 0;
     bool optics_set = false;

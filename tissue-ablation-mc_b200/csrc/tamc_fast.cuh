@@ -117,6 +117,50 @@ __device__ __forceinline__ Launched launch_fast(const DevGrid &g, const uint4 w,
     return L;
 }
 
+// Gaussian beam (tamc_set_source_gaussian; oracle: sourcephGauss): rang()'s polar method on the source stream
+// (counter word 3 = 2), each variate redrawn while it misses the top face; phi and tau are words 2 and 3 of the
+// packet's block 0 `w`, exactly where the disk source takes them.  Not a hot path: plain fp64 log / sqrt.
+__device__ __forceinline__ double rang_fast(const DevGrid &g, uint32_t id_lo, uint32_t id_hi, int &ns, double sigma)
+{
+    const uint2 key = make_uint2(g.rk[0], g.rk[1]);
+    double u, s;
+    do {
+        u = -1. + source_draw(key, id_lo, id_hi, ns) * 2.;
+        s = -1. + source_draw(key, id_lo, id_hi, ns) * 2.;
+        s = s * s + u * u;
+    } while (s >= 1.);
+    return sigma * (u * sqrt(-2. * log(s) / s));
+}
+
+__device__ __forceinline__ Launched launch_fast_gauss(const DevGrid &g, uint32_t id_lo, uint32_t id_hi, const uint4 w, bool need_azimuth)
+{
+    Launched L;
+    int ns = 0;
+    double xp, yp;
+    do { xp = rang_fast(g, id_lo, id_hi, ns, g.gauss_sigma); } while (!(fabs(xp) < g.xmax));
+    do { yp = rang_fast(g, id_lo, id_hi, ns, g.gauss_sigma); } while (!(fabs(yp) < g.ymax));
+    L.xcur = xp + g.xmax;
+    L.ycur = yp + g.ymax;
+    const int celli = min(g.nxg, (int)(L.xcur * g.inv_dx) + 1);
+    const int cellj = min(g.nyg, (int)(L.ycur * g.inv_dy) + 1);
+    L.cells = celli | (cellj << 16);
+    L.ridx = celli + g.sx * (cellj + (g.nyg + 2) * g.cellk0);
+    L.jidx = (celli - 1) + g.nxg * ((cellj - 1) + g.nyg * (g.cellk0 - 1));
+    L.cosp = 1.;
+    L.sinp = 0.;
+    if (need_azimuth) fm::sincospi_0_2(kTWOPI * unit_fast(w.z) * kInvPi, &L.sinp, &L.cosp);
+    L.tau = fm::neglog_u32(w.w);
+    return L;
+}
+
+// Launch of packet (id_lo, id_hi) from whichever source the handle has; consumes block 0 of the packet's main stream.
+__device__ __forceinline__ Launched launch_any(const DevGrid &g, uint32_t id_lo, uint32_t id_hi, bool need_azimuth)
+{
+    const uint4 w = philox_block(g, id_lo, id_hi, 0u);
+    if (g.gauss_sigma > 0.) return launch_fast_gauss(g, id_lo, id_hi, w, need_azimuth);
+    return launch_fast(g, w, need_azimuth);
+}
+
 __device__ __forceinline__ void adopt(const DevGrid &g, const LaunchConsts &lc, FastPhoton &p, const Launched &L)
 {
     p.xcur = L.xcur; p.ycur = L.ycur; p.zcur = lc.zcur0;
@@ -286,6 +330,37 @@ __device__ __forceinline__ bool fresnel_reflect_fast(const DevGrid &g, const dou
         p.nzp = -p.nzp; p.inz = -p.inz; p.dflags ^= 4;
     }
     return true;
+}
+
+// TAMC_PERIODIC on the production arithmetic: repeat_bounds (inttau2.f90:242-279).  After STEP_EXIT exactly one
+// index is out of range; a lateral one re-enters on the opposite side at `delta` / `2*max - delta`.
+__device__ __forceinline__ bool periodic_wrap_fast(const DevGrid &g, FastPhoton &p)
+{
+    if ((unsigned)(p.celli - 1) >= (unsigned)g.nxg) {
+        const bool low = p.celli < 1;                     // left through -x: acur < delta
+        p.xcur = low ? 2. * g.xmax - g.delta : g.delta;
+        const int d = low ? g.nxg : -g.nxg;
+        p.celli += d; p.ridx += d; p.jidx += d;
+        return true;
+    }
+    if ((unsigned)(p.cellj - 1) >= (unsigned)g.nyg) {
+        const bool low = p.cellj < 1;
+        p.ycur = low ? 2. * g.ymax - g.delta : g.delta;
+        const int d = low ? g.nyg : -g.nyg;
+        p.cellj += d; p.ridx += d * g.sx; p.jidx += d * g.nxg;
+        return true;
+    }
+    return false;
+}
+
+// What happens to a packet that a wall crossing took out of the grid, when boundary options are on:
+// 0 = it leaves, 1 = Fresnel-reflected back in, 2 = re-entered through the opposite lateral face.
+__device__ __forceinline__ int boundary_fast(const DevGrid &g, const double *xf, const double *yf, const double *zf,
+                                             FastPhoton &p, uint2 key, uint32_t id_lo, uint32_t id_hi, int &nb)
+{
+    if ((g.flags & TAMC_PERIODIC) && periodic_wrap_fast(g, p)) return 2;
+    if ((g.flags & TAMC_FRESNEL) && fresnel_reflect_fast(g, xf, yf, zf, p, key, id_lo, id_hi, nb)) return 1;
+    return 0;
 }
 
 __device__ __forceinline__ int exit_face_fast(const FastPhoton &p, const DevGrid &g)

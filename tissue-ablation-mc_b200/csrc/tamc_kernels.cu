@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
     stage_faces(g, s_faces, xf, yf, zf);
     const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
     const bool fresnel = (g.flags & TAMC_FRESNEL) != 0;
+    const bool bounds = (g.flags & (TAMC_FRESNEL | TAMC_PERIODIC)) != 0;
     const LaunchConsts lc{g.zcur0, g.cellk0};
 
     Counters c;
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
         PhiloxRng rng;
         rng.seed(seed, first_id + (uint64_t)i);
         FastPhoton p;
-        adopt(g, lc, p, launch_fast(g, philox_block(g, rng), scatter_on));
+        adopt(g, lc, p, launch_any(g, rng.id_lo, rng.id_hi, scatter_on));
+        rng.blk = 1;                                              // block 0 went into the launch
         tally.begin();
         int steps = 0, nscatt = 0, fate = 0, ndraws = 4, nb = 0;
         bool specular = false;
@@ -68,17 +70,18 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
             c.note(CNT_SPECULAR);
         }
         while (!specular) {
-            const int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
+            int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
             ++steps;
+            if (bounds && r == STEP_EXIT) {
+                const int b = boundary_fast(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb);
+                if (b == 1) c.note(CNT_REFLECT);
+                if (b) r = STEP_WALL;                             // reflected or re-entered: the flight goes on
+            }
             if (r == STEP_WALL) {
                 if (steps >= kMaxStepsPerPacket) { c.errors++; break; }
                 continue;
             }
             if (r == STEP_EXIT) {
-                if (fresnel && fresnel_reflect_fast(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb)) {
-                    c.note(CNT_REFLECT);
-                    continue;
-                }
                 fate = exit_face_fast(p, g);
                 break;
             }
@@ -453,6 +456,7 @@ static cudaError_t launch_sized(K kernel, const LaunchCfg &cfg, size_t smem, lon
 // both the product and the truncation are monotonic, so the box below contains every launch voxel.
 bool beam_box(const DevGrid &g, ColGeom &cg)
 {
+    if (g.gauss_sigma > 0.) return false;          // Gaussian beam: launch points anywhere on the top face
     const double R = sqrt(g.spot_r2);
     cg.i0 = max(1, (int)((g.xmax - R) * g.inv_dx) + 1);
     cg.j0 = max(1, (int)((g.ymax - R) * g.inv_dy) + 1);
@@ -630,7 +634,12 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     if (launches) *launches += 1;
     tamc_packet_record *none = nullptr;
 
-    if (form) *form = cfg.variant == 2 ? FORM_EXACT : ((d_rec || cfg.variant == 0 || ((g.flags & TAMC_FRESNEL) && !(g.flags & TAMC_SCATTER))) ? FORM_SIMPLE : (pool ? FORM_POOL : FORM_PERSISTENT));
+    // Options outside the shipped path (Fresnel boundaries, periodic lateral boundaries, Gaussian beam) are compiled into
+    // the thread-per-packet kernels and the `ext` build of the pool kernel only; the stub-regime and persistent kernels
+    // stay as they are.  Periodic boundaries alone change nothing in the stub regime (straight-down flights).
+    const bool scat = (g.flags & TAMC_SCATTER) != 0, gauss = g.gauss_sigma > 0.;
+    const bool simple_ext = scat ? (!pool && (gauss || (g.flags & TAMC_PERIODIC))) : (gauss || (g.flags & TAMC_FRESNEL));
+    if (form) *form = cfg.variant == 2 ? FORM_EXACT : ((d_rec || cfg.variant == 0 || simple_ext) ? FORM_SIMPLE : (pool ? FORM_POOL : FORM_PERSISTENT));
     if (cfg.variant == 2) {
         if (d_rec) {
             if (merge) return launch_sized(k_transport_exact<MergeTally, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
@@ -643,8 +652,8 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
         if (merge) return launch_sized(k_transport_simple<MergeTally32, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
         return launch_sized(k_transport_simple<DirectTally32, true>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, d_rec);
     }
-    // Fresnel boundaries without the scatter loop: the stub kernels keep no packet id, use the thread-per-packet kernel
-    if (cfg.variant == 0 || ((g.flags & TAMC_FRESNEL) && !(g.flags & TAMC_SCATTER))) {
+    // e.g. Fresnel boundaries without the scatter loop: the stub kernels keep no packet id, use the thread-per-packet kernel
+    if (cfg.variant == 0 || simple_ext) {
         if (merge) return launch_sized(k_transport_simple<MergeTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
@@ -658,7 +667,7 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
         const bool beyond_l2 = 8. * ((double)g.sxy * (g.nzg + 2) + (double)g.nxg * g.nyg * g.nzg) > 2. * (double)l2;
-        const bool fres = (g.flags & TAMC_FRESNEL) != 0;
+        const bool fres = (g.flags & (TAMC_FRESNEL | TAMC_PERIODIC)) != 0 || gauss;      // the `ext` build
         if (auto_block ? !beyond_l2 : cfg.block <= 128) {       // auto: 128 threads, 5 CTAs per SM while the grids fit L2
             LaunchCfg c2 = cfg;
             c2.block = 128;

@@ -47,7 +47,8 @@ struct alignas(16) WarpPool {
     unsigned long long cnt[CNT_N];
 };
 
-// kFresnel compiles the boundary-optics extension in (TAMC_FRESNEL); the default build carries none of it.
+// kFresnel is the `ext` build: it compiles in everything outside the shipped path -- boundary optics (TAMC_FRESNEL),
+// periodic lateral boundaries (TAMC_PERIODIC), the Gaussian beam -- selected at run time; the default build carries none of it.
 template <int kBlock, int kMinCtas, bool kFresnel, bool kAhead = false>
 __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                                   int chunk, int scatter_min,
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 if (lane < k) {
                     const int s = P.fq[nf - 1 - lane];
                     const uint64_t gid = first_id + (uint64_t)(next + lane);
-                    const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), true);
+                    const Launched L = kFresnel ? launch_any(g, (uint32_t)gid, (uint32_t)(gid >> 32), true)
+                                                : launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), true);
                     PoolSlot &S = P.slot[s];
                     S.pos_xy = make_double2(L.xcur, L.ycur);
                     S.pz_pval = make_double2(lc.zcur0, 0.);
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 steps = g5.y;
                 if (kFresnel) nb = g4.w;
                 walking = true;
-                if (fresnel && nb == 0 && boundary_draw(key, S.id.x, S.id.y, nb) < g.r0sq) {
+                if (fresnel && (g.flags & TAMC_FRESNEL) && nb == 0 && boundary_draw(key, S.id.x, S.id.y, nb) < g.r0sq) {
                     walking = false;                      // fresh packet reflected at the top surface: never enters
                     doa = true;
                 }
@@ -222,9 +224,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
         } else if (walking) {
             int r = voxel_step_fast<true, decltype(tally), kAhead>(g, xf, yf, zf, p, tally);
             ++steps;
-            if (fresnel && r == STEP_EXIT && fresnel_reflect_fast(g, xf, yf, zf, p, key, P.slot[slot].id.x, P.slot[slot].id.y, nb)) {
-                atomicAdd(&P.cnt[CNT_REFLECT], 1ull);
-                r = STEP_WALL;
+            if (fresnel && r == STEP_EXIT) {
+                const int b = boundary_fast(g, xf, yf, zf, p, key, P.slot[slot].id.x, P.slot[slot].id.y, nb);
+                if (b == 1) atomicAdd(&P.cnt[CNT_REFLECT], 1ull);
+                if (b) r = STEP_WALL;                 // reflected or re-entered: the flight goes on
             }
             if (r == STEP_INTERACT) {
                 // the centred-position round trip of inttau2.f90:65-67 / :24-26

@@ -50,6 +50,7 @@ struct DevGrid {
     int cellk0;           // int(nzg*(zp0+zmax)/(2.*zmax))+1, sourceph.f90:47
     int flags;
     double n1, n2, r0sq;  // TAMC_FRESNEL: indices outside / inside the grid, ((n1-n2)/(n1+n2))**2
+    double gauss_sigma;   // > 0: Gaussian beam through rang() (sourceph.f90:73-101) instead of the CO2 disk
     ScatterConsts sc;
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
@@ -85,6 +86,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c)
 // (x + 0.5) * 2^-32: exact in fp64, strictly inside (0,1) like ran2's output (ran2.f:31).
 __device__ __forceinline__ double u32_to_unit(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
+__device__ __forceinline__ double source_draw(uint2 key, uint32_t id_lo, uint32_t id_hi, int &ns);
+
 struct PhiloxRng {
     static constexpr bool kHasBoundary = true;
     uint2 key;
@@ -101,6 +104,17 @@ struct PhiloxRng {
         const uint4 r = philox4x32_10(key, make_uint4(id_lo, id_hi, blk++, 0u));
         u[0] = u32_to_unit(r.x); u[1] = u32_to_unit(r.y); u[2] = u32_to_unit(r.z); u[3] = u32_to_unit(r.w);
     }
+    // Gaussian source: rang()'s draws come from the source stream; phi and tau stay words 2 and 3 of block 0
+    static constexpr bool kSequential = false;
+    __device__ __forceinline__ double src(int &ns) { return source_draw(key, id_lo, id_hi, ns); }
+    __device__ __forceinline__ bool exhausted() const { return false; }
+    __device__ __forceinline__ void launch_tail(double &uphi, double &utau)
+    {
+        double u[4];
+        block(u);
+        uphi = u[2];
+        utau = u[3];
+    }
 };
 
 // Boundary decisions (TAMC_FRESNEL) draw from a stream of their own: counter word 3 = 1, draw nb of the packet.
@@ -109,6 +123,16 @@ __device__ __forceinline__ double boundary_draw(uint2 key, uint32_t id_lo, uint3
     const uint4 r = philox4x32_10(key, make_uint4(id_lo, id_hi, (uint32_t)(nb >> 2), 1u));
     const int l = nb & 3;
     ++nb;
+    return u32_to_unit(l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w)));
+}
+
+// The Gaussian source (tamc_set_source_gaussian) draws from a stream of its own as well: counter word 3 = 2.  The polar
+// method consumes a variable number of draws; the packet's main stream keeps its layout of one block per event.
+__device__ __forceinline__ double source_draw(uint2 key, uint32_t id_lo, uint32_t id_hi, int &ns)
+{
+    const uint4 r = philox4x32_10(key, make_uint4(id_lo, id_hi, (uint32_t)(ns >> 2), 2u));
+    const int l = ns & 3;
+    ++ns;
     return u32_to_unit(l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w)));
 }
 
@@ -135,6 +159,22 @@ struct ReplayRng {
 #pragma unroll
         for (int i = 0; i < 4; ++i) u[i] = (pos + i < end) ? p[pos + i] : 0.5;
         pos += 4;
+    }
+    // Gaussian source: the reference's single sequential stream -- rang()'s draws, then phi, then tau
+    static constexpr bool kSequential = true;
+    __device__ __forceinline__ double src(int &ns)
+    {
+        ++ns;
+        const double v = (pos < end) ? p[pos] : 0.75;
+        ++pos;
+        return v;
+    }
+    __device__ __forceinline__ bool exhausted() const { return pos >= end; }
+    __device__ __forceinline__ void launch_tail(double &uphi, double &utau)
+    {
+        int n = 0;
+        uphi = src(n);
+        utau = src(n);
     }
 };
 
@@ -233,6 +273,68 @@ __device__ __forceinline__ void launch(const DevGrid &g, Photon &p, const double
     p.zcur = zp + g.zmax;
     p.taurun = 0.;
     p.tau = -log(u[3]);
+}
+
+// sourceph.f90:52-70 ranu + :73-101 rang (Marsaglia polar method; the pair's first variate is used), statement for
+// statement.  A replayed packet whose draw list runs out leaves the loop (the record is flagged by the caller).
+template <class Rng>
+__device__ __forceinline__ double rang(Rng &rng, int &ns, double avg, double sigma)
+{
+    double u = 0., s = 1.;
+    while (s >= 1. && !rng.exhausted()) {
+        u = -1. + rng.src(ns) * (1. - -1.);
+        s = -1. + rng.src(ns) * (1. - -1.);
+        s = s * s + u * u;
+    }
+    const double tmp = u * sqrt(-2. * log(s) / s);
+    return avg + sigma * tmp;
+}
+
+// Builder-defined launch on top of rang() (the reference defines rang and never calls it; oracle: sourcephGauss):
+// xp, yp ~ N(0, sigma), each redrawn while it misses the top face; the rest is sourceph.f90:32-47.  Returns the number
+// of draws the launch consumed from the packet's main stream (replay: all of them; Philox: block 0 = 4).
+template <class Rng>
+__device__ __forceinline__ int launch_gauss(const DevGrid &g, Photon &p, Rng &rng)
+{
+    int ns = 0;
+    double xp, yp;
+    do { xp = rang(rng, ns, 0., g.gauss_sigma); } while (!(fabs(xp) < g.xmax) && !rng.exhausted());
+    do { yp = rang(rng, ns, 0., g.gauss_sigma); } while (!(fabs(yp) < g.ymax) && !rng.exhausted());
+    if (!(fabs(xp) < g.xmax)) xp = 0.;          // only a replayed packet that ran out of draws
+    if (!(fabs(yp) < g.ymax)) yp = 0.;
+    const double zp = g.zp0;
+    double uphi, utau;
+    rng.launch_tail(uphi, utau);
+    p.phi = kTWOPI * uphi;
+    p.sint = 0.;
+    p.cost = -1.;
+    p.nxp = 0.;
+    p.nyp = 0.;
+    p.nzp = -1.;
+    p.celli = min(g.nxg, (int)((double)g.nxg * (xp + g.xmax) / (2. * g.xmax)) + 1);
+    p.cellj = min(g.nyg, (int)((double)g.nyg * (yp + g.ymax) / (2. * g.ymax)) + 1);
+    p.cellk = (int)((double)g.nzg * (zp + g.zmax) / (2. * g.zmax)) + 1;
+    p.xcur = xp + g.xmax;
+    p.ycur = yp + g.ymax;
+    p.zcur = zp + g.zmax;
+    p.taurun = 0.;
+    p.tau = -log(utau);
+    return Rng::kSequential ? ns + 2 : 4;
+}
+
+// inttau2.f90:242-279 repeat_bounds on the exact arithmetic (TAMC_PERIODIC): a packet that left through a lateral
+// face re-enters on the opposite side.  Where the Fortran would print 'Error in Repeat_bounds...' the index stays -1.
+__device__ __forceinline__ void repeat_bounds(int &cella, int &cellb, double &acur, double &bcur, double amax, double bmax,
+                                              int nag, int nbg, double delta)
+{
+    if (cella == -1) {
+        if (acur < delta) { acur = 2. * amax - delta; cella = nag; }
+        else if (acur > 2. * amax - delta) { acur = delta; cella = 1; }
+    }
+    if (cellb == -1) {
+        if (bcur < delta) { bcur = 2. * bmax - delta; cellb = nbg; }
+        else if (bcur > 2. * bmax - delta) { bcur = delta; cellb = 1; }
+    }
 }
 
 // tauint1 returns the centred position and the next call shifts it again (inttau2.f90:65-67 then
@@ -454,10 +556,14 @@ __device__ __forceinline__ void transport_packet(const DevGrid &g, const double 
 {
     double u[4];
     Photon p;
-    rng.block(u);
-    launch(g, p, u);
-    tally.begin();
     int ndraws = 4, steps = 0, nscatt = 0, fate = 0;
+    if (g.gauss_sigma > 0.) {
+        ndraws = launch_gauss(g, p, rng);
+    } else {
+        rng.block(u);
+        launch(g, p, u);
+    }
+    tally.begin();
     int nb = 0;
     bool specular = false;
     if constexpr (Rng::kHasBoundary) {
@@ -471,19 +577,24 @@ __device__ __forceinline__ void transport_packet(const DevGrid &g, const double 
         }
     }
     while (!specular) {
-        const int r = voxel_step(g, xf, yf, zf, p, tally);
+        int r = voxel_step(g, xf, yf, zf, p, tally);
         ++steps;
+        if (r == STEP_EXIT && (g.flags & TAMC_PERIODIC) && (p.celli == -1 || p.cellj == -1)) {
+            repeat_bounds(p.celli, p.cellj, p.xcur, p.ycur, g.xmax, g.ymax, g.nxg, g.nyg, g.delta);
+            if (p.celli != -1 && p.cellj != -1 && p.cellk != -1) r = STEP_WALL;      // re-entered: the flight goes on
+        }
+        if constexpr (Rng::kHasBoundary) {
+            if (r == STEP_EXIT && (g.flags & TAMC_FRESNEL) &&
+                fresnel_reflect_exact(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb)) {
+                cnt.reflections++;
+                r = STEP_WALL;
+            }
+        }
         if (r == STEP_WALL) {
             if (steps >= kMaxStepsPerPacket) { cnt.errors++; break; }
             continue;
         }
         if (r == STEP_EXIT) {
-            if constexpr (Rng::kHasBoundary) {
-                if ((g.flags & TAMC_FRESNEL) && fresnel_reflect_exact(g, xf, yf, zf, p, rng.key, rng.id_lo, rng.id_hi, nb)) {
-                    cnt.reflections++;
-                    continue;
-                }
-            }
             fate = exit_face(p);
             break;
         }

@@ -14,7 +14,7 @@ module tamc_mod
     implicit none
 
     integer(c_int), parameter :: TAMC_OK = 0
-    integer(c_int), parameter :: TAMC_SCATTER = 1, TAMC_FRESNEL = 2
+    integer(c_int), parameter :: TAMC_SCATTER = 1, TAMC_FRESNEL = 2, TAMC_PERIODIC = 4
 
     !  mirrors tamc_stats (include/tamc.h)
     type, bind(C) :: tamc_stats
@@ -53,6 +53,13 @@ module tamc_mod
             type(c_ptr), value    :: handle
             real(c_double), value :: spot_diameter_cm
         end function tamc_set_source_co2
+
+        !  Gaussian beam through rang (sourceph.f90:73-101) instead of the CO2 disk
+        integer(c_int) function tamc_set_source_gaussian(handle, sigma_cm) bind(C, name="tamc_set_source_gaussian")
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value    :: handle
+            real(c_double), value :: sigma_cm
+        end function tamc_set_source_gaussian
 
         !  rhokap is passed as the whole allocatable rhokap(0:nxg+1,0:nyg+1,0:nzg+1): contiguous, so the
         !  compiler hands over the address of rhokap(0,0,0) without a temporary.

@@ -6,7 +6,7 @@ include/tamc.h into hand-written CUDA (csrc/).  There is no CPU path here -- if 
 been built, importing succeeds but the first use raises, loudly.
 """
 from .binding import (  # noqa: F401
-    MCTransport, Stats, TamcError, RECORD_DTYPE, SCATTER, FRESNEL, device_count, lib, lib_path, comm_unique_id,
+    MCTransport, Stats, TamcError, RECORD_DTYPE, SCATTER, FRESNEL, PERIODIC, device_count, lib, lib_path, comm_unique_id,
     pin_host, unpin_host,
 )
 from .mcgrid import gridset, init_opt1, delta_for  # noqa: F401

@@ -8,6 +8,7 @@ import numpy as np
 
 SCATTER = 1
 FRESNEL = 2
+PERIODIC = 4
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -84,6 +85,7 @@ def lib() -> C.CDLL:
         "tamc_init": (i, [i, i, i, i, d, d, d, d, C.POINTER(p)]),
         "tamc_finalize": (i, [p]),
         "tamc_set_source_co2": (i, [p, d]),
+        "tamc_set_source_gaussian": (i, [p, d]),
         "tamc_set_optics": (i, [p, p, d, d, d, d, i]),
         "tamc_run": (i, [p, i64, i64, p, C.POINTER(Stats)]),
         "tamc_run_optics": (i, [p, p, d, d, d, d, i, i64, i64, p, C.POINTER(Stats)]),
@@ -123,7 +125,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = [
-    "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_optics", "tamc_run", "tamc_run_optics", "tamc_run_async",
+    "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_source_gaussian", "tamc_set_optics", "tamc_run", "tamc_run_optics", "tamc_run_async",
     "tamc_sync", "tamc_get_jmean", "tamc_get_stats", "tamc_seek", "tamc_run_replay", "tamc_run_records",
     "tamc_comm_unique_id", "tamc_comm_init", "tamc_stream", "tamc_jmean_device", "tamc_rhokap_device",
     "tamc_pin_host", "tamc_unpin_host", "tamc_set_option", "tamc_get_option", "tamc_roofline_probe",
@@ -201,6 +203,10 @@ class MCTransport:
 
     def set_source_co2(self, spot_diameter_cm: float):
         _ck(self.L.tamc_set_source_co2(self.h, float(spot_diameter_cm)))
+
+    def set_source_gaussian(self, sigma_cm: float):
+        """Gaussian beam through rang() (sourceph.f90:73-101); set_source_co2 switches back to the disk."""
+        _ck(self.L.tamc_set_source_gaussian(self.h, float(sigma_cm)))
 
     def set_optics(self, rhokap, albedo, hgg, n1=1.0, n2=1.0, flags=0):
         """rhokap: (nxg+2, nyg+2, nzg+2) Fortran-ordered fp64 with halo, or None to keep the resident grid."""
