@@ -19,6 +19,7 @@
 // shipped parameters).
 //
 //   usage: mcgrid_shim [--params FILE] [--calls N] [--nxg N] [--scatter] [--resident] [--out DIR] [--device D]
+//                      [--gaussian SIGMA_CM] [--periodic]     (the rang / repeat_bounds options, default off)
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -147,7 +148,8 @@ int main(int argc, char **argv)
 {
     std::string params_path, out_dir;
     int calls = 200, nxg = 80, device = 0;
-    bool scatter = false, resident = false;
+    bool scatter = false, resident = false, periodic = false;
+    double gauss_sigma = 0.;
     for (int a = 1; a < argc; ++a) {
         const std::string s = argv[a];
         auto next = [&](const char *name) -> const char * {
@@ -161,6 +163,8 @@ int main(int argc, char **argv)
         else if (s == "--out") out_dir = next("--out");
         else if (s == "--scatter") scatter = true;
         else if (s == "--resident") resident = true;
+        else if (s == "--periodic") periodic = true;
+        else if (s == "--gaussian") gauss_sigma = std::atof(next("--gaussian"));
         else { std::fprintf(stderr, "unknown argument %s\n", s.c_str()); return 2; }
     }
     Params P;
@@ -178,13 +182,15 @@ int main(int argc, char **argv)
     tamc_handle h = nullptr;
     int rc = tamc_init(device, g.nxg, g.nyg, g.nzg, P.xmax, P.ymax, P.zmax, delta, &h);
     if (rc) die("tamc_init", rc);
+    if (gauss_sigma > 0. && (rc = tamc_set_source_gaussian(h, gauss_sigma))) die("tamc_set_source_gaussian", rc);
+    const int xflags = periodic ? TAMC_PERIODIC : 0;
     std::vector<double> jmeanGLOBAL((size_t)g.nxg * g.nyg * g.nzg, 0.);
     tamc_pin_host(g.rhokap.data(), g.rhokap.size() * sizeof(double));
     tamc_pin_host(jmeanGLOBAL.data(), jmeanGLOBAL.size() * sizeof(double));
 
     if (resident) {
         // the reference's loop with its real heat / ablation step, nothing crossing PCIe per iteration
-        rc = tamc_set_optics(h, g.rhokap.data(), o.albedo, o.hgg, P.n1, P.n2, 0);
+        rc = tamc_set_optics(h, g.rhokap.data(), o.albedo, o.hgg, P.n1, P.n2, xflags);
         if (rc) die("tamc_set_optics", rc);
         tamc_heat_params hp{};
         hp.power = P.power; hp.energyPerPixel = P.energyPerPixel; hp.total_time = P.total_time;
@@ -267,7 +273,7 @@ int main(int argc, char **argv)
         const auto t0 = std::chrono::steady_clock::now();
         tamc_stats st;
         // upload of the rewritten rhokap + mcpolar.f90:151-173, in one call so the copies overlap the transport
-        rc = tamc_run_optics(h, g.rhokap.data(), scatter ? 0.9 : o.albedo, o.hgg, P.n1, P.n2, scatter ? TAMC_SCATTER : 0,
+        rc = tamc_run_optics(h, g.rhokap.data(), scatter ? 0.9 : o.albedo, o.hgg, P.n1, P.n2, (scatter ? TAMC_SCATTER : 0) | xflags,
                              P.nphotons, 95648324, jmeanGLOBAL.data(), &st);
         if (rc) die("tamc_run_optics", rc);
         const auto t1 = std::chrono::steady_clock::now();
