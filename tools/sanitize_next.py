@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Driver for compute-sanitizer: the Gaussian beam and periodic lateral boundaries in every kernel that carries them
+(exact, thread-per-packet, pool `ext` build, replay) at small sizes.  No timing claims."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tissue-ablation-mc_b200")]
+import numpy as np  # noqa: E402
+
+import tamc  # noqa: E402
+from oracle import oracle as orc  # noqa: E402  (draw lists for the replay kernel only)
+
+n, npk = 20, int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+rk = tamc.gridset(0.02, 0.02, 0.2, n, n, n, 100.0)[3]
+for sigma in (0.0, 0.015):
+    for flags in (1 | 4, 1 | 2 | 4, 0):
+        t = tamc.MCTransport(n, n, n, 0.02, 0.02, 0.2)
+        t.set_source_co2(0.01)
+        if sigma > 0:
+            t.set_source_gaussian(sigma)
+        t.set_optics(rk, 0.95 if flags & 1 else 0.0, 0.8, n1=1.0, n2=1.38, flags=flags)
+        for variant in (0, 1, 2, 3):
+            t.set_option("variant", variant)
+            t.run_async(npk, 11, 0)
+            st = t.get_stats()
+            assert st["packets"] == npk and (not (flags & 4) or st["exits"][:4] == [0, 0, 0, 0])
+            print("sigma", sigma, "flags", flags, "variant", variant, "form", t.get_option("form"), "steps", st["voxel_steps"])
+        rec, _ = t.run_records(npk, 11, 0)
+        if not (flags & 2):
+            o = orc.Oracle(n, n, n, 0.02, 0.02, 0.2)
+            o.set_rhokap(rk); o.set_optics(0.95 if flags & 1 else 0.0, 0.8); o.set_spot(0.01); o.set_flags(flags)
+            if sigma > 0:
+                o.set_source_gaussian(sigma)
+            o.seed_ran2(1)
+            out = o.run(npk, records=True, draws_cap=npk * 3000)
+            rec, _ = t.run_replay(out["offsets"], out["draws"])
+            assert np.array_equal(rec["steps"], out["records"]["steps"])
+            print("  replay ok", int(rec["steps"].sum()))
+        t.close()
