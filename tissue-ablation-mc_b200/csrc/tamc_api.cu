@@ -461,8 +461,9 @@ extern "C" int tamc_seek(tamc_handle h, int64_t next_packet_id)
 // Without the scatter loop every flight is straight down (sourceph.f90:37-42, mcpolar.f90:166-169), so
 //   * the tally is zero outside the columns under the beam's bounding box -- jmeanGLOBAL is written as a zero fill
 //     (device zeros -> host, a DMA on its own stream WHILE the transport runs) followed by the box columns after the
-//     all-reduce (k_box_mirror stores them straight into the caller's array; long calls use one pitched 3-D DMA whose
-//     descriptors are submitted while the transport runs): the same bytes in host memory as the plain full-grid download;
+//     all-reduce (k_box_mirror stores them straight into the caller's array, skipping rows of the box that hold only
+//     zeros; long calls on grids whose deposits reach deep use one pitched 3-D DMA whose descriptors are submitted while
+//     the transport runs): the same bytes in host memory as the plain full-grid download;
 //   * the column form reads the opacities of those columns only -- in tamc_run_optics k_column_gather fetches them
 //     straight from the caller's array (each voxel once) and the DMA of the full grid, which later calls and the heat
 //     step read, follows on a second stream beside the transport.
@@ -555,8 +556,14 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
     if (box_dn) {
         CU(cudaStreamWaitEvent(h->stream, h->ev[EV_DN], 0));          // the zero fill lands first
         CU(cudaEventRecord(h->ev[EV_D0], h->stream));
-        if (nphotons >= ((int64_t)1 << 22)) {
-            // long call: one pitched 3-D DMA (52 GB/s; its per-slice descriptors are submitted while the transport runs)
+        // Long call on a grid whose deposits reach deep: one pitched 3-D DMA (52 GB/s; its per-slice descriptors are
+        // submitted while the transport runs).  Otherwise posted writes from a kernel (41 GB/s, nothing to submit per
+        // slice) that skips the all-zero rows of the box -- the zero fill above already covers them; in the shipped regime
+        // the tally dies out e-fold per mean free path, so most planes of the box hold nothing (homog200, 1e8 packets:
+        // ~40 of 200 planes).  "Deep" is judged from the previous stub-regime call's voxel-steps per packet.
+        const bool shallow = h->cfg.steps_hint > 0. && 16. * h->cfg.steps_hint < (double)h->nzg;
+        const bool dma = nphotons >= ((int64_t)1 << 22) && !shallow;
+        if (dma) {
             cudaMemcpy3DParms p{};
             p.srcPtr = make_cudaPitchedPtr(h->d_jmean, (size_t)h->nxg * sizeof(double), (size_t)h->nxg, (size_t)h->nyg);
             p.srcPos = make_cudaPos((size_t)(cg.i0 - 1) * sizeof(double), (size_t)(cg.j0 - 1), 0);
@@ -565,13 +572,13 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
             p.extent = make_cudaExtent((size_t)cg.tw * sizeof(double), (size_t)cg.th, (size_t)h->nzg);
             p.kind = cudaMemcpyDeviceToHost;
             CU(cudaMemcpy3DAsync(&p, h->stream));
-        } else      // short call: posted writes from a kernel (41 GB/s, nothing to submit per slice)
+        } else
             CU(launch_box_mirror(g, cg, jm_dev, h->num_sms, h->stream));
         CU(cudaEventRecord(h->ev[EV_D1], h->stream));
         if (box_up) CU(cudaStreamWaitEvent(h->stream, h->ev[EV_UP], 0));
         CU(cudaStreamSynchronize(h->stream));
         h->timed_d2h = true;
-        if (nphotons < ((int64_t)1 << 22)) h->last_launches += 1;
+        if (!dma) h->last_launches += 1;
     } else {
         if (int rc = tamc_get_jmean(h, jmean_global)) return rc;
     }

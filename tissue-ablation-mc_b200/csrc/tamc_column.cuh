@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(256) k_box_copy(const DevGrid g, const ColGeom
 
 // The tally under the beam's bounding box -> the same voxels of `dst`, an array in the tally's own layout: the caller's
 // page-locked jmeanGLOBAL, written over PCIe (posted writes, 256-byte row segments).  The rest of jmeanGLOBAL is zero
-// fill that travelled while the transport ran (tamc_api.cu).
+// fill that travelled while the transport ran (tamc_api.cu) -- and that fill covers the box as well, so a row of the
+// box that holds only zeros (every plane below the deepest deposit: most of the box in the shipped regime) is not sent.
 __global__ void __launch_bounds__(256) k_box_mirror(const DevGrid g, const ColGeom cg, double *__restrict__ dst)
 {
     const int rows = cg.th * g.nzg;
@@ -509,6 +510,9 @@ __global__ void __launch_bounds__(256) k_box_mirror(const DevGrid g, const ColGe
     for (int r = warp; r < rows; r += nwarps) {
         const int dj = r % cg.th, kz = r / cg.th;
         const size_t row = (size_t)(cg.i0 - 1) + (size_t)g.nxg * ((size_t)(cg.j0 - 1 + dj) + (size_t)g.nyg * kz);
+        bool any = false;
+        for (int di = lane; di < cg.tw; di += 32) any |= (g.jmean[row + di] != 0.);
+        if (!__any_sync(0xffffffffu, any)) continue;
         for (int di = lane; di < cg.tw; di += 32) dst[row + di] = g.jmean[row + di];
     }
 }
