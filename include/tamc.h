@@ -133,8 +133,12 @@ int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global
  * transport when they are page-locked (tamc_pin_host) and the scatter loop is off: the tally is zero
  * outside the columns under the beam, so jmean_global is written as a zero fill that runs beside the
  * kernels plus a pitched copy of those columns, and the opacities of those columns are uploaded ahead
- * of the full grid, which follows on a second stream.  Options "box_io" (-1 auto, 0 = plain copies in
- * sequence) and read-only "io_form" (bit0: columns-only download, bit1: columns-first upload).
+ * of the full grid, which follows on a second stream.  From the second such call on, the columns go up only down to the
+ * depth the previous call's packets reached plus a margin ("gather_depth": -1 auto, 0 = every plane, n = n planes; the
+ * rare packet that goes deeper reads the caller's array directly), and the download skips the rows that hold only zeros.
+ * Options "box_io" (-1 auto, 0 = plain copies in sequence) and read-only "io_form" (bit0: columns-only download, bit1:
+ * columns-first upload, bit2: depth-limited) and "depth_hint" (planes from the top face to the deepest stop of the last
+ * column-form call).
  * tamc_run alone uses the same download.  In that mode stats->h2d_ms / d2h_ms time only the column copies
  * that are not hidden behind the transport. */
 int tamc_run_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2, int flags,

@@ -7,6 +7,7 @@ Stale host content outside the beam's columns must be overwritten with zeros."""
 import numpy as np
 import pytest
 
+from oracle import oracle as orc
 from tests.util import compare_grids, make_oracle
 
 pytestmark = pytest.mark.gpu
@@ -143,3 +144,98 @@ def test_plain_path_when_not_applicable():
     assert t.get_option("io_form") == 0 and jp.sum() > 0
     tamc.unpin_host(jp)
     t.close()
+
+
+def _deep_grid(nx, ny, nz, kappa=30.0):
+    rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+    ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+    rk[1:-1, 1:-1, 1:-1] = kappa * (1.0 + 0.25 * ((ii + 2 * jj + 3 * kk) % 4))
+    return rk
+
+
+@pytest.mark.parametrize("dims,depth,tile,park", [((120, 120, 120), 8, -1, -1), ((120, 120, 120), 40, 12, 1), ((33, 40, 70), 5, 0, -1),
+                                                  ((48, 48, 96), 1, 23, 1), ((48, 48, 96), 20, 12, 0)])
+def test_depth_limited_upload_reads_deeper_planes_from_the_callers_grid(dims, depth, tile, park):
+    """Columns-first upload cut at `gather_depth` planes on a grid whose packets go far deeper (mean free path ~ 8 voxels,
+    some leave through the bottom face): the transport and the finish kernel fetch what was not copied from the caller's
+    page-locked array (untiled, tiled and regrouped column kernels).  Same packets, counters and grid as the plain path
+    and as the oracle on the same Philox stream."""
+    import tamc
+
+    nx, ny, nz = dims
+    ext = dict(xmax=0.03, ymax=0.03, zmax=0.06)
+    rk = _deep_grid(nx, ny, nz)
+    n = (1 << 20) + 777
+    res = []
+    for box_io, gd in ((0, 0), (-1, depth), (-1, 0)):
+        t = tamc.MCTransport(nx, ny, nz, ext["xmax"], ext["ymax"], ext["zmax"])
+        t.set_option("box_io", box_io)
+        t.set_option("column", 1)
+        t.set_option("column_tile", tile)
+        t.set_option("column_park", park)
+        t.set_option("gather_depth", gd)
+        jm = _pinned(tamc, t.new_jmean())
+        jm[...] = 3.0
+        rkp = _pinned(tamc, np.asfortranarray(rk.copy()))
+        got, st = t.run_optics(rkp, 0.0, 0.9, n, SEED, out=jm)
+        assert np.array_equal(got, t.get_jmean())
+        res.append((got.copy(), st, t.get_option("io_form"), t.get_option("depth_hint")))
+        # the resident grid is complete after the call (the full upload ran beside the transport)
+        t.set_option("box_io", 0)
+        t.seek(0)
+        again, st2 = t.run(n, SEED)
+        compare_grids(again, got, rtol=1e-11)
+        assert st2["voxel_steps"] == st["voxel_steps"]
+        tamc.unpin_host(jm)
+        tamc.unpin_host(rkp)
+        t.close()
+    (plain, st0, io0, _), (cut, st1, io1, dh), (full, st2, io2, _) = res
+    assert io0 == 0 and io1 == 7 and io2 == 3
+    assert dh > depth and st1["exits"][4] > 0                      # packets did go below the copied planes, some to the bottom
+    for key in ("packets", "voxel_steps", "absorbed", "exits"):
+        assert st0[key] == st1[key] == st2[key], key
+    compare_grids(cut, plain, rtol=1e-11)
+    compare_grids(full, plain, rtol=1e-11)
+    o = orc.Oracle(nx, ny, nz, ext["xmax"], ext["ymax"], ext["zmax"])
+    o.set_rhokap(rk)
+    o.set_optics(0.0, 0.9)
+    o.seed_philox(SEED, 0)
+    want = o.run(n)["stats"]
+    assert st1["voxel_steps"] == want["voxel_steps"] and st1["exits"] == want["exits"]
+    compare_grids(cut, o.jmean, rtol=1e-10)
+
+
+def test_depth_limit_follows_the_previous_call():
+    """Auto mode: the first tamc_run_optics copies every plane of the beam's columns, the next ones only down to the
+    depth the previous call reached plus a margin; when the top 40 planes vanish between two calls (packets suddenly
+    40 voxels deeper than the copied planes) the result is still exact -- the deeper planes come from the caller's array."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["shipped80"]
+    n = 1_500_000
+    t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"])
+    ref = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"])
+    ref.set_option("gather_depth", 0)
+    for h in (t, ref):
+        h.set_option("column", 1)                                       # narrow beam, 1.5e6 packets: below the auto threshold
+    grids = [cfg["rhokap"](), cfg["rhokap"](), list(tamc.configs.crater_sequence(80, 8))[7], cfg["rhokap"]()]
+    grids[2][1:-1, 1:-1, 41:81] = 0.0                                   # the top 40 planes gone everywhere
+    jm, jr = _pinned(tamc, t.new_jmean()), _pinned(tamc, ref.new_jmean())
+    forms = []
+    for rk in grids:
+        rkp = _pinned(tamc, np.asfortranarray(rk.copy()))
+        got, st = t.run_optics(rkp, 0.0, 0.9, n, SEED, out=jm)
+        want, sr = ref.run_optics(rkp, 0.0, 0.9, n, SEED, out=jr)
+        forms.append((t.get_option("io_form"), t.get_option("depth_hint"), ref.get_option("io_form")))
+        for key in ("packets", "voxel_steps", "absorbed", "exits"):
+            assert st[key] == sr[key], key
+        compare_grids(got, want, rtol=1e-11)
+        assert np.array_equal(got, t.get_jmean())
+        tamc.unpin_host(rkp)
+    # (after the deep call the limit would cover the whole column again: plain columns-first upload)
+    assert [f[0] for f in forms] == [3, 7, 7, 3] and all(f[2] == 3 for f in forms)
+    assert 8 <= forms[0][1] <= 40 and forms[2][1] >= forms[1][1] + 30       # the third call reached far deeper
+    tamc.unpin_host(jm)
+    tamc.unpin_host(jr)
+    t.close()
+    ref.close()

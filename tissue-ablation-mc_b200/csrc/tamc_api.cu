@@ -430,6 +430,9 @@ extern "C" int tamc_get_stats(tamc_handle h, tamc_stats *st)
     // feeds the launch plan of the next stub-regime call (LaunchCfg::column_park)
     if (!(h->flags & (TAMC_SCATTER | TAMC_FRESNEL)) && cnt[CNT_PACKETS] >= 10000)
         h->cfg.steps_hint = (double)cnt[CNT_STEPS] / (double)cnt[CNT_PACKETS];
+    // ... and the depth limit of the next columns-first upload (LaunchCfg::gather_depth); only the column form measures it
+    const bool column_form = h->form == FORM_COLUMN || h->form == FORM_COLUMN_TILED || h->form == FORM_COLUMN_PARKED;
+    h->cfg.depth_hint = (column_form && cnt[CNT_PACKETS] >= 10000) ? (int)cnt[CNT_DEPTH] : 0;
     st->scatters = (int64_t)cnt[CNT_SCATTERS];
     st->absorbed = (int64_t)cnt[CNT_ABSORBED];
     for (int f = 0; f < 6; ++f) st->exits[f] = (int64_t)cnt[CNT_EXIT0 + f];
@@ -533,6 +536,7 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
     }
 
     const int rc_mc = enqueue_mc(h, nphotons, seed, -1);
+    if (box_up && h->colws.last_kz_lo > 0) h->io_form |= 4;     // the gather stopped at the depth the last call's packets reached
     h->colws.gather_src = nullptr;
     h->colws.box_rk = nullptr;
     h->colws.ev_gather0 = h->colws.ev_gather1 = nullptr;
@@ -743,6 +747,8 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "column")) return &h->cfg.column;
     if (!strcmp(name, "column_tile")) return &h->cfg.column_tile;
     if (!strcmp(name, "column_park")) return &h->cfg.column_park;
+    if (!strcmp(name, "gather_depth")) return &h->cfg.gather_depth;
+    if (!strcmp(name, "depth_hint")) return &h->cfg.depth_hint;
     if (!strcmp(name, "reduce")) return &h->reduce;
     if (!strcmp(name, "probe_form")) return &h->probe_form;
     if (!strcmp(name, "box_reduce")) return &h->box_reduce;
@@ -758,6 +764,8 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
     if (slot == &h->form) return fail(TAMC_EINVAL, "form is read-only: the kernel the last MC call ran");
     if (slot == &h->io_form) return fail(TAMC_EINVAL, "io_form is read-only: how the last tamc_run moved its arrays");
+    if (slot == &h->cfg.depth_hint) return fail(TAMC_EINVAL, "depth_hint is read-only: planes from the top face to the deepest stop of the last column-form call");
+    if (slot == &h->cfg.gather_depth && (value < -1 || value > 4096)) return fail(TAMC_EINVAL, "gather_depth must be -1 (auto), 0 (all planes) or a number of planes");
     if (slot == &h->probe_form && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "probe_form must be -1, 0 or 1");
     if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");

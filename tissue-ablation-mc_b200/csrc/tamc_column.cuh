@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_column_gather(const DevGrid g, const Co
                                                        double *__restrict__ rkT, double *__restrict__ box)
 {
     __shared__ double tile[32][33];
-    const int dj = blockIdx.y, di0 = blockIdx.x * 32, kz0 = blockIdx.z * 32;
+    const int dj = blockIdx.y, di0 = blockIdx.x * 32, kz0 = cg.kz_lo + blockIdx.z * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long rowj = (long long)g.sx * (cg.j0 + dj);
     double v[4];
@@ -69,6 +69,21 @@ __device__ __forceinline__ void ldg256(const double *p, double &a, double &b, do
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+// The opacities of the four-voxel group kz = gb .. gb+3 of column col_id: one 256-bit load of the z-fastest copy, or --
+// below the depth the columns-first upload copied (ColGeom::kz_lo) -- four loads from the caller's grid over PCIe.
+template <bool kDeep>
+__device__ __forceinline__ void load_group(const ColGeom &cg, const double *__restrict__ col, int col_id, int gb,
+                                           double &r0, double &r1, double &r2, double &r3)
+{
+    if (!kDeep || gb >= cg.kz_lo) {
+        ldg256(col + gb, r0, r1, r2, r3);           // col = the column's slice of the z-fastest copy
+        return;
+    }
+    const int dj = col_id / cg.tw, di = col_id - dj * cg.tw;
+    const double *p = cg.deep + ((long long)(cg.i0 + di) + (long long)cg.deep_sx * (cg.j0 + dj) + cg.deep_sxy * (gb + 1));
+    r0 = p[0]; r1 = p[cg.deep_sxy]; r2 = p[2 * cg.deep_sxy]; r3 = p[3 * cg.deep_sxy];    // gb + 3 < kz_lo <= nzg
+}
+
 // dcell(k) for k = 1..nzp into shared memory (0 past the launch plane / the grid): the wall distance
 // voxel_step_fast computes for a straight-down flight, fmin(fmin(100000., 100000.), (fz - zcur) * inz) with inz = -1.
 __device__ __forceinline__ void stage_column_steps(const DevGrid &g, int nzp, double *s_dz)
@@ -87,7 +102,7 @@ __device__ __forceinline__ void stage_column_steps(const DevGrid &g, int nzp, do
 
 // One packet per thread, grid-stride.  kGather: read the z-fastest copy with 256-bit loads; otherwise walk the
 // resident grid itself (one 8-byte load per voxel-step).
-template <bool kGather, int kMinCtas>
+template <bool kGather, int kMinCtas, bool kDeep = false>
 __global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                              const ColGeom cg, const double *__restrict__ rkT,
                                                              unsigned int *__restrict__ stops,
@@ -109,12 +124,13 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGri
         int kstop = 0;                                   // voxel of the interaction; 0 = left through the bottom face
         if (kGather) {
             const int di = (L.cells & 0xffff) - cg.i0, dj = (L.cells >> 16) - cg.j0;
-            const double *col = rkT + ((size_t)dj * cg.tw + di) * cg.nzp;
+            const int col_id = dj * cg.tw + di;
+            const double *col = rkT + (size_t)col_id * cg.nzp;
             int idx = k0 - 1;                            // k - 1 of the voxel the packet is in
             while (idx >= 0) {
                 const int gb = idx & ~3;
                 double r0, r1, r2, r3;
-                ldg256(col + gb, r0, r1, r2, r3);
+                load_group<kDeep>(cg, col, col_id, gb, r0, r1, r2, r3);
                 const double2 da = *reinterpret_cast<const double2 *>(s_dz + gb), db = *reinterpret_cast<const double2 *>(s_dz + gb + 2);
                 // dcell*rhokap, inttau2.f90:40 -- products and sums rounded separately (no FMA contraction), as the oracle does
                 const double tc3 = __dmul_rn(db.y, r3), tc2 = __dmul_rn(db.x, r2), tc1 = __dmul_rn(da.y, r1), tc0 = __dmul_rn(da.x, r0);
@@ -186,6 +202,7 @@ __device__ __forceinline__ void smem_add_f64(double *p, double v)
     } while (old != assumed);
 }
 
+template <bool kDeep>
 __global__ void __launch_bounds__(1024, 1) k_transport_column_tiled(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                                     const ColGeom cg, const double *__restrict__ rkT,
                                                                     unsigned int *__restrict__ stops,
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_tiled(const DevGri
         while (idx >= 0) {                                                     // as k_transport_column<true>
             const int gb = idx & ~3;
             double r0, r1, r2, r3;
-            ldg256(col + gb, r0, r1, r2, r3);
+            load_group<kDeep>(cg, col, col_id, gb, r0, r1, r2, r3);
             const double2 da = *reinterpret_cast<const double2 *>(s_dz + gb), db = *reinterpret_cast<const double2 *>(s_dz + gb + 2);
             const double tc3 = __dmul_rn(db.y, r3), tc2 = __dmul_rn(db.x, r2), tc1 = __dmul_rn(da.y, r1), tc0 = __dmul_rn(da.x, r0);
             const double t3 = __dadd_rn(taurun, tc3), t2 = __dadd_rn(t3, tc2), t1 = __dadd_rn(t2, tc1), t0 = __dadd_rn(t1, tc0);
@@ -291,11 +308,13 @@ struct ParkQueue {                 // one per warp
 
 // one four-voxel group of a packet's walk (inttau2.f90:37-63 for a straight-down flight); returns the stop voxel
 // (1-based k), 0 = left through the bottom face, -1 = goes on with the group below (idx, taurun advanced)
-__device__ __forceinline__ int column_group(const double *__restrict__ col, const double *s_dz, int &idx, double tau, double &taurun)
+template <bool kDeep>
+__device__ __forceinline__ int column_group(const ColGeom &cg, const double *__restrict__ col, int col_id, const double *s_dz, int &idx,
+                                            double tau, double &taurun)
 {
     const int gb = idx & ~3;
     double r0, r1, r2, r3;
-    ldg256(col + gb, r0, r1, r2, r3);
+    load_group<kDeep>(cg, col, col_id, gb, r0, r1, r2, r3);
     const double2 da = *reinterpret_cast<const double2 *>(s_dz + gb), db = *reinterpret_cast<const double2 *>(s_dz + gb + 2);
     const double tc3 = __dmul_rn(db.y, r3), tc2 = __dmul_rn(db.x, r2), tc1 = __dmul_rn(da.y, r1), tc0 = __dmul_rn(da.x, r0);
     const double t3 = __dadd_rn(taurun, tc3), t2 = __dadd_rn(t3, tc2), t1 = __dadd_rn(t2, tc1), t0 = __dadd_rn(t1, tc0);
@@ -310,6 +329,7 @@ __device__ __forceinline__ int column_group(const double *__restrict__ col, cons
     return idx >= 0 ? -1 : 0;
 }
 
+template <bool kDeep>
 __global__ void __launch_bounds__(1024, 1) k_transport_column_parked(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
                                                                      const ColGeom cg, const double *__restrict__ rkT,
                                                                      unsigned int *__restrict__ stops,
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_parked(const DevGr
     auto advance = [&](bool live, int col_id, int idx, int jidx, double tau, double taurun) {
         int r = 1;
         if (live) {
-            r = column_group(rkT + (size_t)col_id * cg.nzp, s_dz, idx, tau, taurun);
+            r = column_group<kDeep>(cg, rkT + (size_t)col_id * cg.nzp, col_id, s_dz, idx, tau, taurun);
             if (r >= 0) tally(r, col_id, jidx, tau, taurun);
         }
         const bool park = live && r < 0;
@@ -399,7 +419,7 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_parked(const DevGr
         __syncwarp();
         if (live) {
             int r;
-            do r = column_group(rkT + (size_t)col_id * cg.nzp, s_dz, idx, tau, taurun); while (r < 0);
+            do r = column_group<kDeep>(cg, rkT + (size_t)col_id * cg.nzp, col_id, s_dz, idx, tau, taurun); while (r < 0);
             tally(r, col_id, jidx, tau, taurun);
         }
     }
@@ -438,7 +458,9 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_parked(const DevGr
 // again for the next call.
 constexpr int kFinishChunks = 32;
 
-__global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevGrid g, const ColGeom cg, unsigned int *__restrict__ stops)
+template <bool kDeep>
+__global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevGrid g, const ColGeom cg, unsigned int *__restrict__ stops,
+                                                                      unsigned long long *__restrict__ cnt)
 {
     extern __shared__ double s_dz[];
     __shared__ unsigned long long s_sum[kFinishChunks][32];
@@ -450,6 +472,7 @@ __global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevG
     const int plane = g.nxg * g.nyg;
     const int c0 = (i - 1) + g.nxg * (j - 1);
     const long long r0 = (long long)i + (long long)g.sx * j;
+    const long long rdeep = (long long)i + (long long)cg.deep_sx * j;          // the same voxel in the caller's grid (ColGeom::deep)
     const int len = (g.nzg + kFinishChunks - 1) / kFinishChunks;
     const int klo = chunk * len + 1, khi = min(g.nzg, klo + len - 1);      // voxels of this chunk
 
@@ -461,24 +484,30 @@ __global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevG
     }
     s_sum[chunk][lane] = a;
     __syncthreads();
-    if (!live) return;
-    // F of the first voxel of the chunk: plane 0 + every plane below klo
-    // (s_sum[c] covers planes c*len+1 .. (c+1)*len, plus plane 0 for c = 0: together exactly the planes <= klo - 1)
-    unsigned long long F = 0ull;
-    if (chunk == 0) {
-        F = stops[c0];
-        if (F) stops[c0] = 0u;
-    } else {
-        for (int c = 0; c < chunk; ++c) F += s_sum[c][lane];
-    }
-    for (int k = klo; k <= khi; ++k) {
-        const unsigned int c = (k < g.nzg) ? stops[c0 + k * plane] : 0u;
-        if (F) {
-            const double d = (double)F * (s_dz[k - 1] * __ldg(g.rhokap + r0 + g.sxy * k));
-            if (d != 0.) g.jmean[c0 + (k - 1) * plane] += d;
+    int depth = 0;                                                          // planes from the top face down to the deepest stop seen here
+    if (live) {
+        // F of the first voxel of the chunk: plane 0 + every plane below klo
+        // (s_sum[c] covers planes c*len+1 .. (c+1)*len, plus plane 0 for c = 0: together exactly the planes <= klo - 1)
+        unsigned long long F = 0ull;
+        if (chunk == 0) {
+            F = stops[c0];
+            if (F) { stops[c0] = 0u; depth = g.nzg; }
+        } else {
+            for (int c = 0; c < chunk; ++c) F += s_sum[c][lane];
         }
-        if (c) { F += c; stops[c0 + k * plane] = 0u; }
+        for (int k = klo; k <= khi; ++k) {
+            const unsigned int c = (k < g.nzg) ? stops[c0 + k * plane] : 0u;
+            if (F) {
+                const double rk = (!kDeep || k - 1 >= cg.kz_lo) ? __ldg(g.rhokap + r0 + g.sxy * k) : cg.deep[rdeep + cg.deep_sxy * k];
+                const double d = (double)F * (s_dz[k - 1] * rk);
+                if (d != 0.) g.jmean[c0 + (k - 1) * plane] += d;
+            }
+            if (c) { F += c; stops[c0 + k * plane] = 0u; depth = max(depth, g.nzg - k + 1); }
+        }
     }
+    // feeds the depth limit of the next columns-first upload (LaunchCfg::depth_hint)
+    depth = __reduce_max_sync(0xffffffffu, depth);
+    if (lane == 0 && depth > 0) atomicMax(cnt + CNT_DEPTH, (unsigned long long)depth);
 }
 
 // The tally under the beam's bounding box <-> a dense (tw, th, nzg) buffer.  In the shipped regime every deposit lies

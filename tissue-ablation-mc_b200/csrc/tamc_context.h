@@ -35,7 +35,7 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0.};
+    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0., -1, 0};
     tamc::ColumnWorkspace colws;
     int reduce = 1;
     int box_reduce = -1;    // shipped regime: all-reduce only the columns under the beam (-1 = auto, 0 = off, 1 = on)
@@ -45,7 +45,8 @@ struct tamc_context {
     // overlapped boundary copies of the shipped regime (tamc_run / tamc_run_optics, tamc_api.cu)
     int box_io = -1;        // -1 = auto, 0 = off: plain full-grid copies in sequence
     int io_form = 0;        // read-only: bit0 = the last tamc_run downloaded zero fill + beam columns, bit1 = the last
-                            // tamc_run_optics uploaded the beam columns ahead of the grid
+                            // tamc_run_optics uploaded the beam columns ahead of the grid, bit2 = ... and only down to the
+                            // depth the previous call's packets reached (+ margin)
     cudaStream_t s_up = nullptr, s_dn = nullptr;
     double *d_zero = nullptr;           // n_jmean zeros: the tally outside the beam's columns
     double *d_box_rk = nullptr;         // (tw, th, nzg+2) opacities under the beam, uploaded ahead of the full grid

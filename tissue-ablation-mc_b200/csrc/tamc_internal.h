@@ -27,6 +27,10 @@ struct LaunchCfg {
                         // (measured: +7 % at 2.98 steps per packet, -11 % at 1.56, where nearly every packet stops in
                         // its first four-voxel group and there is nothing to regroup)
     double steps_hint;  // voxel-steps per packet of the previous stub-regime call (0 = none yet)
+    int gather_depth;   // columns-first upload (tamc_run_optics): planes below the top face that k_column_gather copies over
+                        // PCIe ahead of the transport; -1 = auto: depth_hint + max(16, depth_hint / 2), 0 = all, > 0 = that many
+                        // (rounded up to whole 32-plane tiles).  A packet that goes deeper reads the caller's grid directly.
+    int depth_hint;     // planes from the top face to the deepest stop of the previous column-form call (0 = unknown)
 };
 
 // Which kernel an MC call ran ("form" read-only option of tamc_get_option)
@@ -46,6 +50,7 @@ struct ColumnWorkspace {
     const double *gather_src = nullptr;
     double *box_rk = nullptr;
     cudaEvent_t ev_gather0 = nullptr, ev_gather1 = nullptr;
+    int last_kz_lo = 0;              // read-back: first plane (k - 1) the last gather copied (> 0: depth-limited)
 };
 
 // shipped regime: the columns every deposit lies in, and the copy between them and a dense buffer

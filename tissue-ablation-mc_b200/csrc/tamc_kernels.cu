@@ -463,6 +463,10 @@ bool beam_box(const DevGrid &g, ColGeom &cg)
     cg.tw = min(g.nxg, (int)((g.xmax + R) * g.inv_dx) + 1) - cg.i0 + 1;
     cg.th = min(g.nyg, (int)((g.ymax + R) * g.inv_dy) + 1) - cg.j0 + 1;
     cg.nzp = (g.nzg + 3) & ~3;
+    cg.kz_lo = 0;
+    cg.deep_sx = 0;
+    cg.deep_sxy = 0;
+    cg.deep = nullptr;
     return cg.tw >= 1 && cg.th >= 1;
 }
 
@@ -480,7 +484,7 @@ cudaError_t launch_box_mirror(const DevGrid &g, const ColGeom &cg, double *dst, 
 }
 
 // the workspace of the column form (+ the z-fastest copy of the opacities under the box)
-static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gather, cudaStream_t s, ColGeom &cg)
+static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gather, cudaStream_t s, ColGeom &cg, int gather_planes = 0)
 {
     if (!beam_box(g, cg)) return cudaErrorInvalidValue;
     const size_t nstops = (size_t)g.nxg * g.nyg * g.nzg;
@@ -503,7 +507,15 @@ static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gath
             if (e != cudaSuccess) return e;
             ws->rkT_elems = nrk;
         }
-        const dim3 gg((cg.tw + 31) / 32, cg.th, (cg.nzp + 31) / 32);
+        // columns-first upload over PCIe: only the planes the packets are expected to reach (gather_planes from the top
+        // face, whole 32-plane tiles); anything deeper is read from the caller's grid where it is needed
+        if (ws->gather_src && ws->box_rk && gather_planes > 0 && gather_planes < g.nzg) {
+            cg.kz_lo = (g.nzg - gather_planes) & ~31;
+            cg.deep = ws->gather_src;
+            cg.deep_sx = g.sx;
+            cg.deep_sxy = g.sxy;
+        }
+        const dim3 gg((cg.tw + 31) / 32, cg.th, (cg.nzp - cg.kz_lo + 31) / 32);
         if (ws->gather_src && ws->box_rk) {
             if (ws->ev_gather0) cudaEventRecord(ws->ev_gather0, s);
             k_column_gather<true><<<gg, 256, 0, s>>>(g, cg, ws->gather_src, ws->rkT, ws->box_rk);
@@ -566,32 +578,40 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
                                  const ColumnPlan &plan)
 {
     ColGeom cg;
-    cudaError_t e0 = column_setup(g, ws, gather, s, cg);
+    int planes = 0;                                    // depth limit of a columns-first upload over PCIe (0 = every plane)
+    if (cfg.gather_depth > 0) planes = cfg.gather_depth;
+    else if (cfg.gather_depth < 0 && cfg.depth_hint > 0) planes = cfg.depth_hint + (cfg.depth_hint / 2 > 16 ? cfg.depth_hint / 2 : 16);
+    cudaError_t e0 = column_setup(g, ws, gather, s, cg, planes);
     if (e0 != cudaSuccess) return e0;
+    ws->last_kz_lo = cg.kz_lo;
     if (launches && gather) *launches += 1;
     const size_t smem = sizeof(double) * (size_t)cg.nzp;
     LaunchCfg c2 = cfg;
     c2.block = 256;
     cudaError_t e;
     const int ta = gather ? plan.ta : 0, tb = gather ? plan.tb : 0;
+    const bool deep = cg.kz_lo > 0;          // depth-limited columns-first upload: the builds that can read the caller's grid
     if (ta + tb > 0) {
         const size_t tsmem = smem + (size_t)cg.tw * cg.th * (8 * (size_t)ta + 4 * (size_t)tb);
-        e = cudaFuncSetAttribute(k_transport_column_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-        if (e != cudaSuccess) return e;
         const long long want = (n + 1023) / 1024;
         const int grid = (int)(want < cfg.num_sms ? want : cfg.num_sms);
         if (column_parked(cfg)) {
             // tiles, then (8-byte aligned) one ParkQueue per warp
             const size_t psmem = smem + 8 * ((size_t)cg.tw * cg.th * (size_t)ta + (((size_t)cg.tw * cg.th * (size_t)tb + 1) >> 1)) + 32 * sizeof(ParkQueue);
-            e = cudaFuncSetAttribute(k_transport_column_parked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            auto kern = deep ? k_transport_column_parked<true> : k_transport_column_parked<false>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
             if (e != cudaSuccess) return e;
-            k_transport_column_parked<<<grid, 1024, psmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
+            kern<<<grid, 1024, psmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
         } else {
-            k_transport_column_tiled<<<grid, 1024, tsmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
+            auto kern = deep ? k_transport_column_tiled<true> : k_transport_column_tiled<false>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, 1024, tsmem, s>>>(g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt, ta, tb);
         }
         e = cudaGetLastError();
     } else
     if (!gather) e = launch_sized(k_transport_column<false, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)nullptr, ws->stops, d_cnt);
+    else if (deep) e = launch_sized(k_transport_column<true, 4, true>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     else if (cfg.min_ctas == 2) e = launch_sized(k_transport_column<true, 6>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     else e = launch_sized(k_transport_column<true, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     if (e != cudaSuccess) return e;
@@ -603,7 +623,8 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
         gf.sxy = (long long)cg.tw * cg.th;
         gf.rhokap = ws->box_rk - ((long long)cg.i0 + (long long)cg.tw * cg.j0 + gf.sxy);
     }
-    k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(gf, cg, ws->stops);
+    if (deep) k_column_finish<true><<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(gf, cg, ws->stops, d_cnt);
+    else k_column_finish<false><<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(gf, cg, ws->stops, d_cnt);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
@@ -762,7 +783,7 @@ cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, ui
         }
         if (e != cudaSuccess) return e;
         const size_t smem = sizeof(double) * (size_t)cg.nzp;
-        k_column_finish<<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(g, cg, ws->stops);
+        k_column_finish<false><<<(cg.tw * cg.th + 31) / 32, 32 * kFinishChunks, smem, s>>>(g, cg, ws->stops, d_cnt);
         return cudaGetLastError();
     }
     return launch_sized(k_probe, c2, 0, n, s, g, n, seed, disk_r_vox, d_cnt);

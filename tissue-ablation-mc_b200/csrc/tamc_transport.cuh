@@ -30,7 +30,9 @@ constexpr double kTWOPI = 6.283185;
 constexpr int kMaxStepsPerPacket = 1 << 26;
 
 enum { CNT_PACKETS = 0, CNT_STEPS, CNT_SCATTERS, CNT_ABSORBED, CNT_EXIT0, CNT_ERRORS = 10, CNT_OVERFLOW = 11, CNT_WORK = 12,
-       CNT_SPECULAR = 13, CNT_REFLECT = 14, CNT_N = 16 };
+       CNT_SPECULAR = 13, CNT_REFLECT = 14,
+       CNT_DEPTH = 15,   // column form: planes from the top face down to the deepest stop of the call (k_column_finish)
+       CNT_N = 16 };
 
 // Constants of the Henyey-Greenstein draw (stokes.f90:48), formed once on the host.
 struct ScatterConsts {
@@ -63,6 +65,13 @@ struct ColGeom {
     int i0, j0;        // first voxel (1-based) of the box in x and y
     int tw, th;        // its extent
     int nzp;           // column length of the z-fastest opacity copy: nzg rounded up to a multiple of 4
+    // Columns-first upload over PCIe with a depth limit (tamc_run_optics, LaunchCfg::gather_depth): only planes kz = k-1
+    // >= kz_lo (a multiple of 32) were copied into the z-fastest / box copies; the rare packet that goes deeper reads the
+    // caller's page-locked grid `deep` itself (reference layout, strides deep_sx / deep_sxy).  kz_lo = 0: everything copied.
+    int kz_lo;
+    int deep_sx;
+    long long deep_sxy;
+    const double *deep;
 };
 
 // ---------------------------------------------------------------------------------------------
