@@ -424,7 +424,9 @@ def run_ours(args, cfg, name):
                     "ms_per_step": 1e3 * float(e2e_s.item()) / args.steps, "parts_ms": e2e_parts,
                     "api": "tamc_run_optics(host rhokap -> host jmeanGLOBAL) = tamc_set_optics + tamc_run, pinned host arrays; io_form %d "
                            "(bit0: jmeanGLOBAL written as zero fill beside the kernels + the beam's columns, bit1: the beam's columns of "
-                           "rhokap uploaded ahead of the full grid); parts_ms h2d/d2h time only the copies not hidden behind the transport" % t.get_option("io_form"),
+                           "rhokap uploaded ahead of the full grid, bit2: ... and only down to the depth the previous call's packets "
+                           "reached + margin, deeper planes read from the caller's array on demand; the full grid and the zero fill "
+                           "still cross PCIe inside the call); parts_ms h2d/d2h time only the copies not hidden behind the transport" % t.get_option("io_form"),
                     "jmean_sum_per_packet": jm_sum / (packets * world)},
             "gpu_launches": int(res["launches"]), "clocks": clocks, "also": also,
         }

@@ -38,3 +38,27 @@ for sigma in (0.0, 0.015):
             assert np.array_equal(rec["steps"], out["records"]["steps"])
             print("  replay ok", int(rec["steps"].sum()))
         t.close()
+
+# depth-limited columns-first upload: deep groups read from the caller's page-locked grid (untiled, tiled, regrouped)
+nx, ny, nz = 48, 40, 96
+rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+rk[1:-1, 1:-1, 1:-1] = 30.0 * (1.0 + 0.25 * ((ii + 2 * jj + 3 * kk) % 4))
+tamc.pin_host(rk)
+big = 40 * npk
+for tile, park in ((0, 0), (12, 0), (12, 1), (23, 1)):
+    t = tamc.MCTransport(nx, ny, nz, 0.03, 0.03, 0.06)
+    jm = t.new_jmean()
+    tamc.pin_host(jm)
+    t.set_option("column", 1)
+    t.set_option("column_tile", tile)
+    t.set_option("column_park", park)
+    for gd in (1, 40, -1, -1):
+        t.set_option("gather_depth", gd)
+        _, st = t.run_optics(rk, 0.0, 0.9, big, 5, out=jm)
+        assert np.array_equal(jm, t.get_jmean()) and st["exits"][4] > 0
+        print("deep upload: tile", tile, "park", park, "gather_depth", gd, "io_form", t.get_option("io_form"), "form", t.get_option("form"),
+              "depth_hint", t.get_option("depth_hint"), "steps", st["voxel_steps"])
+    tamc.unpin_host(jm)
+    t.close()
+tamc.unpin_host(rk)
