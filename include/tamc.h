@@ -187,7 +187,7 @@ int tamc_unpin_host(void *ptr);
  * "min_ctas", "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "column_tile" (shared-memory
  * tiles of the column form: -1 = auto, 0 = off, 10*ta + tb = ta planes of deposits and tb planes of
  * stop counts), "column_park" (regrouped column walk of a tiled call: -1 = auto from the previous call's
- * voxel-steps per packet, 0 = off, 1 = on), "reduce" (0 = skip the all-reduce), "box_reduce" / "box_io" (-1 = auto, 0 = move the
+ * voxel-steps per packet, 0 = off, 1 = on), "launch32" (column form: fp32 first pass of the launch voxel, 1 = on), "reduce" (0 = skip the all-reduce), "box_reduce" / "box_io" (-1 = auto, 0 = move the
  * whole grid), "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 =
  * per-voxel-step address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the
  * last MC call ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on
@@ -199,6 +199,12 @@ int64_t tamc_get_option(tamc_handle h, const char *name);
  * per packet one 256-bit load per four voxels + at most two REDs); ms receives its device time,
  * steps the voxel-steps it stands for. */
 int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *ms, int64_t *steps);
+/* The column form takes a packet's launch voxel from an fp32 first pass (hardware sqrt / sin / cos) and redoes it in the
+ * production fp64 arithmetic (sourceph.f90:28-31,45-46) whenever the point lies within a proven error bound of a voxel
+ * edge, so the voxel is always the fp64 one ("launch32" = 0 switches the first pass off).  This runs both passes over
+ * the first n Philox blocks of `seed` and counts the draws handed to fp64 and the draws where the fp32 pass kept a
+ * voxel that differs (must be 0). */
+int tamc_selfcheck_launch(tamc_handle h, int64_t n, int64_t seed, int64_t *fallbacks, int64_t *mismatches);
 /* Writes >= bytes of device memory to evict L2 between timed steps. */
 int tamc_flush_l2(tamc_handle h, uint64_t bytes);
 

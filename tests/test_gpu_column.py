@@ -149,3 +149,46 @@ def test_auto_tiles_for_calls_that_amortise_the_flush(name, n, split):
     t.run_async(1000, SEED, 0)                         # the probe leaves the stop counts clean
     assert t.get_option("form") == 1 and abs(t.get_jmean().sum() / 1000 - 1.0) < 0.2
     t.close()
+
+
+@pytest.mark.parametrize("dims,ext,spot", [((200, 200, 200), (0.03, 0.03, 0.06), 0.025), ((80, 80, 80), (0.03, 0.03, 0.06), 0.025),
+                                           ((4096, 64, 4), (0.5, 0.01, 0.01), 0.019), ((33, 70, 9), (0.04, 0.03, 0.02), 0.012),
+                                           ((400, 400, 8), (1.0, 1.0, 1.0), 1.9)])
+def test_fp32_first_pass_of_the_launch_voxel_never_disagrees(dims, ext, spot):
+    """The column form's launch voxel: fp32 first pass + fp64 redo near voxel edges.  Both passes over 4e9 Philox blocks:
+    the first pass never keeps a voxel the fp64 arithmetic would not give, and hands over only a few draws in a thousand
+    (more on grids with thousands of voxels per axis, where fp32 resolves a voxel less finely)."""
+    import tamc
+
+    t = tamc.MCTransport(*dims, *ext)
+    t.set_source_co2(spot)
+    n = 4_000_000_000
+    fb, bad = t.selfcheck_launch(n, seed=20261017)
+    assert bad == 0
+    assert 0 < fb < (0.2 if max(dims) > 1000 else 0.02) * n
+    t.set_option("launch32", 0)
+    fb0, bad0 = t.selfcheck_launch(1_000_000, seed=3)
+    assert (fb0, bad0) == (1_000_000, 0)                    # switched off: everything goes to fp64
+    t.close()
+
+
+def test_fp32_first_pass_on_and_off_give_the_same_call():
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["homog200"]
+    rk = cfg["rhokap"]()
+    n = 6_000_000
+    res = []
+    for on in (1, 0):
+        t = tamc.MCTransport(200, 200, 200, cfg["xmax"], cfg["ymax"], cfg["zmax"])
+        t.set_option("launch32", on)
+        t.set_optics(rk, 0.0, 0.9)
+        t.run_async(n, 99, 0)
+        res.append((t.get_jmean().copy(), t.get_stats(), t.get_option("form")))
+        t.close()
+    assert res[0][2] in (5, 7, 8) and res[1][2] == res[0][2]
+    for key in ("packets", "voxel_steps", "absorbed", "exits"):
+        assert res[0][1][key] == res[1][1][key]
+    assert np.array_equal(res[0][0] != 0, res[1][0] != 0)
+    nz = res[1][0] != 0
+    assert np.abs(res[0][0][nz] / res[1][0][nz] - 1).max() < 1e-11

@@ -112,6 +112,18 @@ static DevGrid make_grid(const tamc_context *c)
     g.n1 = c->n1; g.n2 = c->n2;
     g.r0sq = ((c->n1 - c->n2) / (c->n1 + c->n2)) * ((c->n1 - c->n2) / (c->n1 + c->n2));
     g.gauss_sigma = c->gauss_sigma;
+    {   // launch_cells (tamc_fast.cuh): error bound of the fp32 pass in voxel units, see the derivation there
+        const double R = c->spot / 2.;
+        const double ex = 4. * (3.5e-6 * R * g.inv_dx + 6.0e-8 * (double)c->nxg + 1e-7);
+        const double ey = 4. * (3.5e-6 * R * g.inv_dy + 6.0e-8 * (double)c->nyg + 1e-7);
+        g.spot_r2_f = (float)g.spot_r2;
+        g.inv_dx_f = (float)g.inv_dx;
+        g.inv_dy_f = (float)g.inv_dy;
+        g.x0_f = 0.5f * (float)c->nxg;
+        g.y0_f = 0.5f * (float)c->nyg;
+        g.half_x = (ex < 0.125 && c->launch32) ? (float)(0.5 - ex) : -1.f;
+        g.half_y = (ey < 0.125 && c->launch32) ? (float)(0.5 - ey) : -1.f;
+    }
     g.sc.one_m_g2 = 1. - g.g2;                                         // stokes.f90:48
     g.sc.one_p_g2 = 1. + g.g2;
     g.sc.one_m_g = 1. - g.hgg;
@@ -747,6 +759,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "column")) return &h->cfg.column;
     if (!strcmp(name, "column_tile")) return &h->cfg.column_tile;
     if (!strcmp(name, "column_park")) return &h->cfg.column_park;
+    if (!strcmp(name, "launch32")) return &h->launch32;
     if (!strcmp(name, "gather_depth")) return &h->cfg.gather_depth;
     if (!strcmp(name, "depth_hint")) return &h->cfg.depth_hint;
     if (!strcmp(name, "reduce")) return &h->reduce;
@@ -783,6 +796,24 @@ extern "C" int64_t tamc_get_option(tamc_handle h, const char *name)
 {
     int *slot = option_slot(h, name);
     return slot ? *slot : -1;
+}
+
+extern "C" int tamc_selfcheck_launch(tamc_handle h, int64_t n, int64_t seed, int64_t *fallbacks, int64_t *mismatches)
+{
+    if (int rc = check(h)) return rc;
+    if (n < 0 || !fallbacks || !mismatches) return fail(TAMC_EINVAL, "tamc_selfcheck_launch: bad arguments");
+    const DevGrid g = make_grid(h);
+    unsigned long long *d_out = nullptr, out[2] = {0ull, 0ull};
+    CU(cudaMalloc(&d_out, sizeof(out)));
+    cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(out), h->stream);
+    if (e == cudaSuccess && n > 0) e = launch_selfcheck(g, n, (uint64_t)seed, 0, d_out, h->num_sms, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(TAMC_ECUDA, std::string("tamc_selfcheck_launch: ") + cudaGetErrorString(e));
+    *fallbacks = (int64_t)out[0];
+    *mismatches = (int64_t)out[1];
+    return TAMC_OK;
 }
 
 extern "C" int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *ms, int64_t *steps)

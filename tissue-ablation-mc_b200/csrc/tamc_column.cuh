@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGri
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t gid = first_id + (uint64_t)i;
-        const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), false);
+        const LaunchedColumn L = launch_column(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u));
         const double tau = L.tau;
         double taurun = 0.;
         int kstop = 0;                                   // voxel of the interaction; 0 = left through the bottom face
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_column(const DevGri
                 idx = gb - 1;
             }
         } else {
-            int ridx = L.ridx;
+            int ridx = (L.cells & 0xffff) + g.sx * ((L.cells >> 16) + (g.nyg + 2) * k0);
             for (int k = k0; k >= 1; --k) {
                 const double taucell = __dmul_rn(s_dz[k - 1], __ldg(g.rhokap + ridx));
                 const double t = __dadd_rn(taurun, taucell);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_tiled(const DevGri
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t gid = first_id + (uint64_t)i;
-        const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), false);
+        const LaunchedColumn L = launch_column(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u));
         const double tau = L.tau;
         double taurun = 0.;
         int kstop = 0;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(1024, 1) k_transport_column_parked(const DevGr
         const long long i = wbase + lane;
         const bool live = i < n;
         const uint64_t gid = first_id + (uint64_t)i;
-        const Launched L = launch_fast(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u), false);
+        const LaunchedColumn L = launch_column(g, philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u));
         const int di = (L.cells & 0xffff) - cg.i0, dj = (L.cells >> 16) - cg.j0;
         if (live) ++packets;
         advance(live, dj * cg.tw + di, k0 - 1, L.jidx, L.tau, 0.);

@@ -40,6 +40,7 @@ struct tamc_context {
     int reduce = 1;
     int box_reduce = -1;    // shipped regime: all-reduce only the columns under the beam (-1 = auto, 0 = off, 1 = on)
     int form = -1;          // FORM_* of the last MC call
+    int launch32 = 1;       // column form: fp32 first pass for the launch voxel (exact: redone in fp64 near voxel edges); 0 = off
     int probe_form = -1;    // tamc_roofline_probe: -1 = match the transport, 0 = per-voxel-step stream, 1 = column form
 
     // overlapped boundary copies of the shipped regime (tamc_run / tamc_run_optics, tamc_api.cu)

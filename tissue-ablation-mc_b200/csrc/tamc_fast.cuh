@@ -94,19 +94,78 @@ struct Launched {
     int ridx, jidx;   // linear indices of the launch voxel in rhokap / jmean
 };
 
+// sourceph.f90:28-31,45-46 in the production arithmetic: the launch point (shifted frame) and its voxel.
+__device__ __forceinline__ void launch_point(const DevGrid &g, uint32_t wx, uint32_t wy, double &xcur, double &ycur, int &celli, int &cellj)
+{
+    const double r = unit_fast(wx) * g.spot_r2;
+    const double theta = unit_fast(wy) * kTWOPI;
+    double s, c;
+    fm::sincospi_0_2(theta * kInvPi, &s, &c);
+    const double sr = (r > 1e-280) ? fm::sqrt_normal(r) : sqrt(r);   // (spot diameter 0: r = 0)
+    xcur = sr * c + g.xmax;
+    ycur = sr * s + g.ymax;
+    celli = (int)(xcur * g.inv_dx) + 1;
+    cellj = (int)(ycur * g.inv_dy) + 1;
+}
+
+// The launch VOXEL alone -- all the column form needs of the launch point (a straight-down flight never leaves its
+// column and its deposits do not depend on where in the column it flies).  fp32 first pass with hardware sqrt / sin /
+// cos; launch_point() decides whenever the fp32 result lies within eps of a voxel edge, so the voxel is ALWAYS the one
+// launch_point() gives.  Error of the fp32 pass in voxel units, R = spot radius in voxels, n = voxels per axis:
+//   u (x + 0.5) 2^-32 in fp32: relative 1.2e-7; r = u * spot_r2: 2.4e-7; sqrt.approx: 1.2e-7 on top of half of that
+//     -> sr relative 2.4e-7;
+//   angle a = u * 6.283185f: relative 2.4e-7 -> <= 1.5e-6 rad; minus 2 pi (fp32) above pi: 2e-6 rad in all;
+//   sin.approx / cos.approx on [-pi, pi]: absolute 2^-20 = 9.5e-7 (PTX ISA: 2^-20.5 in the primary range)
+//     -> sr * cos: absolute <= R * 3.3e-6; times inv_dx in fp32: + R * 6e-8; the fma rounds X <= n to 6e-8 * n;
+//   X - floor(X) and the comparison with 0.5: exact / 3e-8.
+// Bound: R * 3.5e-6 + n * 6e-8 + 1e-7; DevGrid::half_* holds 0.5 - 4 x that bound (tamc_api.cu).  For homog200
+// (R = 41.7 voxels, n = 200) eps = 6.3e-4: one packet in 400 is redone in fp64.  tamc_selfcheck_launch() runs both
+// passes over billions of draws and counts disagreements (tests/test_gpu_column.py: zero).
+__device__ __forceinline__ bool launch_voxel_fp32(const DevGrid &g, uint32_t wx, uint32_t wy, int &celli, int &cellj)
+{
+    const float u0 = fmaf((float)wx, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (x + 0.5) 2^-32
+    const float u1 = fmaf((float)wy, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float sr, sn, cs;
+    const float r = u0 * g.spot_r2_f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sr) : "f"(r));
+    float a = u1 * 6.283185f;                               // the reference's truncated TWOPI (constants.f90:13)
+    a = a > 3.14159265f ? a - 6.28318531f : a;              // the same angle, in [-pi, pi]
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(a));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(a));
+    const float X = fmaf(sr * cs, g.inv_dx_f, g.x0_f), Y = fmaf(sr * sn, g.inv_dy_f, g.y0_f);
+    const float Xi = floorf(X), Yi = floorf(Y);
+    celli = (int)Xi + 1;
+    cellj = (int)Yi + 1;
+    return fabsf((X - Xi) - 0.5f) < g.half_x && fabsf((Y - Yi) - 0.5f) < g.half_y;
+}
+
+struct LaunchedColumn {
+    double tau;
+    int cells;        // celli | cellj << 16
+    int jidx;         // linear index of the launch voxel in jmean
+};
+
+// Launch of a stub-regime packet in the column form: voxel + optical depth (sourceph.f90:28-47, inttau2.f90:36).
+__device__ __forceinline__ LaunchedColumn launch_column(const DevGrid &g, const uint4 w)
+{
+    LaunchedColumn L;
+    int celli, cellj;
+    if (!launch_voxel_fp32(g, w.x, w.y, celli, cellj)) {
+        double xcur, ycur;
+        launch_point(g, w.x, w.y, xcur, ycur, celli, cellj);
+    }
+    L.cells = celli | (cellj << 16);
+    L.jidx = (celli - 1) + g.nxg * ((cellj - 1) + g.nyg * (g.cellk0 - 1));
+    L.tau = fm::neglog_u32(w.w);
+    return L;
+}
+
 // sourceph.f90:28-47 + inttau2.f90:36.  w = one Philox block = the (r, theta, phi, tau) draws in the reference's order.
 __device__ __forceinline__ Launched launch_fast(const DevGrid &g, const uint4 w, bool need_azimuth)
 {
     Launched L;
-    const double r = unit_fast(w.x) * g.spot_r2;
-    const double theta = unit_fast(w.y) * kTWOPI;
-    double s, c;
-    fm::sincospi_0_2(theta * kInvPi, &s, &c);
-    const double sr = (r > 1e-280) ? fm::sqrt_normal(r) : sqrt(r);   // (spot diameter 0: r = 0)
-    L.xcur = sr * c + g.xmax;
-    L.ycur = sr * s + g.ymax;
-    const int celli = (int)(L.xcur * g.inv_dx) + 1;
-    const int cellj = (int)(L.ycur * g.inv_dy) + 1;
+    int celli, cellj;
+    launch_point(g, w.x, w.y, L.xcur, L.ycur, celli, cellj);
     L.cells = celli | (cellj << 16);
     L.ridx = celli + g.sx * (cellj + (g.nyg + 2) * g.cellk0);
     L.jidx = (celli - 1) + g.nxg * ((cellj - 1) + g.nyg * (g.cellk0 - 1));

@@ -75,6 +75,8 @@ cudaError_t launch_replay(const DevGrid &g, long long n, const long long *d_off,
 // 1 = column form) and utilities
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,
                          cudaStream_t s, ColumnWorkspace *ws, int probe_form);
+cudaError_t launch_selfcheck(const DevGrid &g, long long n, uint64_t seed, uint64_t first_id, unsigned long long *d_out, int num_sms,
+                             cudaStream_t s);
 cudaError_t launch_fill(double *p, size_t n, double v, int num_sms, cudaStream_t s);
 
 }  // namespace tamc

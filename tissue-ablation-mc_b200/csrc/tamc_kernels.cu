@@ -756,6 +756,44 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     return launch_sized(k_transport_persistent<DirectTally32, false, 4>, cfg, psmem, n, s, g, n, seed, first_id, chunk, cfg.scatter_min, d_cnt);
 }
 
+// Both passes of the column form's launch voxel (launch_voxel_fp32 / launch_point, tamc_fast.cuh) over n Philox blocks:
+// out[0] = draws the fp32 pass handed to fp64, out[1] = draws where it kept a voxel that differs from fp64's (must be 0).
+__global__ void __launch_bounds__(256) k_selfcheck_launch(const DevGrid g, long long n, uint64_t first_id, unsigned long long *__restrict__ out)
+{
+    unsigned long long fb = 0ull, bad = 0ull;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gid = first_id + (uint64_t)i;
+        const uint4 w = philox_block(g, (uint32_t)gid, (uint32_t)(gid >> 32), 0u);
+        int a, b, c, d;
+        double x, y;
+        const bool ok = launch_voxel_fp32(g, w.x, w.y, a, b);
+        launch_point(g, w.x, w.y, x, y, c, d);
+        fb += !ok;
+        bad += ok && (a != c || b != d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fb += __shfl_xor_sync(0xffffffffu, fb, o);
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (fb) atomicAdd(out, fb);
+        if (bad) atomicAdd(out + 1, bad);
+    }
+}
+
+cudaError_t launch_selfcheck(const DevGrid &g_in, long long n, uint64_t seed, uint64_t first_id, unsigned long long *d_out, int num_sms, cudaStream_t s)
+{
+    DevGrid g = g_in;
+    for (int r = 0; r < 10; ++r) {
+        g.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        g.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    k_selfcheck_launch<<<num_sms * 8, 256, 0, s>>>(g, n, first_id, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, unsigned long long *d_cnt,
                          cudaStream_t s, ColumnWorkspace *ws, int probe_form)
 {

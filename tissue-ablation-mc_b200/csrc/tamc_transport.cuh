@@ -53,6 +53,11 @@ struct DevGrid {
     int flags;
     double n1, n2, r0sq;  // TAMC_FRESNEL: indices outside / inside the grid, ((n1-n2)/(n1+n2))**2
     double gauss_sigma;   // > 0: Gaussian beam through rang() (sourceph.f90:73-101) instead of the CO2 disk
+    // fp32 first pass of the launch voxel in the column form (launch_cells, tamc_fast.cuh): spot_r2, inv_dx, inv_dy in
+    // fp32, the centre of the face in voxel units (nxg/2, nyg/2: exact), and 0.5 - eps per axis, eps = the proven bound
+    // of the fp32 pass in voxel units (x 4); a launch point closer than eps to a voxel edge is redone in fp64.
+    // half < 0 switches the fp32 pass off.
+    float spot_r2_f, inv_dx_f, inv_dy_f, x0_f, y0_f, half_x, half_y;
     ScatterConsts sc;
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
