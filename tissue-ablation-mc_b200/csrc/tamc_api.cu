@@ -543,6 +543,16 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
         h->colws.box_rk = h->d_box_rk;
         h->colws.ev_gather0 = h->ev[EV_H0];
         h->colws.ev_gather1 = h->ev[EV_H1];
+        // "io_early": start the full-grid upload (bit0) / the zero fill (bit1) at once, beside the gather, instead of behind it
+        if (h->io_early & 1) {
+            CU(cudaStreamWaitEvent(h->s_up, h->ev[EV_FORK], 0));
+            CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
+            CU(cudaEventRecord(h->ev[EV_UP], h->s_up));
+        }
+        if (h->io_early & 2) {
+            CU(cudaMemcpyAsync(jmean_global, h->d_zero, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->s_dn));
+            CU(cudaEventRecord(h->ev[EV_DN], h->s_dn));
+        }
     } else if (rhokap) {
         if (int rc = enqueue_upload(h, rhokap)) return rc;
     }
@@ -555,18 +565,23 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
     if (rc_mc) {
         cudaStreamSynchronize(h->stream);
         if (box_dn) cudaStreamSynchronize(h->s_dn);
+        if (box_up) cudaStreamSynchronize(h->s_up);
         return rc_mc;
     }
     if (box_up) {
         // the full grid, for every later reader of the resident rhokap: behind the column upload so the two do not share
         // the link, beside the transport (which no longer reads the resident grid in this call)
         h->timed_h2d = true;
-        CU(cudaStreamWaitEvent(h->s_dn, h->ev[EV_H1], 0));
-        CU(cudaMemcpyAsync(jmean_global, h->d_zero, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->s_dn));
-        CU(cudaEventRecord(h->ev[EV_DN], h->s_dn));
-        CU(cudaStreamWaitEvent(h->s_up, h->ev[EV_H1], 0));
-        CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
-        CU(cudaEventRecord(h->ev[EV_UP], h->s_up));
+        if (!(h->io_early & 2)) {
+            CU(cudaStreamWaitEvent(h->s_dn, h->ev[EV_H1], 0));
+            CU(cudaMemcpyAsync(jmean_global, h->d_zero, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->s_dn));
+            CU(cudaEventRecord(h->ev[EV_DN], h->s_dn));
+        }
+        if (!(h->io_early & 1)) {
+            CU(cudaStreamWaitEvent(h->s_up, h->ev[EV_H1], 0));
+            CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
+            CU(cudaEventRecord(h->ev[EV_UP], h->s_up));
+        }
     }
 
     if (box_dn) {
@@ -760,6 +775,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "column_tile")) return &h->cfg.column_tile;
     if (!strcmp(name, "column_park")) return &h->cfg.column_park;
     if (!strcmp(name, "launch32")) return &h->launch32;
+    if (!strcmp(name, "io_early")) return &h->io_early;
     if (!strcmp(name, "gather_depth")) return &h->cfg.gather_depth;
     if (!strcmp(name, "depth_hint")) return &h->cfg.depth_hint;
     if (!strcmp(name, "reduce")) return &h->reduce;

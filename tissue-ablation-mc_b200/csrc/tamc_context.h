@@ -45,6 +45,8 @@ struct tamc_context {
 
     // overlapped boundary copies of the shipped regime (tamc_run / tamc_run_optics, tamc_api.cu)
     int box_io = -1;        // -1 = auto, 0 = off: plain full-grid copies in sequence
+    int io_early = 0;       // tamc_run_optics, columns-first upload: bit0 = the full-grid upload, bit1 = the zero fill start beside
+                            // the column gather instead of behind it
     int io_form = 0;        // read-only: bit0 = the last tamc_run downloaded zero fill + beam columns, bit1 = the last
                             // tamc_run_optics uploaded the beam columns ahead of the grid, bit2 = ... and only down to the
                             // depth the previous call's packets reached (+ margin)
