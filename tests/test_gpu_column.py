@@ -192,3 +192,39 @@ def test_fp32_first_pass_on_and_off_give_the_same_call():
     assert np.array_equal(res[0][0] != 0, res[1][0] != 0)
     nz = res[1][0] != 0
     assert np.abs(res[0][0][nz] / res[1][0][nz] - 1).max() < 1e-11
+
+
+def test_depth_bound_of_a_call():
+    """k_column_bound: a packet's optical depth is at most 33 ln 2 = 22.87 (one 32-bit Philox word), so no packet gets
+    deeper than where its column's running optical depth passes that -- the bound the multi-rank all-reduce uses
+    ("reduce_bound" = 2 computes it without a communicator).  It must cover the deepest stop actually seen."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["homog200"]
+    t = tamc.MCTransport(200, 200, 200, cfg["xmax"], cfg["ymax"], cfg["zmax"])
+    t.set_option("reduce_bound", 2)
+    t.set_option("column", 1)
+    rk = cfg["rhokap"]()
+    t.set_optics(rk, 0.0, 0.9)
+    t.run_async(3_000_000, 5, 0)
+    st = t.get_stats()
+    # 680 / cm x 0.0006 cm = 0.408 per voxel: 23 / 0.408 -> 57 voxels, one spare
+    assert t.get_option("reduce_planes") == 58
+    assert 20 < t.get_option("depth_hint") <= 57 and st["exits"][4] == 0
+    # a crater (rhokap = 0 in the top planes under the beam) pushes the bound down by its depth; a transparent column
+    # lifts it to the whole grid
+    rk2 = rk.copy()
+    rk2[90:112, 90:112, 181:201] = 0.0
+    t.set_optics(rk2, 0.0, 0.9)
+    t.run_async(3_000_000, 5, 0)
+    assert t.get_option("reduce_planes") == 78 and t.get_option("depth_hint") <= 77
+    rk2[100, 100, :] = 0.0
+    t.set_optics(rk2, 0.0, 0.9)
+    t.run_async(3_000_000, 5, 0)
+    st = t.get_stats()
+    assert t.get_option("reduce_planes") == 200 and st["exits"][4] > 0 and t.get_option("depth_hint") == 200
+    t.set_option("reduce_bound", 1)
+    t.run_async(3_000_000, 5, 0)
+    t.sync()
+    assert t.get_option("reduce_planes") == 0                  # single rank, default: not computed
+    t.close()

@@ -139,12 +139,17 @@ def _stub_worker(rank, world, port, out):
     t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
     t.comm_init(world, rank, tdist.broadcast_unique_id(tamc.comm_unique_id, dist))
     grids = []
-    for column, box in ((0, 0), (0, -1), (1, -1), (1, 1), (2, 0)):
+    for column, box, bound in ((0, 0, 1), (0, -1, 1), (1, -1, 1), (1, 1, 1), (2, 0, 1), (1, -1, 0)):
         t.set_option("column", column)
         t.set_option("box_reduce", box)
+        t.set_option("reduce_bound", bound)
         t.seek(0)
         jm, st = t.run(60000, 7)
         assert st["allreduce_ms"] > 0
+        # the column form on the z-fastest copy derives how deep a packet can get (tau <= 33 ln 2; 1.02 per voxel here:
+        # 23 voxels + one spare) and the all-reduce moves only those planes of the box
+        want = 0 if box == 0 else (24 if (column == 1 and bound) else 80)
+        assert t.get_option("reduce_planes") == want, (column, box, bound, t.get_option("reduce_planes"))
         grids.append(jm.copy())
     np.save(f"{out}.{rank}.npy", np.stack(grids))
     dist.barrier()

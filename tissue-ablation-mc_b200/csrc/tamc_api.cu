@@ -231,6 +231,11 @@ extern "C" int tamc_finalize(tamc_handle h)
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_flush);
     cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense);
+    if (h->colws.s_side) { cudaStreamSynchronize(h->colws.s_side); cudaStreamDestroy(h->colws.s_side); }
+    if (h->colws.h_bound) cudaFreeHost(h->colws.h_bound);
+    cudaFree(h->colws.bound_scratch);
+    if (h->colws.ev_bound) cudaEventDestroy(h->colws.ev_bound);
+    if (h->colws.ev_gathered) cudaEventDestroy(h->colws.ev_gathered);
     if (h->s_up) { cudaStreamSynchronize(h->s_up); cudaStreamDestroy(h->s_up); }
     if (h->s_dn) { cudaStreamSynchronize(h->s_dn); cudaStreamDestroy(h->s_dn); }
     cudaFree(h->d_zero); cudaFree(h->d_box_rk);
@@ -343,6 +348,15 @@ extern "C" int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *i
 static int enqueue_reduce(tamc_handle h)
 {
     h->timed_reduce = false;
+    // the depth bound of this call (k_column_bound), if one was asked for: read as soon as that small kernel has run --
+    // the transport is still going.  Always consumed here, so the next call's kernel never meets an unread answer.
+    int bound = 0;
+    if (h->colws.bound_pending) {
+        CU(cudaEventSynchronize(h->colws.ev_bound));
+        bound = *(volatile int *)h->colws.h_bound;
+        h->colws.bound_pending = false;
+    }
+    h->reduce_planes = bound;
     if (h->comm && h->reduce && h->nranks > 1) {
         // mcpolar.f90:173: MPI_allREDUCE(jmean, jmeanGLOBAL, nxg*nyg*nzg, MPI_DOUBLE_PRECISION, MPI_SUM)
         // Shipped regime (no scatter loop): every flight is straight down, so the tally is zero outside the columns under
@@ -352,8 +366,14 @@ static int enqueue_reduce(tamc_handle h)
         ColGeom cg;
         const bool box = h->box_reduce != 0 && !(h->flags & (TAMC_SCATTER | TAMC_FRESNEL)) && beam_box(g, cg) &&
                          (h->box_reduce > 0 || 2 * (size_t)cg.tw * cg.th <= (size_t)h->nxg * h->nyg);
+        h->reduce_planes = 0;
         if (box) {
-            const size_t cnt = (size_t)cg.tw * cg.th * h->nzg;
+            // how many planes below the top face can hold anything (the same number on every rank: same grid)
+            int planes = h->nzg;
+            if (bound > 0 && bound < planes) planes = bound;
+            const int kz0 = h->nzg - planes;
+            h->reduce_planes = planes;
+            const size_t cnt = (size_t)cg.tw * cg.th * (size_t)planes;
             if (h->colws.dense_elems < cnt) {
                 cudaFree(h->colws.dense);
                 h->colws.dense = nullptr;
@@ -361,9 +381,9 @@ static int enqueue_reduce(tamc_handle h)
                 CU(cudaMalloc(&h->colws.dense, cnt * sizeof(double)));
                 h->colws.dense_elems = cnt;
             }
-            CU(launch_box_copy(g, cg, h->colws.dense, false, h->num_sms, h->stream));
+            CU(launch_box_copy(g, cg, h->colws.dense, false, h->num_sms, h->stream, kz0));
             NC(nccl_api()->AllReduce(h->colws.dense, h->colws.dense, cnt, ncclDouble, ncclSum, h->comm, h->stream));
-            CU(launch_box_copy(g, cg, h->colws.dense, true, h->num_sms, h->stream));
+            CU(launch_box_copy(g, cg, h->colws.dense, true, h->num_sms, h->stream, kz0));
         } else {
             NC(nccl_api()->AllReduce(h->d_jmean, h->d_jmean, h->n_jmean, ncclDouble, ncclSum, h->comm, h->stream));
         }
@@ -389,9 +409,17 @@ static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t fir
     static_assert(sizeof(unsigned long long) == sizeof(double), "the counters sit behind the tally in one allocation");
     CU(cudaMemsetAsync(h->d_jmean, 0, (h->n_jmean + CNT_N) * sizeof(double), h->stream));   // zarray / jmean = 0. (mcpolar.f90:185) + counters
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
-    CU(launch_transport(g, h->cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches, &h->colws, &h->form));
+    LaunchCfg cfg = h->cfg;
+    // ("reduce_bound" = 2: also without a communicator, for diagnostics -- the answer lands in "reduce_planes")
+    cfg.want_bound = ((h->comm && h->reduce && h->nranks > 1 && h->box_reduce != 0 && h->reduce_bound) || h->reduce_bound == 2) ? 1 : 0;
+    h->colws.bound_pending = false;
+    if (cfg.want_bound && !h->colws.s_side) {       // the bound kernel runs beside the transport, on a stream of its own
+        if (cudaStreamCreateWithFlags(&h->colws.s_side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); h->colws.s_side = nullptr; }
+    }
+    CU(launch_transport(g, cfg, nphotons, (uint64_t)seed, (uint64_t)first, h->d_cnt, nullptr, h->stream, &launches, &h->colws, &h->form));
     CU(cudaEventRecord(h->ev[EV_K1], h->stream));
     if (int rc = enqueue_reduce(h)) return rc;
+    h->colws.bound_pending = false;
     h->last_launches = launches;
     h->timed_d2h = false;
     h->ran = true;
@@ -781,6 +809,8 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "reduce")) return &h->reduce;
     if (!strcmp(name, "probe_form")) return &h->probe_form;
     if (!strcmp(name, "box_reduce")) return &h->box_reduce;
+    if (!strcmp(name, "reduce_bound")) return &h->reduce_bound;
+    if (!strcmp(name, "reduce_planes")) return &h->reduce_planes;
     if (!strcmp(name, "form")) return &h->form;
     if (!strcmp(name, "box_io")) return &h->box_io;
     if (!strcmp(name, "io_form")) return &h->io_form;
@@ -793,6 +823,7 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (!slot) return fail(TAMC_EINVAL, std::string("tamc_set_option: unknown option ") + (name ? name : "(null)"));
     if (slot == &h->form) return fail(TAMC_EINVAL, "form is read-only: the kernel the last MC call ran");
     if (slot == &h->io_form) return fail(TAMC_EINVAL, "io_form is read-only: how the last tamc_run moved its arrays");
+    if (slot == &h->reduce_planes) return fail(TAMC_EINVAL, "reduce_planes is read-only: planes of the box the last all-reduce moved");
     if (slot == &h->cfg.depth_hint) return fail(TAMC_EINVAL, "depth_hint is read-only: planes from the top face to the deepest stop of the last column-form call");
     if (slot == &h->cfg.gather_depth && (value < -1 || value > 4096)) return fail(TAMC_EINVAL, "gather_depth must be -1 (auto), 0 (all planes) or a number of planes");
     if (slot == &h->probe_form && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "probe_form must be -1, 0 or 1");

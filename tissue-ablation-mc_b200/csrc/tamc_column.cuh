@@ -510,18 +510,80 @@ __global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevG
     if (lane == 0 && depth > 0) atomicMax(cnt + CNT_DEPTH, (unsigned long long)depth);
 }
 
+// How deep can a packet of this call get?  The optical depth is tau = -log((x + 0.5) 2^-32) for a 32-bit x
+// (inttau2.f90:36 on one Philox word), so tau <= 33 ln 2 = 22.874 for EVERY packet, and a straight-down flight stops no
+// later than where its column's running optical depth passes that.  One thread per column of the z-fastest copy walks
+// down from the launch plane with the kernel's own chords until the sum passes 23; *out receives the largest number of
+// planes (from the top face, one spare) over the columns, nzg when some column never gets there.  Every rank holds the
+// same grid and gets the same number: the all-reduce (mcpolar.f90:173) moves only those planes of the box.
+__global__ void __launch_bounds__(256) k_column_bound(const DevGrid g, const ColGeom cg, const double *__restrict__ rkT, int *__restrict__ acc_max,
+                                                      unsigned int *__restrict__ done, int *__restrict__ out)
+{
+    extern __shared__ double s_dz[];
+    stage_column_steps(g, cg.nzp, s_dz);                               // ends with __syncthreads()
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int planes = 1;
+    if (c < cg.tw * cg.th) {
+        const double *col = rkT + (size_t)c * cg.nzp;
+        double acc = 0.;
+        planes = g.nzg;
+        int kz = g.cellk0 - 1;
+        bool found = false;
+        // four planes per 256-bit load, from the launch plane down (slots above it hold chord 0)
+        for (int gb = kz & ~3; gb >= cg.kz_lo && !found; gb -= 4) {
+            double r0, r1, r2, r3;
+            ldg256(col + gb, r0, r1, r2, r3);
+            const double r[4] = {r0, r1, r2, r3};
+#pragma unroll
+            for (int q = 3; q >= 0; --q) {
+                if (!found && gb + q <= g.cellk0 - 1) {
+                    acc += s_dz[gb + q] * r[q];
+                    kz = gb + q;
+                    if (acc >= 23.0) { planes = min(g.nzg, g.nzg - kz + 1); found = true; }
+                }
+            }
+        }
+        if (!found && cg.kz_lo > 0 && cg.deep) {
+            // (depth-limited upload and a column that needs more than the copied planes: go on in the caller's grid, so the
+            // answer never depends on how much this rank happened to copy)
+            const int dj = c / cg.tw, di = c - dj * cg.tw;
+            const double *q = cg.deep + ((long long)(cg.i0 + di) + (long long)cg.deep_sx * (cg.j0 + dj));
+            for (kz = cg.kz_lo - 1; kz >= 0; --kz) {
+                acc += s_dz[kz] * q[cg.deep_sxy * (kz + 1)];
+                if (acc >= 23.0) { planes = min(g.nzg, g.nzg - kz + 1); break; }
+            }
+        }
+    }
+    planes = __reduce_max_sync(0xffffffffu, planes);
+    if ((threadIdx.x & 31) == 0) atomicMax(acc_max, planes);
+    // the last block to finish hands the answer to the host (a plain store into page-locked memory) and resets the scratch
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        *out = atomicMax(acc_max, 0);
+        *acc_max = 0;
+        *done = 0u;
+        __threadfence_system();
+    }
+}
+
 // The tally under the beam's bounding box <-> a dense (tw, th, nzg) buffer.  In the shipped regime every deposit lies
 // in those columns, so the all-reduce (mcpolar.f90:173) only has to move them: 18 % of the grid for the reference's
 // 0.025 cm spot on a 0.06 cm face.  kUnpack = false: box -> dense; true: dense -> box.
+// kz0: only the planes kz >= kz0 travel (k_column_bound: nothing of this call lies deeper).
 template <bool kUnpack>
-__global__ void __launch_bounds__(256) k_box_copy(const DevGrid g, const ColGeom cg, double *__restrict__ dense)
+__global__ void __launch_bounds__(256) k_box_copy(const DevGrid g, const ColGeom cg, double *__restrict__ dense, int kz0)
 {
-    const size_t total = (size_t)cg.tw * cg.th * g.nzg;
+    const size_t total = (size_t)cg.tw * cg.th * (g.nzg - kz0);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
         const int di = (int)(t % cg.tw);
         const size_t r = t / cg.tw;
-        const int dj = (int)(r % cg.th), kz = (int)(r / cg.th);
+        const int dj = (int)(r % cg.th), kz = kz0 + (int)(r / cg.th);
         const size_t j = (size_t)(cg.i0 - 1 + di) + (size_t)g.nxg * ((size_t)(cg.j0 - 1 + dj) + (size_t)g.nyg * kz);
         if (kUnpack) g.jmean[j] = dense[t];
         else dense[t] = g.jmean[j];

@@ -35,9 +35,11 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0., -1, 0};
+    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0., -1, 0, 0};
     tamc::ColumnWorkspace colws;
     int reduce = 1;
+    int reduce_bound = 1;   // all-reduce only the planes k_column_bound proves reachable (column form; 0 = every plane of the box)
+    int reduce_planes = 0;  // read-only: planes of the box the last all-reduce moved (0 = no box reduce)
     int box_reduce = -1;    // shipped regime: all-reduce only the columns under the beam (-1 = auto, 0 = off, 1 = on)
     int form = -1;          // FORM_* of the last MC call
     int launch32 = 1;       // column form: fp32 first pass for the launch voxel (exact: redone in fp64 near voxel edges); 0 = off

@@ -31,6 +31,7 @@ struct LaunchCfg {
                         // PCIe ahead of the transport; -1 = auto: depth_hint + max(16, depth_hint / 2), 0 = all, > 0 = that many
                         // (rounded up to whole 32-plane tiles).  A packet that goes deeper reads the caller's grid directly.
     int depth_hint;     // planes from the top face to the deepest stop of the previous column-form call (0 = unknown)
+    int want_bound;     // set per call by the C-ABI layer: compute the depth bound of this call (k_column_bound) for the all-reduce
 };
 
 // Which kernel an MC call ran ("form" read-only option of tamc_get_option)
@@ -51,6 +52,13 @@ struct ColumnWorkspace {
     double *box_rk = nullptr;
     cudaEvent_t ev_gather0 = nullptr, ev_gather1 = nullptr;
     int last_kz_lo = 0;              // read-back: first plane (k - 1) the last gather copied (> 0: depth-limited)
+    // depth bound of the call (k_column_bound): one int in mapped page-locked memory, written by the kernel, read by the
+    // host once ev_bound has passed -- while the transport is still running
+    int *h_bound = nullptr, *d_bound = nullptr;
+    int *bound_scratch = nullptr;    // device: running maximum + finished-block counter of k_column_bound (both zero between calls)
+    cudaEvent_t ev_bound = nullptr, ev_gathered = nullptr;
+    cudaStream_t s_side = nullptr;   // a side stream, if the handle has one: the bound is computed beside the transport
+    bool bound_pending = false;
 };
 
 // shipped regime: the columns every deposit lies in, and the copy between them and a dense buffer
@@ -58,7 +66,7 @@ bool beam_box(const DevGrid &g, ColGeom &cg);
 // true when launch_transport would run the column form on the z-fastest copy (the only form that reads rhokap
 // solely through k_column_gather / k_column_finish)
 bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n);
-cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s);
+cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s, int kz0 = 0);
 cudaError_t launch_box_mirror(const DevGrid &g, const ColGeom &cg, double *dst, int num_sms, cudaStream_t s);
 
 // production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.

@@ -470,10 +470,10 @@ bool beam_box(const DevGrid &g, ColGeom &cg)
     return cg.tw >= 1 && cg.th >= 1;
 }
 
-cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s)
+cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s, int kz0)
 {
-    if (unpack) k_box_copy<true><<<num_sms * 8, 256, 0, s>>>(g, cg, dense);
-    else k_box_copy<false><<<num_sms * 8, 256, 0, s>>>(g, cg, dense);
+    if (unpack) k_box_copy<true><<<num_sms * 8, 256, 0, s>>>(g, cg, dense, kz0);
+    else k_box_copy<false><<<num_sms * 8, 256, 0, s>>>(g, cg, dense, kz0);
     return cudaGetLastError();
 }
 
@@ -585,6 +585,37 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     if (e0 != cudaSuccess) return e0;
     ws->last_kz_lo = cg.kz_lo;
     if (launches && gather) *launches += 1;
+    ws->bound_pending = false;
+    if (cfg.want_bound && gather) {
+        // the depth bound of this call for the all-reduce, from the copy the transport is about to read
+        if (!ws->h_bound) {
+            if (cudaHostAlloc((void **)&ws->h_bound, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer((void **)&ws->d_bound, ws->h_bound, 0) != cudaSuccess ||
+                cudaMalloc((void **)&ws->bound_scratch, 2 * sizeof(int)) != cudaSuccess ||
+                cudaMemsetAsync(ws->bound_scratch, 0, 2 * sizeof(int), s) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ws->ev_bound, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ws->ev_gathered, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                if (ws->h_bound) cudaFreeHost(ws->h_bound);
+                ws->h_bound = nullptr;
+            }
+        }
+        if (ws->h_bound) {
+            *ws->h_bound = 0;
+            // beside the transport when the handle has a side stream (it only reads the copy the gather just made)
+            cudaStream_t sb = ws->s_side ? ws->s_side : s;
+            if (sb != s) {
+                cudaEventRecord(ws->ev_gathered, s);
+                cudaStreamWaitEvent(sb, ws->ev_gathered, 0);
+            }
+            const int cols = cg.tw * cg.th;
+            k_column_bound<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, (const double *)ws->rkT, ws->bound_scratch,
+                                                                                          reinterpret_cast<unsigned int *>(ws->bound_scratch + 1), ws->d_bound);
+            cudaEventRecord(ws->ev_bound, sb);
+            ws->bound_pending = true;
+            if (launches) *launches += 1;
+        }
+    }
     const size_t smem = sizeof(double) * (size_t)cg.nzp;
     LaunchCfg c2 = cfg;
     c2.block = 256;
