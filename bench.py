@@ -418,7 +418,8 @@ def run_ours(args, cfg, name):
             "voxel_steps_per_s": vsteps_per_s,
             "voxel_steps_per_packet": res["voxel_steps"] / total_packets,
             "breakdown_ms_per_step": {"kernel": res["kernel_ms"] / args.steps, "allreduce": res["allreduce_ms"] / args.steps,
-                                      "wall_incl_l2_flush": res["wall_ms"] / args.steps},
+                                      "wall_incl_l2_flush": res["wall_ms"] / args.steps,
+                                      "allreduce_planes_of_box": int(t.get_option("reduce_planes"))},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rk.nbytes), "d2h_bytes_per_step": int(jm.nbytes),
                     "ms_per_step": 1e3 * float(e2e_s.item()) / args.steps, "parts_ms": e2e_parts,

@@ -137,7 +137,8 @@ int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global
  * depth the previous call's packets reached plus a margin ("gather_depth": -1 auto, 0 = every plane, n = n planes; the
  * rare packet that goes deeper reads the caller's array directly), and the download skips the rows that hold only zeros.
  * Options "box_io" (-1 auto, 0 = plain copies in sequence) and read-only "io_form" (bit0: columns-only download, bit1:
- * columns-first upload, bit2: depth-limited) and "depth_hint" (planes from the top face to the deepest stop of the last
+ * columns-first upload, bit2: depth-limited), "io_early" (bit0 / bit1: start the full-grid upload / the zero fill beside the
+ * column gather instead of behind it; measured slower, default 0) and "depth_hint" (planes from the top face to the deepest stop of the last
  * column-form call).
  * tamc_run alone uses the same download.  In that mode stats->h2d_ms / d2h_ms time only the column copies
  * that are not hidden behind the transport. */
