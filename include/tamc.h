@@ -188,7 +188,7 @@ int tamc_unpin_host(void *ptr);
  * "min_ctas", "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "column_tile" (shared-memory
  * tiles of the column form: -1 = auto, 0 = off, 10*ta + tb = ta planes of deposits and tb planes of
  * stop counts), "column_park" (regrouped column walk of a tiled call: -1 = auto from the previous call's
- * voxel-steps per packet, 0 = off, 1 = on), "launch32" (column form: fp32 first pass of the launch voxel, 1 = on), "reduce" (0 = skip the all-reduce), "reduce_bound" (column form: all-reduce only the planes of the box that a packet of the call can reach -- the optical depth of a packet is at most 33 ln 2, so every rank derives the same bound from its copy of the grid; 1 = on, 0 = every plane, 2 = compute it even without a communicator; read-only "reduce_planes" = the planes the last all-reduce moved), "box_reduce" / "box_io" (-1 = auto, 0 = move the
+ * voxel-steps per packet -- off in a process that holds a communicator, where it measured slower --, 0 = off, 1 = on), "launch32" (column form: fp32 first pass of the launch voxel, 1 = on), "reduce" (0 = skip the all-reduce), "reduce_bound" (column form: all-reduce only the planes of the box that a packet of the call can reach -- the optical depth of a packet is at most 33 ln 2, so every rank derives the same bound from its copy of the grid; 1 = on, 0 = every plane, 2 = compute it even without a communicator; read-only "reduce_planes" = the planes the last all-reduce moved), "box_reduce" / "box_io" (-1 = auto, 0 = move the
  * whole grid), "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 =
  * per-voxel-step address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the
  * last MC call ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on

@@ -412,6 +412,11 @@ static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t fir
     LaunchCfg cfg = h->cfg;
     // ("reduce_bound" = 2: also without a communicator, for diagnostics -- the answer lands in "reduce_planes")
     cfg.want_bound = ((h->comm && h->reduce && h->nranks > 1 && h->box_reduce != 0 && h->reduce_bound) || h->reduce_bound == 2) ? 1 : 0;
+    // Measured on 2-GPU boxes (profiles/README.md, tools/ab_multi3.sh): in a process that holds an NCCL communicator the
+    // regrouped column walk loses its edge -- 1.50-1.62 ms per 1e8 packets with rank-to-rank jitter (the all-reduce then
+    // waits for the slower rank) against 1.40 ms in lockstep for the tiled kernel, while single-process runs on the same
+    // box give 1.36 (regrouped) / 1.44 (tiled).  Cause not established; until it is, auto picks the tiled kernel there.
+    if (h->comm && h->nranks > 1 && cfg.column_park < 0) cfg.column_park = 0;
     h->colws.bound_pending = false;
     if (cfg.want_bound && !h->colws.s_side) {       // the bound kernel runs beside the transport, on a stream of its own
         if (cudaStreamCreateWithFlags(&h->colws.s_side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); h->colws.s_side = nullptr; }
