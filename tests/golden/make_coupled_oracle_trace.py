@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""CPU oracle version of tools/coupled_trace.py (photon loop on the same Philox ids + heat step): slow,
+"""Generator of tests/golden/coupled_shipped_events.json (test infrastructure: it runs the oracle).  CPU oracle version of tools/coupled_trace.py (photon loop on the same Philox ids + heat step): slow,
 one-off validation of where the shipped configuration first boils / ablates / diverges."""
 import os
 import sys
@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT]
 from oracle import oracle as orc  # noqa: E402
 

@@ -134,7 +134,7 @@ def test_shipped_configuration_coupled_trace_matches_oracle_fixture():
     """The reference's own run (res/input.params, 80^3, 125 000 packets per call, gaussian pulse) through the
     device-resident loop: temperatures at checkpoints and the iterations of the first boiling voxel, the first
     ablated voxel and the divergence of the explicit scheme equal the CPU oracle's (tests/golden/
-    coupled_shipped_events.json, produced by tools/coupled_oracle_trace.py in 5.5 CPU-minutes)."""
+    coupled_shipped_events.json, produced by tests/golden/make_coupled_oracle_trace.py in 5.5 CPU-minutes)."""
     import json
     import os
 
