@@ -102,3 +102,37 @@ def test_run_ranks_equals_sum_of_single_ranks():
     assert np.array_equal(res["jmean"], tot)
     assert res["stats"]["packets"] == 15000 and res["stats"]["voxel_steps"] == steps
     assert res["seconds"] > 0 and res["threads"] >= 1
+
+
+def test_depth_bound_from_the_32_bit_uniform():
+    """What the multi-rank all-reduce relies on (k_column_bound): with the production generator the
+    optical depth is tau = -log((x + 0.5) 2^-32) <= 33 ln 2 for every packet, so in the shipped regime no packet stops
+    deeper than where its column's running optical depth passes 23 -- checked on the oracle with heterogeneous grids
+    (ablated voxels, weak and strong layers), packet by packet."""
+    rng = np.random.default_rng(7)
+    for n, kappa in ((24, 900.0), (40, 300.0), (32, 1500.0)):
+        xmax = ymax = 0.03
+        zmax = 0.06
+        o = orc.Oracle(n, n, n, xmax, ymax, zmax)
+        rk = np.zeros((n + 2, n + 2, n + 2), order="F")
+        rk[1:-1, 1:-1, 1:-1] = kappa * rng.uniform(0.2, 1.8, size=(n, n, n))
+        rk[n // 2 - 2:n // 2 + 3, n // 2 - 2:n // 2 + 3, n - 3:n + 1] = 0.0          # a small crater under the beam
+        o.set_rhokap(rk)
+        o.seed_philox(4242, 0)
+        npk = 200000
+        rec = o.run(npk, records=True)["records"]
+        assert rec["deposit"].max() <= 33 * np.log(2.0) + 1e-12                      # deposit = tau for absorbed packets
+        # the bound exactly as the kernel forms it: chords of a straight-down flight, threshold 23, one spare plane
+        zf = o.faces()[2]
+        dz = np.diff(zf)
+        chord = dz.copy()
+        chord[n - 1] = (o.zmax - 1.0e-8 * (2.0 * o.zmax / n) + o.zmax) - zf[n - 1]   # launch plane: from zp0 down
+        cum = np.cumsum((rk[1:-1, 1:-1, 1:-1] * chord[None, None, :])[:, :, ::-1], axis=2)   # from the top face down
+        reach = (cum >= 23.0).argmax(axis=2) + 1                                    # planes needed per column
+        reach[cum[:, :, -1] < 23.0] = n
+        planes = np.minimum(n, reach + 1)
+        absorbed = rec["fate"] == 0
+        depth = n - rec["zcell"][absorbed] + 1                                       # planes from the top face to the stop
+        col_bound = planes[rec["xcell"][absorbed] - 1, rec["ycell"][absorbed] - 1]
+        assert np.all(depth <= col_bound - 1)
+        assert depth.max() >= 0.3 * col_bound[depth.argmax()]                         # not vacuous: 2e5 packets reach tau ~ 12 of 22.9
