@@ -13,8 +13,8 @@
  * cites the file:line it follows; -freal-4-real-8 promotion semantics from
  * src/Makefile:3).  What pins it instead: the hand-evaluated ran2 / first-packet
  * known answers of SURVEY.md section 8(c), an independent Python transliteration
- * (oracle/pyref.py) and the analytic invariants of the shipped regime
- * (tests/test_oracle_*.py).
+ * (oracle/pyref.py), the analytic invariants of the shipped regime and, for the
+ * scatter loop, Chandrasekhar's semi-infinite-slab reflectance (tests/test_oracle_*.py).
  */
 #ifndef TAMC_ORACLE_H
 #define TAMC_ORACLE_H

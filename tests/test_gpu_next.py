@@ -194,3 +194,36 @@ def test_argument_checks_for_the_options():
     with pytest.raises(tamc.TamcError):
         t.set_optics(None, 0.0, 0.9, flags=8)
     t.close()
+
+
+@pytest.mark.parametrize("omega", [0.5, 0.9, 0.99])
+def test_semi_infinite_slab_reflectance_matches_chandrasekhar_on_the_device(omega):
+    """The external pin of tests/test_oracle_next.py on the production kernels: isotropic scattering in a laterally
+    infinite (periodic), optically thick, index-matched slab reflects 1 - H(1) sqrt(1 - omega) of a normally incident
+    beam (Chandrasekhar's H-function).  4e5 packets, binomial error; the oracle on the same Philox ids gives the same
+    counts (z = 1.6, -0.1, -0.1 sigma for the three albedos)."""
+    import tamc
+    from oracle import oracle as orc
+    from tests.test_oracle_next import _chandrasekhar_H
+
+    npk = 400000
+    t = tamc.MCTransport(8, 8, 30, 0.01, 0.01, 0.03)
+    t.set_source_co2(0.004)
+    t.set_optics(tamc.gridset(0.01, 0.01, 0.03, 8, 8, 30, 1000.0)[3], omega, 0.0, flags=1 | PERIODIC)
+    o = orc.Oracle(8, 8, 30, 0.01, 0.01, 0.03)
+    o.gridset_uniform(1000.0)
+    o.set_optics(omega, 0.0)
+    o.set_spot(0.004)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_philox(SEED, 0)
+    ref = o.run(npk)["stats"]
+    want = 1.0 - _chandrasekhar_H(omega, 1.0) * np.sqrt(1.0 - omega)
+    for variant in (3, 0):
+        t.set_option("variant", variant)
+        t.run_async(npk, SEED, 0)
+        st = t.get_stats()
+        assert st["packets"] == npk and st["exits"][:4] == [0, 0, 0, 0]
+        got = st["exits"][5] / npk
+        assert abs(got - want) < 4.0 * np.sqrt(want * (1.0 - want) / npk), (variant, got, want)
+        assert abs(st["exits"][5] - ref["exits"][5]) <= 10 and abs(st["absorbed"] - ref["absorbed"]) <= 10
+    t.close()

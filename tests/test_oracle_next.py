@@ -170,3 +170,42 @@ def test_philox_mode_source_stream_is_separate():
     # same tau (word 3 of block 0) -> same total deposit per packet in the uniform stub regime
     assert np.allclose(a["deposit"], b["deposit"], rtol=1e-12)
     assert not np.allclose(a["xp"], b["xp"])
+
+
+def _chandrasekhar_H(omega, mu, nq=64):
+    """Chandrasekhar's H-function for isotropic scattering with single-scattering albedo omega, by iterating
+    1/H(mu) = sqrt(1 - omega) + (omega / 2) * int_0^1 mu' H(mu') / (mu + mu') dmu' on Gauss-Legendre nodes."""
+    x, w = np.polynomial.legendre.leggauss(nq)
+    x, w = 0.5 * (x + 1.0), 0.5 * w
+    H = np.ones(nq)
+    for _ in range(500):
+        Hn = 1.0 / (np.sqrt(1.0 - omega) + 0.5 * omega * ((w * x * H)[None, :] / (x[:, None] + x[None, :])).sum(axis=1))
+        if np.abs(Hn - H).max() < 1e-13:
+            H = Hn
+            break
+        H = Hn
+    return 1.0 / (np.sqrt(1.0 - omega) + 0.5 * omega * (w * x * H / (mu + x)).sum())
+
+
+@pytest.mark.parametrize("omega", [0.5, 0.9])
+def test_semi_infinite_slab_reflectance_matches_chandrasekhar(omega):
+    """An EXTERNAL pin of the scatter loop, the exit accounting and the periodic boundaries: for isotropic scattering
+    (hgg = 0) in a laterally infinite, optically thick slab with index-matched faces, the fraction of a normally
+    incident beam that comes back out of the top face is 1 - H(1) sqrt(1 - omega) (Chandrasekhar, Radiative
+    Transfer, 1960, section 38).  Periodic lateral boundaries make the grid that slab; 60 optical depths make it
+    semi-infinite (transmission < 1e-10).  Analog absorption: every packet carries unit weight, so the fraction of
+    packets that leave through +z estimates the reflectance with binomial error."""
+    n, npk = 30, 150000
+    o = orc.Oracle(8, 8, n, 0.01, 0.01, 0.03)
+    o.gridset_uniform(1000.0)                       # 0.06 cm x 1000 / cm = 60 optical depths
+    o.set_optics(omega, 0.0)
+    o.set_spot(0.004)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_ran2(0)
+    st = o.run(npk)["stats"]
+    assert st["exits"][:5] == [0, 0, 0, 0, 0]
+    want = 1.0 - _chandrasekhar_H(omega, 1.0) * np.sqrt(1.0 - omega)
+    got = st["exits"][5] / npk
+    assert abs(got - want) < 4.0 * np.sqrt(want * (1.0 - want) / npk), (got, want)
+    # H(1) itself against the tabulated value for omega = 0.5 (Chandrasekhar 1960, table XI: 1.2513)
+    assert _chandrasekhar_H(0.5, 1.0) == pytest.approx(1.2513, abs=2e-4)
