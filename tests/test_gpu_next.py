@@ -227,3 +227,33 @@ def test_semi_infinite_slab_reflectance_matches_chandrasekhar_on_the_device(omeg
         assert abs(got - want) < 4.0 * np.sqrt(want * (1.0 - want) / npk), (variant, got, want)
         assert abs(st["exits"][5] - ref["exits"][5]) <= 10 and abs(st["absorbed"] - ref["absorbed"]) <= 10
     t.close()
+
+
+def test_slab_benchmark_of_van_de_hulst_on_the_device():
+    """tests/test_oracle_next.py's anisotropic benchmark on the production kernels: slab of optical thickness 2, albedo
+    0.9, g = 0.75, index-matched: Rd = 0.09739, Tt = 0.66096 (van de Hulst 1980 / MCML 1995 table 1).  The oracle on the
+    same Philox ids gives -0.5 and +1.1 sigma at 4e5 packets."""
+    import tamc
+    from oracle import oracle as orc
+
+    npk = 400000
+    t = tamc.MCTransport(8, 8, 20, 0.01, 0.01, 0.01)
+    t.set_source_co2(0.004)
+    t.set_optics(tamc.gridset(0.01, 0.01, 0.01, 8, 8, 20, 100.0)[3], 0.9, 0.75, flags=1 | PERIODIC)
+    o = orc.Oracle(8, 8, 20, 0.01, 0.01, 0.01)
+    o.gridset_uniform(100.0)
+    o.set_optics(0.9, 0.75)
+    o.set_spot(0.004)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_philox(SEED, 0)
+    ref = o.run(npk)["stats"]
+    for variant in (3, 0, 2):
+        t.set_option("variant", variant)
+        t.run_async(npk, SEED, 0)
+        st = t.get_stats()
+        assert st["packets"] == npk and st["exits"][:4] == [0, 0, 0, 0]
+        for f, want in ((5, 0.09739), (4, 0.66096)):
+            got = st["exits"][f] / npk
+            assert abs(got - want) < 4.0 * np.sqrt(want * (1.0 - want) / npk), (variant, f, got, want)
+            assert abs(st["exits"][f] - ref["exits"][f]) <= 20
+    t.close()

@@ -209,3 +209,23 @@ def test_semi_infinite_slab_reflectance_matches_chandrasekhar(omega):
     assert abs(got - want) < 4.0 * np.sqrt(want * (1.0 - want) / npk), (got, want)
     # H(1) itself against the tabulated value for omega = 0.5 (Chandrasekhar 1960, table XI: 1.2513)
     assert _chandrasekhar_H(0.5, 1.0) == pytest.approx(1.2513, abs=2e-4)
+
+
+def test_slab_benchmark_of_van_de_hulst():
+    """A second EXTERNAL pin, for anisotropic scattering (the Henyey-Greenstein draw AND the direction update of
+    stokes.f90): the index-matched slab of optical thickness 2, albedo 0.9, g = 0.75 under a normally incident pencil
+    beam has total diffuse reflectance 0.09739 and total transmittance 0.66096 (van de Hulst, Multiple Light Scattering,
+    1980, adding-doubling tables; the validation case of Wang, Jacques & Zheng, MCML, Comput. Methods Programs Biomed.
+    47 (1995), table 1, which found 0.09734 +- 0.00035 and 0.66096 +- 0.00020).  Periodic lateral boundaries make the
+    grid that infinitely wide slab; unit-weight packets, binomial errors."""
+    npk = 400000
+    o = orc.Oracle(8, 8, 20, 0.01, 0.01, 0.01)
+    o.gridset_uniform(100.0)                          # 0.02 cm x 100 / cm
+    o.set_optics(0.9, 0.75)
+    o.set_spot(0.004)
+    o.set_flags(orc.FLAG_SCATTER | orc.FLAG_PERIODIC)
+    o.seed_ran2(0)
+    st = o.run(npk)["stats"]
+    assert st["exits"][:4] == [0, 0, 0, 0] and st["absorbed"] + st["exits"][4] + st["exits"][5] == npk
+    for got, want in ((st["exits"][5] / npk, 0.09739), (st["exits"][4] / npk, 0.66096)):
+        assert abs(got - want) < 4.0 * np.sqrt(want * (1.0 - want) / npk), (got, want)
