@@ -44,6 +44,15 @@ FORMS = {0: "k_transport_simple", 1: "k_transport_persistent", 2: "k_transport_e
          8: "k_transport_column_parked", 9: "k_transport_flight"}
 
 
+T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (rank 0 only): where the run is when something takes long"""
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -55,6 +64,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--also", default="homog200,phantom400,coupled_calls_shipped80,resident_loop_shipped80",
+                    help="comma-separated secondary measurements to run")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--option", action="append", default=[], help="name=value passed to tamc_set_option")
     return ap.parse_args()
@@ -402,10 +413,13 @@ def also_homog200(ctx, options, steps=10):
     per = 100_000_000
     for _ in range(3):
         t.run_async(per, SEED); t.sync()
+    log("also.homog200: warm")
     r = timed_steps(ctx, t, per, steps)
+    log("also.homog200: device-resident steps timed")
     jm = t.new_jmean()
     tamc.pin_host(jm)
     secs, parts, per_call = timed_e2e(ctx, t, c, [rk, rk_b], jm, per, steps)
+    log("also.homog200: e2e timed")
     out = {"workload": workload_desc("homog200", c, per * ctx.world) + " (weak: 1e8 per GPU)",
            "packets_per_s": per * ctx.world * steps / (r["dev_ms"] * 1e-3),
            "voxel_steps_per_s": r["voxel_steps"] / (r["dev_ms"] * 1e-3), "ms_per_step": r["dev_ms"] / steps,
@@ -418,6 +432,7 @@ def also_homog200(ctx, options, steps=10):
     if ctx.rank == 0:
         try:
             vs_rate = r["local_voxel_steps"] / steps / (r["local_kernel_ms"] / steps * 1e-3)
+            t.set_optics(rk, c["albedo"], c["hgg"], flags=c["flags"])      # the probe runs on the uniform grid the timed steps used
             t.set_option("probe_form", 1)
             t.roofline_probe(per, SEED)
             pms, psteps = t.roofline_probe(per, SEED)
@@ -542,7 +557,9 @@ def run_ours(args, cfg, name):
     except Exception:
         gpu_id = str(ctx.local)
 
+    log(f"set-up done: {name}, {total:.3g} packets per step over {world} rank(s)")
     parity = parity_check(ctx, t, cfg)
+    log(f"parity check: {parity.get('status')}")
 
     # ---- warm-up, then the timed device-resident steps
     for _ in range(max(args.warmup, 0)):
@@ -551,6 +568,7 @@ def run_ours(args, cfg, name):
     sampler = ClockSampler(gpu_id) if rank == 0 else None
     res = timed_steps(ctx, t, per_rank, args.steps)
     value = float(total) * args.steps / (res["dev_ms"] * 1e-3)
+    log(f"timed steps done: {value:.4g} packets/s")
     vsteps_per_s = res["voxel_steps"] / (res["dev_ms"] * 1e-3)
 
     # ---- e2e: the reference-facing call with host buffers (upload rhokap, run, download jmean)
@@ -566,21 +584,27 @@ def run_ours(args, cfg, name):
                       "around the K calls, barrier on both sides, max over ranks; bytes are the sum over ranks",
                "jmean_sum_per_packet": float(jm.sum()) / total}
     clocks = sampler.stop() if sampler else None      # sampled across both timed regions (device-resident + e2e)
+    log("e2e done")
 
     roofline = roofline_block(ctx, t, name, res, args.steps, per_rank)
+    log(f"roofline probe done: {roofline.get('frac_of_probe', roofline.get('probe_error'))}")
     ctx.barrier()
 
     also = {}
+    want_also = set(args.also.split(","))
     if not args.no_also:
         for key, fn in (("homog200", lambda: also_homog200(ctx, args.option)),
                         ("phantom400", lambda: also_phantom400(ctx, args.option)),
                         ("coupled_calls_shipped80", lambda: also_coupled_calls(ctx, args.option))):
+            if key not in want_also:
+                continue
             try:
                 also[key] = fn()
             except Exception as e:
                 also[key] = {"error": f"{type(e).__name__}: {e}"}
+            log(f"also.{key} done: {str(also[key])[:300]}")
             ctx.barrier()
-        if rank == 0:
+        if rank == 0 and "resident_loop_shipped80" in want_also:
             try:
                 also["resident_loop_shipped80"] = also_resident_loop(ctx)
             except Exception as e:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TAMC_VERSION 103
+#define TAMC_VERSION 104
 
 enum {
     TAMC_OK = 0,
@@ -200,6 +200,12 @@ int64_t tamc_get_option(tamc_handle h, const char *name);
  * per packet one 256-bit load per four voxels + at most two REDs); ms receives its device time,
  * steps the voxel-steps it stands for. */
 int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed, double *ms, int64_t *steps);
+/* Roofline probe of the scatter regime: records the voxel-index stream of `npackets` real packets of the current optics
+ * (production arithmetic, disk source, no boundary options) and replays it as memory operations only -- per voxel-step one
+ * 8-byte load of the voxel's opacity, per voxel left one fp64 RED into its tally, on the interleaved {rhokap, jmean}
+ * records the flight kernel uses -- i.e. the grid-lookup / L2-atomic rate this address stream admits with no transport
+ * arithmetic at all.  ms = device time of the replay (best of 3), steps / reds = loads / REDs it issued. */
+int tamc_trace_probe(tamc_handle h, int64_t npackets, int64_t seed, double *ms, int64_t *steps, int64_t *reds);
 /* The column form takes a packet's launch voxel from an fp32 first pass (hardware sqrt / sin / cos) and redoes it in the
  * production fp64 arithmetic (sourceph.f90:28-31,45-46) whenever the point lies within a proven error bound of a voxel
  * edge, so the voxel is always the fp64 one ("launch32" = 0 switches the first pass off).  This runs both passes over

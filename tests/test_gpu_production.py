@@ -272,6 +272,7 @@ def test_fresnel_index_matched_is_a_no_op_and_counts():
     base = tamc.configs.scaled("skin200", 48)
     n = 60000
     t0 = make_transport(base)
+    t0.set_option("flight", 0)          # the work-queue kernel, whose `ext` build carries the boundary options
     t0.run_async(n, SEED, 0)
     j0, s0 = t0.get_jmean(), t0.get_stats()
     t0.close()
@@ -349,13 +350,14 @@ def test_chi_square_full_size_layered_skin_200():
 
 
 def test_pool_kernel_with_early_opacity_fetch_at_400_cubed():
-    """Grids beyond L2 (phantom400: BASELINE config 4) take the pool kernel that fetches the next voxel's opacity one
-    loop pass early.  Same production arithmetic, so against the persistent kernel on the same packet ids the
-    counters are equal and the grid agrees to summation order."""
+    """Grids beyond L2 (phantom400: BASELINE config 4).  The work-queue kernel ("flight" = 0) fetches the next voxel's
+    opacity one loop pass early there: same production arithmetic as the persistent kernel, so on the same packet ids
+    the counters are equal and the grid agrees to summation order."""
     import tamc
 
     cfg = tamc.configs.CONFIGS["phantom400"]
     t = make_transport(cfg)
+    t.set_option("flight", 0)
     n = 4000
     res = {}
     for variant in (3, 1):
@@ -371,3 +373,29 @@ def test_pool_kernel_with_early_opacity_fetch_at_400_cubed():
     assert np.abs(a[nz] - b[nz]).max() <= 1e-9 * np.abs(b[nz]).max()
     assert res[3][1]["scatters"] > 100 * n
     t.close()
+
+
+def test_flight_kernel_against_oracle_at_400_cubed():
+    """BASELINE config 4 at its full grid size: the kernel a production call really runs there (the flight kernel, form 9)
+    against the ORACLE on the same Philox streams -- counters by fate exact, voxel-steps within the edge-flip slack, the
+    grid within the production tolerance of test_philox_exact (a deposit scale of one voxel's optical depth)."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["phantom400"]
+    rk = cfg["rhokap"]()
+    n = 1500
+    o = make_oracle(cfg, rk)
+    o.seed_philox(SEED, 0)
+    want = o.run(n)["stats"]
+    t = make_transport(cfg, rk)
+    t.run_async(n, SEED, 0)
+    jm, st = t.get_jmean(), t.get_stats()
+    assert t.get_option("form") == 9
+    t.close()
+    assert st["packets"] == n and st["scatters"] == want["scatters"] and st["absorbed"] == want["absorbed"]
+    assert st["exits"] == want["exits"]
+    assert abs(st["voxel_steps"] - want["voxel_steps"]) <= max(4, int(2e-6 * want["voxel_steps"]))
+    # 1.1e6 voxel-steps through 190 scatterings per packet: a path that differs from the oracle's in the 9th digit passes a
+    # voxel corner on the other side a few times, which moves a sliver of up to a few per cent of a voxel's optical depth
+    # between two neighbours (the same effect test_philox_exact bounds at 2e-2 for its shorter walks); the totals agree to 1e-7
+    compare_grids(jm, o.jmean, rtol=0.1, dep_scale=voxel_tau(cfg, rk), sum_rtol=1e-7)

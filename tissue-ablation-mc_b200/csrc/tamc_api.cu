@@ -230,7 +230,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_flush);
-    cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense);
+    cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense); cudaFree(h->colws.vox);
     if (h->colws.s_side) { cudaStreamSynchronize(h->colws.s_side); cudaStreamDestroy(h->colws.s_side); }
     if (h->colws.h_bound) cudaFreeHost(h->colws.h_bound);
     cudaFree(h->colws.bound_scratch);
@@ -339,6 +339,28 @@ extern "C" int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *i
     NC(n->CommInitRank(&h->comm, nranks, id, rank));
     h->nranks = nranks;
     h->rank = rank;
+    // Every rank must describe the same grid and the same reduction (mcpolar.f90:173 sums arrays of one size): compare a
+    // fingerprint of what shapes the all-reduce -- the max over the ranks of each word and of its negative must coincide.
+    if (nranks > 1) {
+        const double fp[16] = {(double)h->nxg, (double)h->nyg, (double)h->nzg, h->xmax, h->ymax, h->zmax, h->delta, h->spot,
+                               h->gauss_sigma, (double)h->reduce, (double)h->box_reduce, (double)h->reduce_bound,
+                               (double)TAMC_VERSION, 0., 0., 0.};
+        double *d_fp = nullptr;
+        CU(cudaMalloc(&d_fp, 32 * sizeof(double)));
+        double both[32];
+        for (int i = 0; i < 16; ++i) { both[i] = fp[i]; both[16 + i] = -fp[i]; }
+        CU(cudaMemcpyAsync(d_fp, both, sizeof(both), cudaMemcpyHostToDevice, h->stream));
+        const ncclResult_t r = n->AllReduce(d_fp, d_fp, 32, ncclDouble, ncclMax, h->comm, h->stream);
+        cudaError_t e = cudaMemcpyAsync(both, d_fp, sizeof(both), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(d_fp);
+        if (r != ncclSuccess) return fail(TAMC_ENCCL, "tamc_comm_init: fingerprint all-reduce failed");
+        if (e != cudaSuccess) return fail(TAMC_ECUDA, std::string("tamc_comm_init: ") + cudaGetErrorString(e));
+        for (int i = 0; i < 16; ++i)
+            if (both[i] != -both[16 + i])
+                return fail(TAMC_ESTATE, "tamc_comm_init: the ranks disagree on the grid, the source or the reduction options (word " +
+                                             std::to_string(i) + " of the fingerprint): every rank must set them identically before tamc_comm_init");
+    }
     return TAMC_OK;
 }
 
@@ -360,8 +382,11 @@ static int enqueue_reduce(tamc_handle h)
     if (h->comm && h->reduce && h->nranks > 1) {
         // mcpolar.f90:173: MPI_allREDUCE(jmean, jmeanGLOBAL, nxg*nyg*nzg, MPI_DOUBLE_PRECISION, MPI_SUM)
         // Shipped regime (no scatter loop): every flight is straight down, so the tally is zero outside the columns under
-        // the beam's bounding box on every rank -- reduce only those.  The rule depends on the optics flags, the grid and
-        // the spot, which all ranks share, never on the packet count or the kernel a rank happened to run.
+        // the beam's bounding box on every rank -- reduce only those, and only down to the depth bound of the grid.  The
+        // element count must be the same on every rank: it depends on the optics flags, the grid, the spot and the options
+        // "reduce" / "box_reduce" / "reduce_bound" (checked against the other ranks by tamc_comm_init and to be kept equal
+        // afterwards), and NOT on the packet count or the kernel form a rank ran: the bound is computed for every form
+        // (k_column_bound on the gathered copy, k_column_bound_resident otherwise) whenever the box reduce is on.
         const DevGrid g = make_grid(h);
         ColGeom cg;
         const bool box = h->box_reduce != 0 && !(h->flags & (TAMC_SCATTER | TAMC_FRESNEL)) && beam_box(g, cg) &&
@@ -411,7 +436,8 @@ static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t fir
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
     LaunchCfg cfg = h->cfg;
     // ("reduce_bound" = 2: also without a communicator, for diagnostics -- the answer lands in "reduce_planes")
-    cfg.want_bound = ((h->comm && h->reduce && h->nranks > 1 && h->box_reduce != 0 && h->reduce_bound) || h->reduce_bound == 2) ? 1 : 0;
+    const bool stub = !(h->flags & (TAMC_SCATTER | TAMC_FRESNEL));
+    cfg.want_bound = (stub && ((h->comm && h->reduce && h->nranks > 1 && h->box_reduce != 0 && h->reduce_bound) || h->reduce_bound == 2)) ? 1 : 0;
     // Measured on 2-GPU boxes (profiles/README.md, tools/ab_multi3.sh): in a process that holds an NCCL communicator the
     // regrouped column walk loses its edge -- 1.50-1.62 ms per 1e8 packets with rank-to-rank jitter (the all-reduce then
     // waits for the slower rank) against 1.40 ms in lockstep for the tiled kernel, while single-process runs on the same
@@ -807,6 +833,10 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "column")) return &h->cfg.column;
     if (!strcmp(name, "column_tile")) return &h->cfg.column_tile;
     if (!strcmp(name, "column_park")) return &h->cfg.column_park;
+    if (!strcmp(name, "flight")) return &h->cfg.flight;
+    if (!strcmp(name, "walk_min")) return &h->cfg.walk_min;
+    if (!strcmp(name, "flight_regs")) return &h->cfg.flight_regs;
+    if (!strcmp(name, "flight_inter")) return &h->cfg.flight_inter;
     if (!strcmp(name, "launch32")) return &h->launch32;
     if (!strcmp(name, "io_early")) return &h->io_early;
     if (!strcmp(name, "gather_depth")) return &h->cfg.gather_depth;
@@ -834,6 +864,9 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (slot == &h->probe_form && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "probe_form must be -1, 0 or 1");
     if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");
+    if (slot == &h->cfg.flight && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "flight must be -1 (auto), 0 or 1");
+    if (slot == &h->cfg.walk_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "walk_min must be in [1,32]");
+    if (slot == &h->cfg.flight_regs && value != 0 && (value < 2 || value > 4)) return fail(TAMC_EINVAL, "flight_regs must be 0, 2, 3 or 4");
     if (slot == &h->cfg.scatter_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "scatter_min must be in [1,32]");
     if (slot == &h->cfg.chunk && (value < 0 || value > 65536 || value % 32)) return fail(TAMC_EINVAL, "chunk must be 0 (auto) or a multiple of 32 up to 65536");
     if (slot == &h->cfg.min_ctas && (value < 2 || value > 3)) return fail(TAMC_EINVAL, "min_ctas must be 2 or 3");
@@ -873,6 +906,15 @@ extern "C" int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed
     if (int rc = check(h)) return rc;
     if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_roofline_probe: tamc_set_optics has not been called");
     const DevGrid g = make_grid(h);
+    {   // the probe draws its step counts from the opacity at the centre of the top face: it has to be positive
+        double rk0 = 0.;
+        const size_t at = (size_t)(h->nxg / 2) + (size_t)g.sx * (size_t)(h->nyg / 2) + (size_t)g.sxy * (size_t)h->nzg;
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(&rk0, h->d_rhokap + at, sizeof(double), cudaMemcpyDeviceToHost));
+        if (!(rk0 > 0.) || !(rk0 < 1e300))
+            return fail(TAMC_EINVAL, "tamc_roofline_probe: the resident grid has no positive opacity at the centre of the top face "
+                                     "(the probe's geometric step count is drawn from it)");
+    }
     CU(cudaMemsetAsync(h->d_jmean, 0, h->n_jmean * sizeof(double), h->stream));
     CU(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev[EV_K0], h->stream));
@@ -887,6 +929,69 @@ extern "C" int tamc_roofline_probe(tamc_handle h, int64_t nphotons, int64_t seed
     if (steps) *steps = (int64_t)cnt[CNT_STEPS];
     h->ran = false;
     return TAMC_OK;
+}
+
+extern "C" int tamc_trace_probe(tamc_handle h, int64_t npackets, int64_t seed, double *ms, int64_t *steps, int64_t *reds)
+{
+    if (int rc = check(h)) return rc;
+    if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_trace_probe: tamc_set_optics has not been called");
+    if (npackets < 1 || npackets > ((int64_t)1 << 26)) return fail(TAMC_EINVAL, "tamc_trace_probe: npackets must be in [1, 2^26]");
+    if ((h->flags & (TAMC_FRESNEL | TAMC_PERIODIC)) || h->gauss_sigma > 0.)
+        return fail(TAMC_EINVAL, "tamc_trace_probe: records the disk source without boundary options only");
+    const DevGrid g = make_grid(h);
+    int *d_counts = nullptr, *d_trace = nullptr;
+    long long *d_off = nullptr;
+    int rc = TAMC_OK;
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == TAMC_OK) rc = fail(TAMC_ECUDA, std::string("tamc_trace_probe: ") + what + ": " + cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    std::vector<int> counts((size_t)npackets);
+    std::vector<long long> off((size_t)npackets + 1);
+    const size_t nvox = h->n_jmean;
+    // ids far behind anything a run uses, so the probe never replays a production stream's packets twice in a bench
+    const uint64_t first = (uint64_t)1 << 50;
+    do {
+        if (!cu(cudaMalloc(&d_counts, (size_t)npackets * sizeof(int)), "cudaMalloc counts")) break;
+        if (!cu(cudaMalloc(&d_off, ((size_t)npackets + 1) * sizeof(long long)), "cudaMalloc offsets")) break;
+        if (!cu(launch_trace(g, npackets, (uint64_t)seed, first, nullptr, nullptr, d_counts, h->num_sms, h->stream), "count pass")) break;
+        if (!cu(cudaMemcpyAsync(counts.data(), d_counts, (size_t)npackets * sizeof(int), cudaMemcpyDeviceToHost, h->stream), "D2H counts")) break;
+        if (!cu(cudaStreamSynchronize(h->stream), "sync")) break;
+        long long tot = 0;
+        for (int64_t i = 0; i < npackets; ++i) { off[(size_t)i] = tot; tot += (counts[(size_t)i] + 3) & ~3; }
+        off[(size_t)npackets] = tot;
+        if (!cu(cudaMalloc(&d_trace, (size_t)(tot > 0 ? tot : 4) * sizeof(int)), "cudaMalloc trace")) break;
+        if (!cu(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream), "H2D offsets")) break;
+        if (!cu(launch_trace(g, npackets, (uint64_t)seed, first, d_off, d_trace, d_counts, h->num_sms, h->stream), "record pass")) break;
+        if (h->colws.vox_elems < nvox) {
+            cudaFree(h->colws.vox);
+            h->colws.vox = nullptr;
+            h->colws.vox_elems = 0;
+            if (!cu(cudaMalloc(&h->colws.vox, nvox * sizeof(double2)), "cudaMalloc vox")) break;
+            h->colws.vox_elems = nvox;
+        }
+        float best = 0.f;
+        unsigned long long cnt[CNT_N] = {};
+        for (int rep = 0; rep < 3; ++rep) {           // first pass warms the caches the way consecutive MC calls do
+            cu(launch_probe_trace(g, h->cfg, h->colws.vox, npackets, d_off, d_trace, h->d_cnt, h->num_sms, h->stream, true), "pack");
+            cu(cudaMemsetAsync(h->d_cnt, 0, CNT_N * sizeof(unsigned long long), h->stream), "clear counters");
+            cu(cudaEventRecord(h->ev[EV_K0], h->stream), "event");
+            cu(launch_probe_trace(g, h->cfg, h->colws.vox, npackets, d_off, d_trace, h->d_cnt, h->num_sms, h->stream, false), "replay");
+            cu(cudaEventRecord(h->ev[EV_K1], h->stream), "event");
+            cu(cudaStreamSynchronize(h->stream), "sync");
+            if (rc != TAMC_OK) break;
+            float t = 0.f;
+            cu(cudaEventElapsedTime(&t, h->ev[EV_K0], h->ev[EV_K1]), "elapsed");
+            if (rep == 0 || t < best) best = t;
+            cu(cudaMemcpy(cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost), "D2H counters");
+        }
+        if (ms) *ms = best;
+        if (steps) *steps = (int64_t)cnt[CNT_STEPS];
+        if (reds) *reds = (int64_t)cnt[CNT_SCATTERS];
+    } while (false);
+    cudaFree(d_counts); cudaFree(d_off); cudaFree(d_trace);
+    h->ran = false;
+    return rc;
 }
 
 extern "C" int tamc_flush_l2(tamc_handle h, uint64_t bytes)

@@ -571,6 +571,43 @@ __global__ void __launch_bounds__(256) k_column_bound(const DevGrid g, const Col
     }
 }
 
+// The same bound from the RESIDENT grid (reference layout), for calls that do not take the column form (small calls,
+// "column" = 0 / 2): the number of planes the all-reduce moves must not depend on which kernel a rank happened to run
+// -- ranks may differ in packet count -- only on the grid and the options every rank shares.  One thread per column,
+// neighbouring threads neighbouring x, so every plane is read in coalesced row segments.
+__global__ void __launch_bounds__(256) k_column_bound_resident(const DevGrid g, const ColGeom cg, int *__restrict__ acc_max,
+                                                               unsigned int *__restrict__ done, int *__restrict__ out)
+{
+    extern __shared__ double s_dz[];
+    stage_column_steps(g, cg.nzp, s_dz);                               // ends with __syncthreads()
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int planes = 1;
+    if (c < cg.tw * cg.th) {
+        const int dj = c / cg.tw, di = c - dj * cg.tw;
+        const double *q = g.rhokap + ((long long)(cg.i0 + di) + (long long)g.sx * (cg.j0 + dj));
+        double acc = 0.;
+        planes = g.nzg;
+        for (int kz = g.cellk0 - 1; kz >= 0; --kz) {
+            acc += s_dz[kz] * q[g.sxy * (kz + 1)];
+            if (acc >= 23.0) { planes = min(g.nzg, g.nzg - kz + 1); break; }
+        }
+    }
+    planes = __reduce_max_sync(0xffffffffu, planes);
+    if ((threadIdx.x & 31) == 0) atomicMax(acc_max, planes);
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        *out = atomicMax(acc_max, 0);
+        *acc_max = 0;
+        *done = 0u;
+        __threadfence_system();
+    }
+}
+
 // The tally under the beam's bounding box <-> a dense (tw, th, nzg) buffer.  In the shipped regime every deposit lies
 // in those columns, so the all-reduce (mcpolar.f90:173) only has to move them: 18 % of the grid for the reference's
 // 0.025 cm spot on a 0.06 cm face.  kUnpack = false: box -> dense; true: dense -> box.

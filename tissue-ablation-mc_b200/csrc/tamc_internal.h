@@ -32,10 +32,15 @@ struct LaunchCfg {
                         // (rounded up to whole 32-plane tiles).  A packet that goes deeper reads the caller's grid directly.
     int depth_hint;     // planes from the top face to the deepest stop of the previous column-form call (0 = unknown)
     int want_bound;     // set per call by the C-ABI layer: compute the depth bound of this call (k_column_bound) for the all-reduce
+    int flight;         // scatter loop: the flight kernel (tamc_flight.cuh) instead of the work-queue kernel; -1 = auto (on unless
+                        // Fresnel / periodic boundaries / the Gaussian beam are selected), 0 = off, 1 = on
+    int walk_min;       // flight kernel: the walk phase hands over to the event phase once fewer lanes than this are in flight
+    int flight_regs;    // flight kernel: 0 = auto, 2 / 3 / 4 = the 256-thread build for that many CTAs per SM
+    int flight_inter;   // flight kernel: interleaved {opacity, tally} voxel records; -1 = auto (grids beyond L2), 0 = off, 1 = on
 };
 
 // Which kernel an MC call ran ("form" read-only option of tamc_get_option)
-enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6, FORM_COLUMN_TILED = 7, FORM_COLUMN_PARKED = 8 };
+enum { FORM_SIMPLE = 0, FORM_PERSISTENT = 1, FORM_EXACT = 2, FORM_POOL = 3, FORM_TILE = 4, FORM_COLUMN = 5, FORM_COLUMN_RESIDENT = 6, FORM_COLUMN_TILED = 7, FORM_COLUMN_PARKED = 8, FORM_FLIGHT = 9 };
 
 // Device buffers of the column form, owned by the handle and grown on demand by launch_transport.
 struct ColumnWorkspace {
@@ -59,6 +64,9 @@ struct ColumnWorkspace {
     cudaEvent_t ev_bound = nullptr, ev_gathered = nullptr;
     cudaStream_t s_side = nullptr;   // a side stream, if the handle has one: the bound is computed beside the transport
     bool bound_pending = false;
+    // flight kernel (tamc_flight.cuh): the interleaved {rhokap, jmean} voxel records, rebuilt per MC call
+    double2 *vox = nullptr;
+    size_t vox_elems = 0;
 };
 
 // shipped regime: the columns every deposit lies in, and the copy between them and a dense buffer
@@ -86,5 +94,11 @@ cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, ui
 cudaError_t launch_selfcheck(const DevGrid &g, long long n, uint64_t seed, uint64_t first_id, unsigned long long *d_out, int num_sms,
                              cudaStream_t s);
 cudaError_t launch_fill(double *p, size_t n, double v, int num_sms, cudaStream_t s);
+// scatter-regime roofline probe: record the voxel-index stream of n packets (d_trace == nullptr: count the steps per
+// packet into d_counts), replay it as loads + REDs on the interleaved voxel records (pack = true: build them instead)
+cudaError_t launch_trace(const DevGrid &g, long long n, uint64_t seed, uint64_t first_id, const long long *d_off, int *d_trace,
+                         int *d_counts, int num_sms, cudaStream_t s);
+cudaError_t launch_probe_trace(const DevGrid &g, const LaunchCfg &cfg, double2 *vox, long long n, const long long *d_off, const int *d_trace,
+                               unsigned long long *d_cnt, int num_sms, cudaStream_t s, bool pack);
 
 }  // namespace tamc

@@ -19,6 +19,7 @@
 #include "tamc_internal.h"
 #include "tamc_column.cuh"
 #include "tamc_pool.cuh"
+#include "tamc_flight.cuh"
 #include "tamc_stub_tile.cuh"
 
 namespace tamc {
@@ -412,6 +413,122 @@ __global__ void __launch_bounds__(kTiled ? 1024 : 256) k_probe_column(const DevG
     if (keep == 123.456) cnt[CNT_N - 1] = 1ull;
 }
 
+// ---------------------------------------------------------------------------------------------
+// roofline probe of the scatter regime: the REAL voxel-index stream of a sample of packets, recorded once
+// (k_trace: production arithmetic, one packet per thread; pass 1 counts the voxel-steps per packet, pass 2 writes
+// the jmean index of every step) and then replayed as memory operations only (k_probe_trace): per voxel-step one
+// 8-byte load of the voxel record's opacity and, when the packet leaves the voxel, one fp64 RED into its tally --
+// the access pattern of the flight kernel (tamc_flight.cuh) on the same interleaved layout, with no transport
+// arithmetic.  The only extra traffic is the index stream itself, read 16 bytes (four steps) at a time.
+// ---------------------------------------------------------------------------------------------
+struct TraceTally {
+    int *out;            // null in the counting pass
+    long long pos;
+    int count;
+    __device__ __forceinline__ void begin() { count = 0; }
+    __device__ __forceinline__ void add(const FastPhoton &p, double)
+    {
+        if (out) out[pos + count] = p.jidx;
+        ++count;
+    }
+    __device__ __forceinline__ void flush() {}
+};
+
+__global__ void __launch_bounds__(256) k_trace(const DevGrid g, long long n, uint64_t seed, uint64_t first_id,
+                                               const long long *__restrict__ off, int *__restrict__ trace, int *__restrict__ counts)
+{
+    extern __shared__ double s_faces[];
+    const double *xf, *yf, *zf;
+    stage_faces(g, s_faces, xf, yf, zf);
+    const bool scatter_on = (g.flags & TAMC_SCATTER) != 0;
+    const LaunchConsts lc{g.zcur0, g.cellk0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        PhiloxRng rng;
+        rng.seed(seed, first_id + (uint64_t)i);
+        FastPhoton p;
+        adopt(g, lc, p, launch_fast(g, philox_block(g, rng.id_lo, rng.id_hi, 0u), scatter_on));
+        rng.blk = 1;
+        TraceTally tally;
+        tally.out = trace;
+        tally.pos = trace ? off[i] : 0;
+        tally.begin();
+        for (;;) {
+            const int r = voxel_step_fast<true>(g, xf, yf, zf, p, tally);
+            if (r == STEP_WALL) continue;
+            if (r == STEP_EXIT || !scatter_on) break;
+            const uint4 w = philox_block(g, rng);
+            if (!(unit_fast(w.x) < g.albedo)) break;
+            scatter_fast(g, p, unit_fast(w.y), unit_fast(w.z), fm::neglog_u32(w.w));
+        }
+        if (!trace) counts[i] = tally.count;
+        else for (int k = tally.count; k & 3; ++k) trace[tally.pos + k] = -1;       // pad to a multiple of four steps
+    }
+}
+
+template <bool kInter>
+__global__ void __launch_bounds__(256) k_probe_trace(const double *__restrict__ rkb, double *__restrict__ jmb, long long n,
+                                                     const long long *__restrict__ off, const int *__restrict__ trace,
+                                                     unsigned long long *__restrict__ cnt)
+{
+    constexpr int ws = kInter ? 2 : 1;            // doubles per voxel record: the flight kernel's two layouts (tamc_flight.cuh)
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    long long pos = 0, end = 0;           // this lane's slice of the index stream
+    long long next = 0, last = 0;         // warp-uniform: packets this warp owns
+    bool exhausted = false;
+    unsigned long long steps = 0ull, reds = 0ull;
+    double keep = 0.;
+    int cur = -1;
+    for (;;) {
+        // lanes whose packet is finished take the next one (64 packets per claim)
+        const unsigned idle = __ballot_sync(full, pos >= end);
+        if (idle) {
+            if (cur >= 0 && pos >= end) { atomicAdd(jmb + (size_t)cur * ws, 1.0); ++reds; cur = -1; }
+            if (!exhausted) {
+                if (next >= last) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(cnt + CNT_WORK, 64ull);
+                    base = __shfl_sync(full, base, 0);
+                    if ((long long)base >= n) exhausted = true;
+                    else { next = (long long)base; last = min(next + 64, n); }
+                }
+                if (!exhausted) {
+                    const int rank = __popc(idle & lt_mask);
+                    if (pos >= end && next + rank < last) { pos = off[next + rank]; end = off[next + rank + 1]; }
+                    next += min((long long)__popc(idle), last - next);
+                }
+            } else if (idle == full) {
+                break;
+            }
+        }
+        if (pos < end) {
+            const int4 q = *reinterpret_cast<const int4 *>(trace + pos);            // four voxel-steps of this packet
+            pos += 4;
+            const int ix[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = ix[k];
+                if (idx < 0) continue;                                              // padding
+                if (idx != cur) {                                                   // the packet left voxel `cur`
+                    if (cur >= 0) { atomicAdd(jmb + (size_t)cur * ws, 1.0); ++reds; }
+                    cur = idx;
+                }
+                keep += __ldg(rkb + (size_t)idx * ws);
+                ++steps;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        steps += __shfl_xor_sync(full, steps, o);
+        reds += __shfl_xor_sync(full, reds, o);
+    }
+    if (lane == 0) { atomicAdd(cnt + CNT_STEPS, steps); atomicAdd(cnt + CNT_SCATTERS, reds); }
+    if (keep == 123.456) cnt[CNT_N - 1] = 1ull;   // keeps the loads alive
+}
+
 __global__ void __launch_bounds__(256) k_fill(double *__restrict__ p, size_t n, double v)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -450,6 +567,8 @@ static cudaError_t launch_sized(K kernel, const LaunchCfg &cfg, size_t smem, lon
     kernel<<<grid, cfg.block, smem, s>>>(args...);
     return cudaGetLastError();
 }
+
+bool flight_interleaved(const LaunchCfg &cfg, size_t nvox);
 
 // Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
 // Bounding box of the launch voxels: launch_fast computes celli = int(xcur*inv_dx) + 1 with |xcur - xmax| <= R, and
@@ -572,6 +691,42 @@ bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n)
     return column_plan(g, cfg, n).use && cfg.column != 2;
 }
 
+// The depth bound of this call for the all-reduce (k_column_bound): computed on a side stream beside the transport when the
+// handle has one, handed to the host through one int in mapped page-locked memory.  from_copy: walk the z-fastest copy the
+// gather just made (the resident grid may still be on its way over PCIe); otherwise walk the resident grid.
+static void enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *ws, cudaStream_t s, int *launches, bool from_copy)
+{
+    if (!ws->h_bound) {
+        if (cudaHostAlloc((void **)&ws->h_bound, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void **)&ws->d_bound, ws->h_bound, 0) != cudaSuccess ||
+            cudaMalloc((void **)&ws->bound_scratch, 2 * sizeof(int)) != cudaSuccess ||
+            cudaMemsetAsync(ws->bound_scratch, 0, 2 * sizeof(int), s) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ws->ev_bound, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ws->ev_gathered, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            if (ws->h_bound) cudaFreeHost(ws->h_bound);
+            ws->h_bound = nullptr;
+        }
+    }
+    if (!ws->h_bound) return;
+    *ws->h_bound = 0;
+    cudaStream_t sb = ws->s_side ? ws->s_side : s;
+    if (sb != s) {
+        cudaEventRecord(ws->ev_gathered, s);
+        cudaStreamWaitEvent(sb, ws->ev_gathered, 0);
+    }
+    const int cols = cg.tw * cg.th;
+    if (from_copy)
+        k_column_bound<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, (const double *)ws->rkT, ws->bound_scratch,
+                                                                                      reinterpret_cast<unsigned int *>(ws->bound_scratch + 1), ws->d_bound);
+    else
+        k_column_bound_resident<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, ws->bound_scratch,
+                                                                                               reinterpret_cast<unsigned int *>(ws->bound_scratch + 1), ws->d_bound);
+    cudaEventRecord(ws->ev_bound, sb);
+    ws->bound_pending = true;
+    if (launches) *launches += 1;
+}
+
 // Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
 static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long long n, uint64_t seed, uint64_t first_id,
                                  unsigned long long *d_cnt, cudaStream_t s, int *launches, ColumnWorkspace *ws, bool gather,
@@ -586,36 +741,8 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     ws->last_kz_lo = cg.kz_lo;
     if (launches && gather) *launches += 1;
     ws->bound_pending = false;
-    if (cfg.want_bound && gather) {
-        // the depth bound of this call for the all-reduce, from the copy the transport is about to read
-        if (!ws->h_bound) {
-            if (cudaHostAlloc((void **)&ws->h_bound, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
-                cudaHostGetDevicePointer((void **)&ws->d_bound, ws->h_bound, 0) != cudaSuccess ||
-                cudaMalloc((void **)&ws->bound_scratch, 2 * sizeof(int)) != cudaSuccess ||
-                cudaMemsetAsync(ws->bound_scratch, 0, 2 * sizeof(int), s) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ws->ev_bound, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ws->ev_gathered, cudaEventDisableTiming) != cudaSuccess) {
-                cudaGetLastError();
-                if (ws->h_bound) cudaFreeHost(ws->h_bound);
-                ws->h_bound = nullptr;
-            }
-        }
-        if (ws->h_bound) {
-            *ws->h_bound = 0;
-            // beside the transport when the handle has a side stream (it only reads the copy the gather just made)
-            cudaStream_t sb = ws->s_side ? ws->s_side : s;
-            if (sb != s) {
-                cudaEventRecord(ws->ev_gathered, s);
-                cudaStreamWaitEvent(sb, ws->ev_gathered, 0);
-            }
-            const int cols = cg.tw * cg.th;
-            k_column_bound<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, (const double *)ws->rkT, ws->bound_scratch,
-                                                                                          reinterpret_cast<unsigned int *>(ws->bound_scratch + 1), ws->d_bound);
-            cudaEventRecord(ws->ev_bound, sb);
-            ws->bound_pending = true;
-            if (launches) *launches += 1;
-        }
-    }
+    if (cfg.want_bound && gather) enqueue_bound(g, cg, ws, s, launches, true);
+    else if (cfg.want_bound) enqueue_bound(g, cg, ws, s, launches, false);
     const size_t smem = sizeof(double) * (size_t)cg.nzp;
     LaunchCfg c2 = cfg;
     c2.block = 256;
@@ -685,6 +812,12 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     }
     if (launches) *launches += 1;
     tamc_packet_record *none = nullptr;
+    if (ws && !d_rec) {
+        ws->bound_pending = false;
+        ColGeom cgb;
+        // the all-reduce's depth bound must not depend on the kernel form (ranks may differ in packet count): same rule here
+        if (cfg.want_bound && !(g.flags & (TAMC_SCATTER | TAMC_FRESNEL)) && beam_box(g, cgb)) enqueue_bound(g, cgb, ws, s, launches, false);
+    }
 
     // Options outside the shipped path (Fresnel boundaries, periodic lateral boundaries, Gaussian beam) are compiled into
     // the thread-per-packet kernels and the `ext` build of the pool kernel only; the stub-regime and persistent kernels
@@ -710,6 +843,46 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
     if (pool) {
+        const bool ext = (g.flags & (TAMC_FRESNEL | TAMC_PERIODIC)) != 0 || gauss;      // options only the `ext` pool build carries
+        if (ws && cfg.flight != 0 && !ext) {
+            // flight kernel (tamc_flight.cuh): interleaved voxel records built before, tally written back after
+            const size_t nvox = (size_t)g.nxg * g.nyg * g.nzg;
+            if (ws->vox_elems < nvox) {
+                cudaFree(ws->vox);
+                ws->vox = nullptr;
+                ws->vox_elems = 0;
+                cudaError_t e = cudaMalloc(&ws->vox, nvox * sizeof(double2));
+                if (e != cudaSuccess) return e;
+                ws->vox_elems = nvox;
+            }
+            // interleaved {opacity, tally} records once the grids exceed L2 (one sector per visited voxel instead of two);
+            // while they fit, separate arrays: the REDs under a narrow beam must not share sectors with the loads
+            const bool inter = flight_interleaved(cfg, nvox);
+            double *voxd = reinterpret_cast<double *>(ws->vox);
+            if (inter) k_vox_pack<<<cfg.num_sms * 8, 256, 0, s>>>(g, ws->vox);
+            else k_rk_compact<<<cfg.num_sms * 8, 256, 0, s>>>(g, voxd);
+            const int chunk = cfg.chunk > 0 ? cfg.chunk : 64;
+            const int walk_min = cfg.walk_min < 1 ? 1 : (cfg.walk_min > 32 ? 32 : cfg.walk_min);
+            const size_t fsmem = ((smem + 7) & ~(size_t)7) + (size_t)(256 / 32) * CNT_N * sizeof(unsigned long long) + 2 * 256 * sizeof(double);
+            LaunchCfg c2 = cfg;
+            c2.block = 256;
+            cudaError_t e;
+            const int regs = cfg.flight_regs ? cfg.flight_regs : (inter ? 2 : 3);
+            if (inter) {
+                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+                else e = launch_sized(k_transport_flight<256, 3, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+            } else {
+                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+                else e = launch_sized(k_transport_flight<256, 3, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+            }
+            if (e != cudaSuccess) return e;
+            if (inter) k_vox_unpack<<<cfg.num_sms * 8, 256, 0, s>>>(g, ws->vox);
+            if (launches) *launches += inter ? 2 : 1;
+            if (form) *form = FORM_FLIGHT;
+            return cudaGetLastError();
+        }
         // work-queue regrouping: faces + one 64-packet pool per warp in shared memory
         int chunk = cfg.chunk > 0 ? cfg.chunk : 64;
         // grids beyond L2 (400^3: 1 GB): the walk waits on DRAM for every opacity (ncu: long scoreboard 3.5 per issue) --
@@ -856,6 +1029,49 @@ cudaError_t launch_probe(const DevGrid &g, const LaunchCfg &cfg, long long n, ui
         return cudaGetLastError();
     }
     return launch_sized(k_probe, c2, 0, n, s, g, n, seed, disk_r_vox, d_cnt);
+}
+
+// record / replay of the voxel-index stream (see k_trace)
+cudaError_t launch_trace(const DevGrid &g_in, long long n, uint64_t seed, uint64_t first_id, const long long *d_off, int *d_trace,
+                         int *d_counts, int num_sms, cudaStream_t s)
+{
+    DevGrid g = g_in;
+    for (int r = 0; r < 10; ++r) {
+        g.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        g.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    const long long want = (n + 255) / 256;
+    const int grid = (int)(want < (long long)num_sms * 8 ? want : (long long)num_sms * 8);
+    k_trace<<<grid, 256, faces_bytes(g), s>>>(g, n, seed, first_id, d_off, d_trace, d_counts);
+    return cudaGetLastError();
+}
+
+// the layout rule of the flight kernel: interleaved {opacity, tally} records once the grids exceed L2
+bool flight_interleaved(const LaunchCfg &cfg, size_t nvox)
+{
+    if (cfg.flight_inter >= 0) return cfg.flight_inter != 0;
+    int dev = 0, l2 = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+    return 16. * (double)nvox > 2. * (double)l2;
+}
+
+cudaError_t launch_probe_trace(const DevGrid &g, const LaunchCfg &cfg, double2 *vox, long long n, const long long *d_off, const int *d_trace,
+                               unsigned long long *d_cnt, int num_sms, cudaStream_t s, bool pack)
+{
+    const bool inter = flight_interleaved(cfg, (size_t)g.nxg * g.nyg * g.nzg);
+    double *voxd = reinterpret_cast<double *>(vox);
+    if (pack) {
+        if (inter) k_vox_pack<<<num_sms * 8, 256, 0, s>>>(g, vox);
+        else {
+            k_rk_compact<<<num_sms * 8, 256, 0, s>>>(g, voxd);
+            cudaMemsetAsync(g.jmean, 0, sizeof(double) * (size_t)g.nxg * g.nyg * g.nzg, s);
+        }
+        return cudaGetLastError();
+    }
+    if (inter) k_probe_trace<true><<<num_sms * 6, 256, 0, s>>>(voxd, voxd + 1, n, d_off, d_trace, d_cnt);
+    else k_probe_trace<false><<<num_sms * 6, 256, 0, s>>>(voxd, g.jmean, n, d_off, d_trace, d_cnt);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill(double *p, size_t n, double v, int num_sms, cudaStream_t s)

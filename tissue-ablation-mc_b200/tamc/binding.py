@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "tamc_get_option": (i64, [p, C.c_char_p]),
         "tamc_roofline_probe": (i, [p, i64, i64, C.POINTER(d), C.POINTER(i64)]),
         "tamc_selfcheck_launch": (i, [p, i64, i64, C.POINTER(i64), C.POINTER(i64)]),
+        "tamc_trace_probe": (i, [p, i64, i64, C.POINTER(d), C.POINTER(i64), C.POINTER(i64)]),
         "tamc_flush_l2": (i, [p, C.c_uint64]),
         "tamc_heat_init": (i, [p, C.POINTER(HeatParams), C.POINTER(d)]),
         "tamc_heat_step": (i, [p, i64]),
@@ -129,7 +130,7 @@ EXPORTS = [
     "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_source_gaussian", "tamc_set_optics", "tamc_run", "tamc_run_optics", "tamc_run_async",
     "tamc_sync", "tamc_get_jmean", "tamc_get_stats", "tamc_seek", "tamc_run_replay", "tamc_run_records",
     "tamc_comm_unique_id", "tamc_comm_init", "tamc_stream", "tamc_jmean_device", "tamc_rhokap_device",
-    "tamc_pin_host", "tamc_unpin_host", "tamc_set_option", "tamc_get_option", "tamc_roofline_probe", "tamc_selfcheck_launch",
+    "tamc_pin_host", "tamc_unpin_host", "tamc_set_option", "tamc_get_option", "tamc_roofline_probe", "tamc_selfcheck_launch", "tamc_trace_probe",
     "tamc_flush_l2", "tamc_last_error", "tamc_version", "tamc_device_count",
     "tamc_heat_init", "tamc_heat_step", "tamc_coupled_loop", "tamc_heat_array", "tamc_heat_scalar",
 ]
@@ -352,6 +353,16 @@ class MCTransport:
         ms, steps = C.c_double(0), C.c_int64(0)
         _ck(self.L.tamc_roofline_probe(self.h, int(nphotons), int(seed), C.byref(ms), C.byref(steps)))
         return ms.value, steps.value
+
+    def trace_probe(self, npackets, seed=1):
+        """Scatter-regime roofline probe (tamc_trace_probe): the recorded voxel-index stream replayed as loads + REDs."""
+        ms, steps, reds = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        _ck(self.L.tamc_trace_probe(self.h, int(npackets), int(seed), C.byref(ms), C.byref(steps), C.byref(reds)))
+        return {"ms": ms.value, "voxel_steps": steps.value, "reds": reds.value, "packets": int(npackets),
+                "voxel_steps_per_s": steps.value / (ms.value * 1e-3) if ms.value > 0 else 0.0,
+                "what": "grid-lookup / L2-atomic roofline of this workload: the voxel-index stream of real packets (recorded once), replayed "
+                        "as one 8-byte opacity load per voxel-step + one fp64 RED per voxel left, on the layout the kernel itself uses (separate arrays while the grids fit L2, interleaved records beyond), "
+                        "no transport arithmetic"}
 
     def selfcheck_launch(self, n, seed=1):
         """(draws the fp32 launch-voxel pass handed to fp64, draws where it kept a different voxel -- must be 0)."""
