@@ -148,9 +148,24 @@ def _stub_worker(rank, world, port, out):
         assert st["allreduce_ms"] > 0
         # the column form on the z-fastest copy derives how deep a packet can get (tau <= 33 ln 2; 1.02 per voxel here:
         # 23 voxels + one spare) and the all-reduce moves only those planes of the box
-        want = 0 if box == 0 else (24 if (column == 1 and bound) else 80)
+        # ... for EVERY kernel form (the bound comes from the gathered copy or from the resident grid): the element count of
+        # the all-reduce must not depend on the form a rank happened to run
+        want = 0 if box == 0 else (24 if bound else 80)
         assert t.get_option("reduce_planes") == want, (column, box, bound, t.get_option("reduce_planes"))
         grids.append(jm.copy())
+    # ranks that differ in packet count, straddling the 2^20 threshold of the column form: rank 0 takes the column form,
+    # rank 1 the step-by-step kernel, and both must pass NCCL the same count (explicit id ranges, no overlap)
+    for name, value in (("column", -1), ("box_reduce", -1), ("reduce_bound", 1)):
+        t.set_option(name, value)
+    n0, n1 = (1 << 20) + 1000, (1 << 20) - 1000
+    t.run_async(n0 if rank == 0 else n1, 7, 0 if rank == 0 else n0)
+    mixed = t.get_jmean()
+    forms = torch.tensor([t.get_option("form")], device="cuda")
+    both = [torch.zeros_like(forms) for _ in range(world)]
+    dist.all_gather(both, forms)
+    assert int(both[0]) in (5, 7, 8) and int(both[1]) in (1, 4), [int(b) for b in both]
+    assert t.get_option("reduce_planes") == 24
+    grids.append(mixed.copy())
     np.save(f"{out}.{rank}.npy", np.stack(grids))
     dist.barrier()
     t.close()
@@ -180,5 +195,10 @@ def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
     one = t.get_jmean()
     t.close()
     compare_grids(a[0], a[1], rtol=1e-12)               # same kernel, box vs whole-grid reduction (atomics order differs)
-    for g in a:
+    for g in a[:-1]:
         compare_grids(g, one, rtol=1e-10)
+    t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=0)
+    t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
+    t.run_async(1 << 21, 7, 0)
+    compare_grids(a[-1], t.get_jmean(), rtol=1e-10)     # ranks of different packet counts / kernel forms
+    t.close()
