@@ -28,6 +28,11 @@ import sys
 import tempfile
 import time
 
+# NCCL plumbing, before anything initialises NCCL in this process (libtamc sets the same defaults, tamc_api.cu nccl_api()):
+# with NVLS / cuMem-backed communicator buffers the one-CTA-per-SM stub-regime kernels measured 10-30 % slower on 2 x B200
+os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+os.environ.setdefault("NCCL_CUMEM_ENABLE", "0")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "tissue-ablation-mc_b200")
 for _p in (ROOT, PKG):
@@ -266,7 +271,7 @@ class Ctx:
         return t.tolist()
 
 
-def make_transport(ctx, cfg, rk, options):
+def make_transport(ctx, cfg, rk, options, root_io=0):
     import tamc
     from tamc import dist as tdist
 
@@ -275,6 +280,8 @@ def make_transport(ctx, cfg, rk, options):
     for kv in options:
         k, v = kv.split("=")
         t.set_option(k, int(v))
+    if root_io:
+        t.set_option("root_io", 1)                # before comm_init: it shapes the collectives of every call
     t.set_optics(rk, cfg["albedo"], cfg["hgg"], flags=cfg["flags"])
     if ctx.world > 1:
         t.comm_init(ctx.world, ctx.rank, tdist.broadcast_unique_id(tamc.comm_unique_id, ctx.dist, ctx.dev))
@@ -429,6 +436,18 @@ def also_homog200(ctx, options, steps=10):
            "e2e_ms_by_grid": {"uniform": 1e3 * statistics.mean(per_call[0::2]), "crater": 1e3 * statistics.mean(per_call[1::2])},
            "e2e_parts_ms": parts, "io_form": int(t.get_option("io_form")),
            "note": "e2e alternates two opacity grids (uniform / ablated crater under the beam), so the depth-limited upload cannot coast"}
+    if ctx.world > 1:
+        # the same end-to-end loop with only rank 0 moving host arrays ("root_io": rhokap broadcast over NVLink, one download)
+        t2 = make_transport(ctx, c, rk, options, root_io=1)
+        for _ in range(2):
+            t2.run_async(per, SEED); t2.sync()
+        secs2, parts2, _ = timed_e2e(ctx, t2, c, [rk, rk_b], jm, per, steps)
+        out["e2e_root_io_packets_per_s"] = per * ctx.world * steps / secs2
+        out["e2e_root_io_ms_per_step"] = 1e3 * secs2 / steps
+        out["e2e_root_io_parts_ms"] = parts2
+        out["e2e_root_io_form"] = int(t2.get_option("io_form"))
+        t2.close()
+        log("also.homog200: root_io e2e timed")
     if ctx.rank == 0:
         try:
             vs_rate = r["local_voxel_steps"] / steps / (r["local_kernel_ms"] / steps * 1e-3)
@@ -583,6 +602,15 @@ def run_ours(args, cfg, name):
                       "two opacity grids alternating call by call (layered skin / the same with an ablated crater); host clock "
                       "around the K calls, barrier on both sides, max over ranks; bytes are the sum over ranks",
                "jmean_sum_per_packet": float(jm.sum()) / total}
+        if world > 1:
+            t_root = make_transport(ctx, cfg, rk, args.option, root_io=1)
+            t_root.run_async(min(per_rank, 1_000_000), SEED); t_root.sync()
+            secs_r, parts_r, _ = timed_e2e(ctx, t_root, cfg, [rk, rk_b], jm, per_rank, args.steps)
+            e2e["root_io"] = {"value": float(total) * args.steps / secs_r, "ms_per_step": 1e3 * secs_r / args.steps, "parts_ms": parts_r,
+                              "h2d_bytes_per_step": int(rk.nbytes), "d2h_bytes_per_step": int(jm.nbytes),
+                              "what": "the same loop with tamc_set_option(root_io, 1): only rank 0's rhokap is uploaded (ncclBroadcast to the "
+                                      "other GPUs) and only rank 0's jmeanGLOBAL is written"}
+            t_root.close()
     clocks = sampler.stop() if sampler else None      # sampled across both timed regions (device-resident + e2e)
     log("e2e done")
 

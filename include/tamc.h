@@ -240,7 +240,8 @@ enum {   /* tamc_heat_array ids; arrays are Fortran column-major fp64 as the ref
 enum {   /* tamc_heat_scalar ids */
     TAMC_HEAT_S_DELT = 0, TAMC_HEAT_S_TIME, TAMC_HEAT_S_TOTAL_TIME, TAMC_HEAT_S_PULSELENGTH, TAMC_HEAT_S_REALPULSELENGTH,
     TAMC_HEAT_S_LASERON, TAMC_HEAT_S_PULSECOUNT, TAMC_HEAT_S_REPETITIONCOUNT, TAMC_HEAT_S_LASER_FLAG, TAMC_HEAT_S_QVAPOR,
-    TAMC_HEAT_S_PWR, TAMC_HEAT_S_COUNTER
+    TAMC_HEAT_S_PWR, TAMC_HEAT_S_COUNTER,
+    TAMC_HEAT_S_NEGATIVE_TEMP /* 1 once a temperature went negative: where the reference calls mpi_abort (3dFD.f90:179-182) */
 };
 
 /* initThermalCoeff (3dFD.f90:233-309) + the driver's temperature boundary set-up and total_time
@@ -250,6 +251,10 @@ int tamc_heat_init(tamc_handle h, const tamc_heat_params *p, double *delt);
 /* mcpolar.f90:174-182 on the resident arrays: the tally left by the last MC call, scaled on the fly, heat_sim_3D
  * (3dFD.f90:21-230, single-rank semantics), Arrhenius (:424-466), setupThermalCoeff (:312-361, which
  * rewrites the resident rhokap for the next MC call). */
+/* Asynchronous (enqueued on the handle's stream, nothing is read back): a driver that steps with tamc_run_async +
+ * tamc_heat_step must poll tamc_heat_scalar(TAMC_HEAT_S_NEGATIVE_TEMP) for the reference's abort condition
+ * (tamc_coupled_loop does, and returns an error).  The step swaps the resident opacity buffer with its successor: a pointer
+ * obtained from tamc_rhokap_device() before the call refers to the PREVIOUS opacity afterwards -- query it again. */
 int tamc_heat_step(tamc_handle h, int64_t nphotons_times_numproc);
 /* The whole `do while(time <= total_time)` loop (mcpolar.f90:148-186): MC call, all-reduce, heat step,
  * property update, with nothing crossing PCIe.  max_iterations < 0 = run to total_time. */

@@ -153,11 +153,12 @@ def _stub_worker(rank, world, port, out):
         want = 0 if box == 0 else (24 if bound else 80)
         assert t.get_option("reduce_planes") == want, (column, box, bound, t.get_option("reduce_planes"))
         grids.append(jm.copy())
-    # ranks that differ in packet count, straddling the 2^20 threshold of the column form: rank 0 takes the column form,
+    # ranks that differ in packet count, straddling the threshold of the column form (narrow beam: 8 x 148 x columns x tile
+    # planes = 4.1e6 packets): rank 0 takes the column form,
     # rank 1 the step-by-step kernel, and both must pass NCCL the same count (explicit id ranges, no overlap)
     for name, value in (("column", -1), ("box_reduce", -1), ("reduce_bound", 1)):
         t.set_option(name, value)
-    n0, n1 = (1 << 20) + 1000, (1 << 20) - 1000
+    n0, n1 = 4_400_000, 1_000_000
     t.run_async(n0 if rank == 0 else n1, 7, 0 if rank == 0 else n0)
     mixed = t.get_jmean()
     forms = torch.tensor([t.get_option("form")], device="cuda")
@@ -199,6 +200,6 @@ def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
         compare_grids(g, one, rtol=1e-10)
     t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=0)
     t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
-    t.run_async(1 << 21, 7, 0)
+    t.run_async(5_400_000, 7, 0)
     compare_grids(a[-1], t.get_jmean(), rtol=1e-10)     # ranks of different packet counts / kernel forms
     t.close()

@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +45,7 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGetVersion) GetVersion = nullptr;
@@ -55,6 +57,13 @@ static NcclApi *nccl_api()
     static bool tried = false;
     if (tried) return api.so ? &api : nullptr;
     tried = true;
+    // Measured on 2 x B200 (profiles/README.md, round 2): once a communicator with NVLS (NVLink SHARP multicast) and
+    // cuMem-backed buffers exists in the process, the one-CTA-per-SM stub-regime kernels run 10-30 % slower with
+    // rank-to-rank jitter (k_transport_column_parked 1.30 -> 1.43-1.71 ms per 1e8 packets); with both off they run at
+    // their single-process speed.  The tally all-reduce is a few MB to 512 MB once per MC call and does not need either,
+    // so they are switched off unless the caller's environment says otherwise (read by NCCL at its first use in the process).
+    setenv("NCCL_NVLS_ENABLE", "0", 0);
+    setenv("NCCL_CUMEM_ENABLE", "0", 0);
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {
         api.so = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -62,9 +71,9 @@ static NcclApi *nccl_api()
     }
     if (!api.so) return nullptr;
 #define BIND(f) api.f = reinterpret_cast<decltype(api.f)>(dlsym(api.so, "nccl" #f))
-    BIND(GetUniqueId); BIND(CommInitRank); BIND(AllReduce); BIND(CommDestroy); BIND(GetErrorString); BIND(GetVersion);
+    BIND(GetUniqueId); BIND(CommInitRank); BIND(AllReduce); BIND(Broadcast); BIND(CommDestroy); BIND(GetErrorString); BIND(GetVersion);
 #undef BIND
-    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.Broadcast || !api.CommDestroy) {
         dlclose(api.so);
         api.so = nullptr;
         return nullptr;
@@ -177,6 +186,13 @@ extern "C" int tamc_init(int device, int nxg, int nyg, int nzg, double xmax, dou
     // the snap `face -+ delta` must move the position off the face (inttau2.f90:142-166)
     if (2. * zmax + delta == 2. * zmax || 2. * xmax + delta == 2. * xmax || 2. * ymax + delta == 2. * ymax)
         return fail(TAMC_EINVAL, "tamc_init: delta is below the fp64 resolution of the face coordinates");
+    // ... and land in the adjacent voxel: the production kernels re-index the crossed axis by +-1 (the reference re-derives
+    // the voxel from the position, inttau2.f90:190-239), which is the same thing only while delta is a small part of an edge
+    {
+        const double wmin = fmin(fmin(2. * xmax / nxg, 2. * ymax / nyg), 2. * zmax / nzg);
+        if (!(delta < 1e-3 * wmin))
+            return fail(TAMC_EINVAL, "tamc_init: delta must stay below 1e-3 of the smallest voxel edge (the reference uses 1e-8 of it, mcpolar.f90:112)");
+    }
 
     CU(cudaSetDevice(device));
     tamc_context *c = new tamc_context();
@@ -238,7 +254,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     if (h->colws.ev_gathered) cudaEventDestroy(h->colws.ev_gathered);
     if (h->s_up) { cudaStreamSynchronize(h->s_up); cudaStreamDestroy(h->s_up); }
     if (h->s_dn) { cudaStreamSynchronize(h->s_dn); cudaStreamDestroy(h->s_dn); }
-    cudaFree(h->d_zero); cudaFree(h->d_box_rk);
+    cudaFree(h->d_zero); cudaFree(h->d_box_rk); cudaFree(h->d_path);
     for (int i = 0; i < EV_N; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -281,16 +297,28 @@ static int check_optics(tamc_handle h, const double *rhokap, double albedo, doub
     return TAMC_OK;
 }
 
+// root_io: after an overlapped columns-first call only rank 0 holds the new opacity grid in full (the other GPUs got the
+// beam's columns, all that call read).  The next use of the RESIDENT grid -- a call without a new rhokap, a kernel form
+// that walks the resident grid, the heat step -- first brings the other ranks up to date over NVLink.  The flag is set and
+// cleared by the same calls on every rank, so the broadcast stays collective.
+static int sync_resident(tamc_handle h)
+{
+    if (!h->resident_behind) return TAMC_OK;
+    h->resident_behind = false;
+    if (h->comm && h->nranks > 1)
+        NC(nccl_api()->Broadcast(h->d_rhokap, h->d_rhokap, h->n_rhokap, ncclDouble, 0, h->comm, h->stream));
+    return TAMC_OK;
+}
+int tamc_sync_resident_(tamc_handle h) { return sync_resident(h); }
+
 // full-grid upload on the handle's stream, not synchronised
 static int enqueue_upload(tamc_handle h, const double *rhokap)
 {
     CU(cudaEventRecord(h->ev[EV_H0], h->stream));
-    if (host_is_pinned(rhokap))
-        CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    else {
-        CU(cudaStreamSynchronize(h->stream));
-        CU(cudaMemcpy(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice));
-    }
+    // stream-ordered for pageable memory too (the runtime stages it and returns once the caller's buffer is free again): a
+    // legacy-stream cudaMemcpy is not ordered against the handle's non-blocking stream
+    CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!host_is_pinned(rhokap)) CU(cudaStreamSynchronize(h->stream));
     CU(cudaEventRecord(h->ev[EV_H1], h->stream));
     h->timed_h2d = true;
     return TAMC_OK;
@@ -303,7 +331,10 @@ extern "C" int tamc_set_optics(tamc_handle h, const double *rhokap, double albed
     if (int rc = check_optics(h, rhokap, albedo, hgg, n1, n2, flags, "tamc_set_optics")) return rc;
     h->timed_h2d = false;
     if (rhokap) {
-        if (int rc = enqueue_upload(h, rhokap)) return rc;
+        const bool rooted = h->root_io && h->comm && h->nranks > 1;
+        if (!rooted || h->rank == 0) { if (int rc = enqueue_upload(h, rhokap)) return rc; }
+        if (rooted) NC(nccl_api()->Broadcast(h->d_rhokap, h->d_rhokap, h->n_rhokap, ncclDouble, 0, h->comm, h->stream));
+        h->resident_behind = false;
         // the caller may rewrite rhokap as soon as this returns (no host pointer is kept past the call)
         CU(cudaStreamSynchronize(h->stream));
     }
@@ -344,7 +375,7 @@ extern "C" int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *i
     if (nranks > 1) {
         const double fp[16] = {(double)h->nxg, (double)h->nyg, (double)h->nzg, h->xmax, h->ymax, h->zmax, h->delta, h->spot,
                                h->gauss_sigma, (double)h->reduce, (double)h->box_reduce, (double)h->reduce_bound,
-                               (double)TAMC_VERSION, 0., 0., 0.};
+                               (double)TAMC_VERSION, (double)h->root_io, 0., 0.};
         double *d_fp = nullptr;
         CU(cudaMalloc(&d_fp, 32 * sizeof(double)));
         double both[32];
@@ -438,11 +469,6 @@ static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t fir
     // ("reduce_bound" = 2: also without a communicator, for diagnostics -- the answer lands in "reduce_planes")
     const bool stub = !(h->flags & (TAMC_SCATTER | TAMC_FRESNEL));
     cfg.want_bound = (stub && ((h->comm && h->reduce && h->nranks > 1 && h->box_reduce != 0 && h->reduce_bound) || h->reduce_bound == 2)) ? 1 : 0;
-    // Measured on 2-GPU boxes (profiles/README.md, tools/ab_multi3.sh): in a process that holds an NCCL communicator the
-    // regrouped column walk loses its edge -- 1.50-1.62 ms per 1e8 packets with rank-to-rank jitter (the all-reduce then
-    // waits for the slower rank) against 1.40 ms in lockstep for the tiled kernel, while single-process runs on the same
-    // box give 1.36 (regrouped) / 1.44 (tiled).  Cause not established; until it is, auto picks the tiled kernel there.
-    if (h->comm && h->nranks > 1 && cfg.column_park < 0) cfg.column_park = 0;
     h->colws.bound_pending = false;
     if (cfg.want_bound && !h->colws.s_side) {       // the bound kernel runs beside the transport, on a stream of its own
         if (cudaStreamCreateWithFlags(&h->colws.s_side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); h->colws.s_side = nullptr; }
@@ -460,6 +486,7 @@ static int enqueue_mc(tamc_handle h, int64_t nphotons, int64_t seed, int64_t fir
 extern "C" int tamc_run_async(tamc_handle h, int64_t nphotons, int64_t seed, int64_t first_packet_id)
 {
     if (int rc = check(h)) return rc;
+    if (int rc = sync_resident(h)) return rc;
     return enqueue_mc(h, nphotons, seed, first_packet_id);
 }
 
@@ -475,12 +502,7 @@ extern "C" int tamc_get_jmean(tamc_handle h, double *jmean_global)
     if (int rc = check(h)) return rc;
     if (!jmean_global) return fail(TAMC_EINVAL, "tamc_get_jmean: null destination");
     CU(cudaEventRecord(h->ev[EV_D0], h->stream));
-    if (host_is_pinned(jmean_global))
-        CU(cudaMemcpyAsync(jmean_global, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    else {
-        CU(cudaStreamSynchronize(h->stream));
-        CU(cudaMemcpy(jmean_global, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost));
-    }
+    CU(cudaMemcpyAsync(jmean_global, h->d_jmean, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev[EV_D1], h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->timed_d2h = true;
@@ -546,6 +568,14 @@ extern "C" int tamc_seek(tamc_handle h, int64_t next_packet_id)
 // PCIe is full duplex, so the step costs  box up + transport + box down  instead of  grid up + transport + grid down.
 // Needs page-locked host arrays (tamc_pin_host); anything else takes the plain sequential path.
 // ------------------------------------------------------------------------------------------------
+// root_io: rank 0's copies of the beam's columns to the other GPUs (called by the column set-up, tamc_kernels.cu)
+static cudaError_t share_broadcast(void *comm, double *buf, size_t count, cudaStream_t s)
+{
+    NcclApi *n = nccl_api();
+    if (!n || !comm) return cudaErrorInvalidValue;
+    return n->Broadcast(buf, buf, count, ncclDouble, 0, (ncclComm_t)comm, s) == ncclSuccess ? cudaSuccess : cudaErrorUnknown;
+}
+
 static int side_streams(tamc_handle h)
 {
     if (!h->s_up) CU(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
@@ -564,21 +594,57 @@ static bool box_io_wanted(tamc_handle h, int flags, ColGeom &cg)
     return beam_box(g, cg) && 2 * (size_t)cg.tw * cg.th <= (size_t)h->nxg * h->nyg;
 }
 
+// TAMC_TRACE=1: host-clock marks of one boundary call on stderr (where a call spends its wall time)
+struct CallTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    char buf[512];
+    int len = 0;
+    CallTrace() : on(getenv("TAMC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        len += snprintf(buf + len, sizeof(buf) - (size_t)len, " %s=%.0f", what, us);
+    }
+    void flush(int rank) { if (on) fprintf(stderr, "[tamc trace r%d]%s\n", rank, buf); }
+};
+
 static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
 {
+    CallTrace tr;
     ColGeom cg{};
     const DevGrid g = make_grid(h);
     // device-visible addresses of the caller's page-locked arrays (cudaHostRegister / cudaHostAlloc memory is mapped)
     double *jm_dev = nullptr;
     const double *rk_dev = nullptr;
-    bool box_dn = box_io_wanted(h, h->flags, cg) && host_is_pinned(jmean_global);
-    if (box_dn && cudaHostGetDevicePointer((void **)&jm_dev, jmean_global, 0) != cudaSuccess) { cudaGetLastError(); box_dn = false; }
-    bool box_up = rhokap && box_dn && host_is_pinned(rhokap) && column_gather_selected(g, h->cfg, nphotons);
-    if (box_up && cudaHostGetDevicePointer((void **)&rk_dev, const_cast<double *>(rhokap), 0) != cudaSuccess) { cudaGetLastError(); box_up = false; }
-    h->io_form = (box_dn ? 1 : 0) | (box_up ? 2 : 0);
+    // "root_io" (several ranks): only rank 0 touches host arrays.  Its rhokap goes up once and reaches the other GPUs over
+    // NVLink (ncclBroadcast), and only its jmeanGLOBAL is written -- the reference's ranks all hold identical copies of both
+    // (3dFD.f90:312-361 runs on every rank, and only rank 0's jmeanGLOBAL is read, :95), so nothing is lost and the host's
+    // PCIe / memory system carries 130 MB per call instead of nranks x 130 MB.  Every rank must make the same call with the
+    // same `rhokap != NULL`; on ranks > 0 the contents of rhokap are never read and jmean_global may be NULL.
+    const bool rooted = h->root_io && h->comm && h->nranks > 1;
+    const bool root = !rooted || h->rank == 0;
+    bool box_dn = box_io_wanted(h, h->flags, cg) && (root ? host_is_pinned(jmean_global) : true);
+    if (box_dn && root && cudaHostGetDevicePointer((void **)&jm_dev, jmean_global, 0) != cudaSuccess) { cudaGetLastError(); box_dn = false; }
+    bool box_up = rhokap && box_dn && (root ? host_is_pinned(rhokap) : true) && column_gather_selected(g, h->cfg, nphotons);
+    if (box_up && root && cudaHostGetDevicePointer((void **)&rk_dev, const_cast<double *>(rhokap), 0) != cudaSuccess) { cudaGetLastError(); box_up = false; }
+    if (rooted) {
+        // the ranks must take the same path (the collectives below differ): rank 0 decides, from what its host arrays allow
+        int path[2] = {box_dn ? 1 : 0, box_up ? 1 : 0};
+        if (!h->d_path) CU(cudaMalloc(&h->d_path, 2 * sizeof(int)));
+        CU(cudaMemcpyAsync(h->d_path, path, sizeof(path), cudaMemcpyHostToDevice, h->stream));
+        NC(nccl_api()->Broadcast(h->d_path, h->d_path, 2, ncclInt, 0, h->comm, h->stream));
+        CU(cudaMemcpyAsync(path, h->d_path, sizeof(path), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        box_dn = path[0] != 0;
+        box_up = path[1] != 0;
+        tr.mark("path");
+    }
+    h->io_form = (box_dn ? 1 : 0) | (box_up ? 2 : 0) | (rooted ? 8 : 0);
     if (rhokap) h->timed_h2d = false;   // otherwise keep the upload time of the tamc_set_optics before this call
 
-    if (box_dn) {
+    if (box_dn && root) {
         if (int rc = side_streams(h)) return rc;
         // nothing of this call may overtake work already queued on the handle's stream
         CU(cudaEventRecord(h->ev[EV_FORK], h->stream));
@@ -602,32 +668,45 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
         h->colws.box_rk = h->d_box_rk;
         h->colws.ev_gather0 = h->ev[EV_H0];
         h->colws.ev_gather1 = h->ev[EV_H1];
+        // root_io: rank 0 gathers every plane (the other ranks have no host array to fall back on below a depth limit) and
+        // hands both copies of the columns to the other GPUs over NVLink; those skip their gather
+        h->colws.share_gather = rooted ? (root ? 1 : 2) : 0;
+        h->colws.share_comm = rooted ? (void *)h->comm : nullptr;
+        h->colws.share_fn = share_broadcast;
         // "io_early": start the full-grid upload (bit0) / the zero fill (bit1) at once, beside the gather, instead of behind it
-        if (h->io_early & 1) {
+        if (root && (h->io_early & 1)) {
             CU(cudaStreamWaitEvent(h->s_up, h->ev[EV_FORK], 0));
             CU(cudaMemcpyAsync(h->d_rhokap, rhokap, h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->s_up));
             CU(cudaEventRecord(h->ev[EV_UP], h->s_up));
         }
-        if (h->io_early & 2) {
+        if (root && (h->io_early & 2)) {
             CU(cudaMemcpyAsync(jmean_global, h->d_zero, h->n_jmean * sizeof(double), cudaMemcpyDeviceToHost, h->s_dn));
             CU(cudaEventRecord(h->ev[EV_DN], h->s_dn));
         }
     } else if (rhokap) {
-        if (int rc = enqueue_upload(h, rhokap)) return rc;
+        if (root) { if (int rc = enqueue_upload(h, rhokap)) return rc; }
+        if (rooted) NC(nccl_api()->Broadcast(h->d_rhokap, h->d_rhokap, h->n_rhokap, ncclDouble, 0, h->comm, h->stream));
+        h->resident_behind = false;
+    } else {
+        if (int rc = sync_resident(h)) return rc;
     }
 
+    tr.mark("pre");
     const int rc_mc = enqueue_mc(h, nphotons, seed, -1);
+    tr.mark("mc_enqueued");
     if (box_up && h->colws.last_kz_lo > 0) h->io_form |= 4;     // the gather stopped at the depth the last call's packets reached
     h->colws.gather_src = nullptr;
     h->colws.box_rk = nullptr;
     h->colws.ev_gather0 = h->colws.ev_gather1 = nullptr;
+    h->colws.share_gather = 0;
+    h->colws.share_comm = nullptr;
     if (rc_mc) {
         cudaStreamSynchronize(h->stream);
         if (box_dn) cudaStreamSynchronize(h->s_dn);
         if (box_up) cudaStreamSynchronize(h->s_up);
         return rc_mc;
     }
-    if (box_up) {
+    if (box_up && root) {
         // the full grid, for every later reader of the resident rhokap: behind the column upload so the two do not share
         // the link, beside the transport (which no longer reads the resident grid in this call)
         h->timed_h2d = true;
@@ -643,6 +722,12 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
         }
     }
 
+    if (box_up && rooted) h->resident_behind = true;      // the other ranks' resident grid: brought up to date when next read
+    if (!root) {
+        CU(cudaStreamSynchronize(h->stream));
+        h->timed_d2h = false;
+        tr.mark("synced");
+    } else
     if (box_dn) {
         CU(cudaStreamWaitEvent(h->stream, h->ev[EV_DN], 0));          // the zero fill lands first
         CU(cudaEventRecord(h->ev[EV_D0], h->stream));
@@ -666,12 +751,26 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
             CU(launch_box_mirror(g, cg, jm_dev, h->num_sms, h->stream));
         CU(cudaEventRecord(h->ev[EV_D1], h->stream));
         if (box_up) CU(cudaStreamWaitEvent(h->stream, h->ev[EV_UP], 0));
+        tr.mark("dn_enqueued");
         CU(cudaStreamSynchronize(h->stream));
+        tr.mark("synced");
+        if (tr.on && box_up) {
+            float a = 0.f, b = 0.f;
+            cudaEventSynchronize(h->ev[EV_UP]); cudaEventSynchronize(h->ev[EV_DN]);
+            cudaEventElapsedTime(&a, h->ev[EV_FORK], h->ev[EV_UP]); cudaEventElapsedTime(&b, h->ev[EV_FORK], h->ev[EV_DN]);
+            tr.len += snprintf(tr.buf + tr.len, sizeof(tr.buf) - (size_t)tr.len, " up_done_at=%.0f dn_done_at=%.0f", a * 1e3, b * 1e3);
+            cudaEventElapsedTime(&a, h->ev[EV_FORK], h->ev[EV_K0]); cudaEventElapsedTime(&b, h->ev[EV_FORK], h->ev[EV_K1]);
+            tr.len += snprintf(tr.buf + tr.len, sizeof(tr.buf) - (size_t)tr.len, " k0=%.0f k1=%.0f", a * 1e3, b * 1e3);
+            cudaEventElapsedTime(&a, h->ev[EV_FORK], h->ev[EV_AR1]); cudaEventElapsedTime(&b, h->ev[EV_FORK], h->ev[EV_D1]);
+            tr.len += snprintf(tr.buf + tr.len, sizeof(tr.buf) - (size_t)tr.len, " ar1=%.0f d1=%.0f", a * 1e3, b * 1e3);
+        }
         h->timed_d2h = true;
         if (!dma) h->last_launches += 1;
     } else {
         if (int rc = tamc_get_jmean(h, jmean_global)) return rc;
     }
+    tr.mark("end");
+    tr.flush(h->rank);
     if (stats) return tamc_get_stats(h, stats);
     tamc_stats tmp;
     return tamc_get_stats(h, &tmp);   // surfaces transport errors even when the caller wants no stats
@@ -680,7 +779,7 @@ static int run_boundary(tamc_handle h, const double *rhokap, int64_t nphotons, i
 extern "C" int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
 {
     if (int rc = check(h)) return rc;
-    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_run: jmean_global is null");
+    if (!jmean_global && !(h->root_io && h->comm && h->rank > 0)) return fail(TAMC_EINVAL, "tamc_run: jmean_global is null");
     if (!h->optics_set) return fail(TAMC_ESTATE, "tamc_run: tamc_set_optics has not been called");
     if (nphotons < 0 || nphotons > ((int64_t)1 << 46)) return fail(TAMC_EINVAL, "tamc_run: nphotons out of range");
     return run_boundary(h, nullptr, nphotons, seed, jmean_global, stats);
@@ -690,7 +789,7 @@ extern "C" int tamc_run_optics(tamc_handle h, const double *rhokap, double albed
                                int64_t nphotons, int64_t seed, double *jmean_global, tamc_stats *stats)
 {
     if (int rc = check(h)) return rc;
-    if (!jmean_global) return fail(TAMC_EINVAL, "tamc_run_optics: jmean_global is null");
+    if (!jmean_global && !(h->root_io && h->comm && h->rank > 0)) return fail(TAMC_EINVAL, "tamc_run_optics: jmean_global is null");
     if (int rc = check_optics(h, rhokap, albedo, hgg, n1, n2, flags, "tamc_run_optics")) return rc;
     if (nphotons < 0 || nphotons > ((int64_t)1 << 46)) return fail(TAMC_EINVAL, "tamc_run_optics: nphotons out of range");
     h->albedo = albedo; h->hgg = hgg; h->n1 = n1; h->n2 = n2; h->flags = flags;
@@ -848,6 +947,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "reduce_planes")) return &h->reduce_planes;
     if (!strcmp(name, "form")) return &h->form;
     if (!strcmp(name, "box_io")) return &h->box_io;
+    if (!strcmp(name, "root_io")) return &h->root_io;
     if (!strcmp(name, "io_form")) return &h->io_form;
     return nullptr;
 }
@@ -864,6 +964,8 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (slot == &h->probe_form && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "probe_form must be -1, 0 or 1");
     if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");
+    if (slot == &h->root_io && (value < 0 || value > 1)) return fail(TAMC_EINVAL, "root_io must be 0 or 1");
+    if (slot == &h->root_io && h->comm) return fail(TAMC_ESTATE, "root_io shapes the collectives of every call: set it on every rank before tamc_comm_init");
     if (slot == &h->cfg.flight && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "flight must be -1 (auto), 0 or 1");
     if (slot == &h->cfg.walk_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "walk_min must be in [1,32]");
     if (slot == &h->cfg.flight_regs && value != 0 && (value < 2 || value > 4)) return fail(TAMC_EINVAL, "flight_regs must be 0, 2, 3 or 4");

@@ -49,6 +49,9 @@ struct tamc_context {
     int box_io = -1;        // -1 = auto, 0 = off: plain full-grid copies in sequence
     int io_early = 0;       // tamc_run_optics, columns-first upload: bit0 = the full-grid upload, bit1 = the zero fill start beside
                             // the column gather instead of behind it
+    int root_io = 0;        // several ranks: 1 = only rank 0's host arrays are read / written (broadcast + root download); set before tamc_comm_init
+    bool resident_behind = false;   // root_io: ranks > 0 hold only the beam's columns of the last uploaded grid (sync_resident, tamc_api.cu)
+    int *d_path = nullptr;  // root_io: the copy path rank 0 chose for this call, broadcast to the other ranks
     int io_form = 0;        // read-only: bit0 = the last tamc_run downloaded zero fill + beam columns, bit1 = the last
                             // tamc_run_optics uploaded the beam columns ahead of the grid, bit2 = ... and only down to the
                             // depth the previous call's packets reached (+ margin)
@@ -69,5 +72,6 @@ struct tamc_context {
 int tamc_fail_(int code, const std::string &msg);
 int tamc_check_(tamc_handle h);
 tamc::DevGrid tamc_make_grid_(const tamc_context *c);
+int tamc_sync_resident_(tamc_handle h);
 // defined in tamc_heat.cu
 void tamc_heat_release_(tamc_context *c);

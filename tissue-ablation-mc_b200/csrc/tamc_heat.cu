@@ -251,6 +251,7 @@ extern "C" int tamc_heat_init(tamc_handle h, const tamc_heat_params *p, double *
 {
     if (int rc = tamc_check_(h)) return rc;
     if (!p) return tamc_fail_(TAMC_EINVAL, "tamc_heat_init: null parameters");
+    if (int rc = tamc_sync_resident_(h)) return rc;
     if (h->nxg != h->nyg || h->nxg != h->nzg)
         return tamc_fail_(TAMC_EINVAL, "tamc_heat_init: the heat solver assumes nxg = nyg = nzg (numpoints, mcpolar.f90:61)");
     if (!h->optics_set) return tamc_fail_(TAMC_ESTATE, "tamc_heat_init: call tamc_set_optics first (rhokap must be resident)");
@@ -329,7 +330,7 @@ static int need_heat(tamc_handle h, const char *who)
 {
     if (int rc = tamc_check_(h)) return rc;
     if (!h->heat) return tamc_fail_(TAMC_ESTATE, std::string(who) + ": tamc_heat_init has not been called");
-    return TAMC_OK;
+    return tamc_sync_resident_(h);          // root_io: the heat step reads the resident opacity grid on every rank
 }
 
 // mcpolar.f90:174 followed by :178-182: scale the resident tally, heat_sim_3d, arrhenius, setupThermalCoeff.
@@ -450,6 +451,14 @@ extern "C" int tamc_heat_scalar(tamc_handle h, int which, double *out)
     case TAMC_HEAT_S_QVAPOR: *out = s->QVapor; break;
     case TAMC_HEAT_S_PWR: *out = get_pwr(s); break;
     case TAMC_HEAT_S_COUNTER: *out = (double)s->counter; break;
+    case TAMC_HEAT_S_NEGATIVE_TEMP: {
+        // the sticky flag of the stencil kernel: the condition on which the reference calls mpi_abort (3dFD.f90:179-182)
+        int flags[2] = {0, 0};
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(flags, s->flags, sizeof(flags), cudaMemcpyDeviceToHost));
+        *out = flags[1] ? 1. : 0.;
+        break;
+    }
     default: return tamc_fail_(TAMC_EINVAL, "tamc_heat_scalar: unknown scalar id");
     }
     return TAMC_OK;

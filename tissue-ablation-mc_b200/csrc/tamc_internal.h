@@ -57,6 +57,11 @@ struct ColumnWorkspace {
     double *box_rk = nullptr;
     cudaEvent_t ev_gather0 = nullptr, ev_gather1 = nullptr;
     int last_kz_lo = 0;              // read-back: first plane (k - 1) the last gather copied (> 0: depth-limited)
+    // root_io (tamc_api.cu): 1 = this rank gathers every plane and broadcasts both copies of the columns, 2 = this rank
+    // receives them instead of gathering; 0 = every rank gathers from its own host array
+    int share_gather = 0;
+    void *share_comm = nullptr;      // ncclComm_t of the handle
+    cudaError_t (*share_fn)(void *comm, double *buf, size_t count, cudaStream_t s) = nullptr;   // broadcast from rank 0 (set by tamc_api.cu)
     // depth bound of the call (k_column_bound): one int in mapped page-locked memory, written by the kernel, read by the
     // host once ev_bound has passed -- while the transport is still running
     int *h_bound = nullptr, *d_bound = nullptr;

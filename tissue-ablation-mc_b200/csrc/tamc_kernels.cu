@@ -628,19 +628,26 @@ static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gath
         }
         // columns-first upload over PCIe: only the planes the packets are expected to reach (gather_planes from the top
         // face, whole 32-plane tiles); anything deeper is read from the caller's grid where it is needed
-        if (ws->gather_src && ws->box_rk && gather_planes > 0 && gather_planes < g.nzg) {
+        if (ws->gather_src && ws->box_rk && gather_planes > 0 && gather_planes < g.nzg && ws->share_gather == 0) {
             cg.kz_lo = (g.nzg - gather_planes) & ~31;
             cg.deep = ws->gather_src;
             cg.deep_sx = g.sx;
             cg.deep_sxy = g.sxy;
         }
         const dim3 gg((cg.tw + 31) / 32, cg.th, (cg.nzp - cg.kz_lo + 31) / 32);
-        if (ws->gather_src && ws->box_rk) {
+        if (ws->share_gather == 2 && ws->box_rk) {
+            // root_io, rank > 0: both copies of the columns arrive from rank 0 below
+        } else if (ws->gather_src && ws->box_rk) {
             if (ws->ev_gather0) cudaEventRecord(ws->ev_gather0, s);
             k_column_gather<true><<<gg, 256, 0, s>>>(g, cg, ws->gather_src, ws->rkT, ws->box_rk);
             if (ws->ev_gather1) cudaEventRecord(ws->ev_gather1, s);
         } else {
             k_column_gather<false><<<gg, 256, 0, s>>>(g, cg, g.rhokap, ws->rkT, nullptr);
+        }
+        if (ws->share_gather && ws->box_rk && ws->share_fn) {
+            cudaError_t e = ws->share_fn(ws->share_comm, ws->rkT, nrk, s);
+            if (e == cudaSuccess) e = ws->share_fn(ws->share_comm, ws->box_rk, (size_t)cg.tw * cg.th * g.nzg, s);
+            if (e != cudaSuccess) return e;
         }
     }
     return cudaGetLastError();
@@ -691,8 +698,8 @@ bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n)
     return column_plan(g, cfg, n).use && cfg.column != 2;
 }
 
-// The depth bound of this call for the all-reduce (k_column_bound): computed on a side stream beside the transport when the
-// handle has one, handed to the host through one int in mapped page-locked memory.  from_copy: walk the z-fastest copy the
+// The depth bound of this call for the all-reduce (k_column_bound), handed to the host through one int in mapped
+// page-locked memory.  from_copy: walk the z-fastest copy the
 // gather just made (the resident grid may still be on its way over PCIe); otherwise walk the resident grid.
 static void enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *ws, cudaStream_t s, int *launches, bool from_copy)
 {
@@ -710,11 +717,11 @@ static void enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *
     }
     if (!ws->h_bound) return;
     *ws->h_bound = 0;
-    cudaStream_t sb = ws->s_side ? ws->s_side : s;
-    if (sb != s) {
-        cudaEventRecord(ws->ev_gathered, s);
-        cudaStreamWaitEvent(sb, ws->ev_gathered, 0);
-    }
+    // On the transport's own stream, AHEAD of the transport (10-15 us): the host waits for this answer before it can
+    // enqueue the reduction, and a kernel on a side stream does not get onto the SMs while the transport's one-CTA-per-SM
+    // launch holds them -- measured (TAMC_TRACE): the host then sat in that wait until the transport had finished, and
+    // everything it enqueues afterwards (the copies that should run BESIDE the transport) started 1.8 ms late.
+    cudaStream_t sb = s;
     const int cols = cg.tw * cg.th;
     if (from_copy)
         k_column_bound<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, (const double *)ws->rkT, ws->bound_scratch,
@@ -774,7 +781,7 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     else e = launch_sized(k_transport_column<true, 4>, c2, smem, n, s, g, n, seed, first_id, cg, (const double *)ws->rkT, ws->stops, d_cnt);
     if (e != cudaSuccess) return e;
     DevGrid gf = g;
-    if (gather && ws->gather_src && ws->box_rk) {
+    if (gather && ws->box_rk && (ws->gather_src || ws->share_gather == 2)) {
         // rhokap(i,j,k) = box[(i-i0) + tw*((j-j0) + th*(k-1))]: the resident index expression i + sx*j + sxy*k with
         // sx = tw, sxy = tw*th and the origin moved
         gf.sx = cg.tw;

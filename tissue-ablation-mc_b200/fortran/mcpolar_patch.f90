@@ -26,11 +26,17 @@
          call tamc_check(ierr, 'tamc_comm_unique_id')
       end if
       call MPI_Bcast(nccl_id, 128, MPI_CHARACTER, 0, new_comm)
+      !  optional, BEFORE tamc_comm_init and on every rank: only rank 0's rhokap is read (it reaches the other GPUs over
+      !  NVLink) and only rank 0's jmeanGLOBAL is written -- all the reference consumes (3dFD.f90:95 scatters rank 0's copy;
+      !  setupThermalCoeff, :312-361, leaves identical rhokap on every rank).  Every rank still makes the same call.
+      ! ierr = tamc_set_option(tamc, 'root_io'//c_null_char, 1_c_int64_t)
       ierr = tamc_comm_init(tamc, int(numproc, c_int), int(id, c_int), nccl_id)
       call tamc_check(ierr, 'tamc_comm_init')
       !  optional: page-lock the two arrays that cross PCIe every MC call
-      ierr = tamc_pin_host(c_loc(rhokap), int(size(rhokap), c_int64_t)*8_c_int64_t)
-      ierr = tamc_pin_host(c_loc(jmeanGLOBAL), int(size(jmeanGLOBAL), c_int64_t)*8_c_int64_t)
+      ierr = tamc_pin_host(rhokap, int(size(rhokap), c_int64_t)*8_c_int64_t)
+      call tamc_check(ierr, 'tamc_pin_host(rhokap)')
+      ierr = tamc_pin_host(jmeanGLOBAL, int(size(jmeanGLOBAL), c_int64_t)*8_c_int64_t)
+      call tamc_check(ierr, 'tamc_pin_host(jmeanGLOBAL)')
       seed64 = 95648324_c_int64_t          ! mcpolar.f90:97: the run seed; ranks are told apart by packet id
       oflags = 0                           ! TAMC_SCATTER to run the albedo/stokes loop instead of the stub
 

@@ -106,11 +106,21 @@ module tamc_mod
             character(kind=c_char), intent(in) :: id128(128)
         end function tamc_comm_init
 
-        integer(c_int) function tamc_pin_host(ptr, bytes) bind(C, name="tamc_pin_host")
-            import :: c_int, c_int64_t, c_ptr
-            type(c_ptr), value        :: ptr
-            integer(c_int64_t), value :: bytes
+        !  the array itself (assumed size, passed by reference): no c_loc, so iarray.f90's plain `real, allocatable`
+        !  arrays need no TARGET attribute
+        integer(c_int) function tamc_pin_host(a, bytes) bind(C, name="tamc_pin_host")
+            import :: c_int, c_int64_t, c_double
+            real(c_double), intent(in) :: a(*)
+            integer(c_int64_t), value  :: bytes
         end function tamc_pin_host
+
+        !  tuning / behaviour knobs by name (include/tamc.h); the name is a NUL-terminated string: 'root_io'//c_null_char
+        integer(c_int) function tamc_set_option(handle, name, value) bind(C, name="tamc_set_option")
+            import :: c_int, c_int64_t, c_char, c_ptr
+            type(c_ptr), value                 :: handle
+            character(kind=c_char), intent(in) :: name(*)
+            integer(c_int64_t), value          :: value
+        end function tamc_set_option
 
         integer(c_int) function tamc_device_count() bind(C, name="tamc_device_count")
             import :: c_int

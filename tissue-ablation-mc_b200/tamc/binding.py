@@ -60,7 +60,7 @@ PULSETYPES = {"tophat": 0, "gaussian": 1, "triangular": 2}
 HEAT_ARRAYS = {"temp": 0, "rhokap": 1, "kappa": 2, "density": 3, "heatcap": 4, "coeff": 5, "alpha": 6,
                "watercontent": 7, "Q": 8, "tissue": 9, "threstime": 10, "jmean": 11}
 HEAT_SCALARS = {"delt": 0, "time": 1, "total_time": 2, "pulselength": 3, "realPulseLength": 4, "laserOn": 5,
-                "pulseCount": 6, "repetitionCount": 7, "laser_flag": 8, "QVapor": 9, "pwr": 10, "counter": 11}
+                "pulseCount": 6, "repetitionCount": 7, "laser_flag": 8, "QVapor": 9, "pwr": 10, "counter": 11, "negative_temp": 12}
 
 
 def lib_path() -> str:
