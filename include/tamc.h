@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TAMC_VERSION 104
+#define TAMC_VERSION 105
 
 enum {
     TAMC_OK = 0,
@@ -115,6 +115,20 @@ int tamc_set_source_gaussian(tamc_handle h, double sigma_cm);
  * stored (the reference reads them, mcpolar.f90:84-85, and never uses them). */
 int tamc_set_optics(tamc_handle h, const double *rhokap, double albedo, double hgg, double n1, double n2,
                     int flags);
+
+/* EXTENSION -- no upstream counterpart: the reference's optics are the per-voxel opacity rhokap (iarray.f90:9) plus the
+ * SCALARS albedo, hgg, n1, n2 of opt_prop.f90:5.  Optional per-voxel grids, each laid out exactly like rhokap
+ * ((0:nxg+1,0:nyg+1,0:nzg+1), column-major, halo included and never read) or NULL to keep the scalar of tamc_set_optics:
+ *   albedo  the albedo test of an interaction (`draw < albedo ? stokes : absorbed`) uses the value of the
+ *           voxel the interaction happens in;
+ *   hgg     ... and the Henyey-Greenstein draw of stokes.f90:48 the anisotropy of that voxel (hgg == 0: the isotropic branch);
+ *   n       with TAMC_FRESNEL the inside index at an outer face of the grid is the index of the voxel the packet leaves,
+ *           and the specular reflection at launch uses the launch voxel's; index changes BETWEEN voxels do not refract.
+ * The grids stay resident (read-only through L2, beside rhokap) until the next call; all three NULL switches them off,
+ * and a call with NULL grids gives bit-identical results to a library that never heard of them.  Trace replay, the exact
+ * and thread-per-packet kernels and the production (flight) kernel honour albedo / hgg grids; calls with boundary options
+ * take the thread-per-packet kernel.  Checked against the extended oracle (orc_set_grids) on the same streams. */
+int tamc_set_optics_grids(tamc_handle h, const double *albedo, const double *hgg, const double *n);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 

@@ -95,6 +95,7 @@ def _bind(path: str) -> C.CDLL:
     lib.orc_set_source_gaussian.argtypes = [p, d]
     lib.orc_set_indices.argtypes = [p, d, d]
     lib.orc_set_flags.argtypes = [p, i]
+    lib.orc_set_grids.argtypes = [p, p, p, p]
     lib.orc_zero_jmean.argtypes = [p]
     lib.orc_seed_ran2.argtypes = [p, i]
     lib.orc_seed_philox.argtypes = [p, C.c_uint64, C.c_uint64]
@@ -218,6 +219,20 @@ class Oracle:
     def set_source_gaussian(self, sigma: float):
         """Gaussian beam through rang() (sourceph.f90:73-101); sigma <= 0 = back to the CO2 disk."""
         self.lib.orc_set_source_gaussian(self.h, float(sigma))
+
+    def set_grids(self, albedo=None, hgg=None, n=None):
+        """EXTENSION: per-voxel albedo / hgg / refractive index, each shaped like rhokap (halo included) or None."""
+        keep = []
+        ptrs = []
+        for a in (albedo, hgg, n):
+            if a is None:
+                ptrs.append(None)
+            else:
+                b = np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+                assert b.size == self.rhokap.size
+                keep.append(b)
+                ptrs.append(b.ctypes.data)
+        self.lib.orc_set_grids(self.h, *ptrs)
 
     def set_flags(self, flags: int):
         self.lib.orc_set_flags(self.h, int(flags))

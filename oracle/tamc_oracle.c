@@ -37,6 +37,9 @@ struct orc_state {
     double *rhokap, *jmean;
     /* opt_prop.f90:5 */
     double mua, mus, g2, hgg, kappa, albedo, mu_water, mu_protein, n1, n2;
+    /* EXTENSION (no upstream counterpart: opt_prop.f90:5 holds scalars): optional per-voxel albedo / hgg / refractive
+     * index, laid out like rhokap (0:nxg+1,0:nyg+1,0:nzg+1); NULL = the scalar above */
+    double *albedo_g, *hgg_g, *n_g;
     /* photon_vars.f90:11 */
     double xp, yp, zp, nxp, nyp, nzp, sint, cost, sinp, cosp, phi;
     /* ran2.f:8-9 SAVEd state */
@@ -64,6 +67,7 @@ struct orc_state {
 };
 
 #define RHOKAP(o, i, j, k) ((o)->rhokap[(size_t)(i) + (size_t)((o)->nxg + 2) * ((size_t)(j) + (size_t)((o)->nyg + 2) * (size_t)(k))])
+#define HALO(o, i, j, k) ((size_t)(i) + (size_t)((o)->nxg + 2) * ((size_t)(j) + (size_t)((o)->nyg + 2) * (size_t)(k)))
 #define JMEAN(o, i, j, k) ((o)->jmean[(size_t)((i)-1) + (size_t)(o)->nxg * ((size_t)((j)-1) + (size_t)(o)->nyg * (size_t)((k)-1))])
 #define XFACE(o, i) ((o)->xface[(i)-1])
 #define YFACE(o, i) ((o)->yface[(i)-1])
@@ -104,6 +108,7 @@ void orc_destroy(orc_state *o)
 {
     if (!o) return;
     free(o->xface); free(o->yface); free(o->zface); free(o->rhokap); free(o->jmean);
+    free(o->albedo_g); free(o->hgg_g); free(o->n_g);
     free(o);
 }
 
@@ -148,6 +153,27 @@ void orc_set_optics(orc_state *o, double albedo, double hgg)
 void orc_set_spot(orc_state *o, double d) { o->spotSize = d; }
 void orc_set_source_gaussian(orc_state *o, double sigma) { o->gauss_sigma = sigma > 0. ? sigma : 0.; }
 void orc_set_indices(orc_state *o, double n1, double n2) { o->n1 = n1; o->n2 = n2; }
+
+/* EXTENSION: per-voxel albedo / hgg / refractive index (each NULL = keep the scalar; all NULL = grids off).  Builder-defined
+ * semantics, the library's tamc_set_optics_grids: the albedo test and the Henyey-Greenstein draw of an interaction take the
+ * values of the voxel the interaction happens in; with ORC_FLAG_FRESNEL the inside index at an outer face is the index of
+ * the voxel the packet leaves (and of the launch voxel for the specular reflection).  Index changes BETWEEN voxels do not
+ * refract (documented limitation). */
+void orc_set_grids(orc_state *o, const double *albedo, const double *hgg, const double *n)
+{
+    const size_t nh = (size_t)(o->nxg + 2) * (size_t)(o->nyg + 2) * (size_t)(o->nzg + 2);
+    const double *src[3] = {albedo, hgg, n};
+    double **dst[3] = {&o->albedo_g, &o->hgg_g, &o->n_g};
+    int i;
+    for (i = 0; i < 3; i++) {
+        free(*dst[i]);
+        *dst[i] = NULL;
+        if (src[i]) {
+            *dst[i] = (double *)malloc(nh * sizeof(double));
+            memcpy(*dst[i], src[i], nh * sizeof(double));
+        }
+    }
+}
 void orc_set_flags(orc_state *o, int flags) { o->flags = flags; }
 void orc_zero_jmean(orc_state *o) { memset(o->jmean, 0, sizeof(double) * (size_t)o->nxg * o->nyg * o->nzg); }
 
@@ -537,7 +563,8 @@ static void tauint1(orc_state *o, double xmax, double ymax, double zmax, int *xc
                     const int only = (a == 0 && celli == -1 && cellj != -1 && cellk != -1) ||
                                      (a == 1 && cellj == -1 && celli != -1 && cellk != -1) ||
                                      (a == 2 && cellk == -1 && celli != -1 && cellj != -1);
-                    if (only && draw_boundary(o) < fresnel_reflectance(o->n2, o->n1, fabs(na))) {
+                    const double n_in = o->n_g ? o->n_g[HALO(o, pi, pj, pk)] : o->n2;
+                    if (only && draw_boundary(o) < fresnel_reflectance(n_in, o->n1, fabs(na))) {
                         o->internal_reflections++;
                         if (a == 0) {
                             xcur = (na > 0.) ? XFACE(o, pi + 1) - delta : XFACE(o, pi) + delta;
@@ -733,7 +760,8 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
         else sourcephCO2(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell);
         if (o->flags & ORC_FLAG_FRESNEL) {
             /* extension: specular reflection at the top surface, normal incidence */
-            const double r0 = (o->n1 - o->n2) / (o->n1 + o->n2);
+            const double n_in = o->n_g ? o->n_g[HALO(o, xcell, ycell, zcell)] : o->n2;
+            const double r0 = (o->n1 - n_in) / (o->n1 + n_in);
             if (draw_boundary(o) < r0 * r0) {
                 specular = 1;
                 tflag = 1;
@@ -749,7 +777,11 @@ int orc_run(orc_state *o, int64_t nphotons, orc_packet_record *records, double *
                 absorbed = 1;
                 break;
             }
-            if (draw(o) < o->albedo) {
+            if (o->hgg_g) {                 /* the voxel of the interaction (tauint1 leaves its indices in x/y/zcell) */
+                o->hgg = o->hgg_g[HALO(o, xcell, ycell, zcell)];
+                o->g2 = o->hgg * o->hgg;
+            }
+            if (draw(o) < (o->albedo_g ? o->albedo_g[HALO(o, xcell, ycell, zcell)] : o->albedo)) {
                 stokes(o);
                 o->nscatt++;
             } else {

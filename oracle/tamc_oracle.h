@@ -78,6 +78,8 @@ void orc_set_optics(orc_state *o, double albedo, double hgg);
 /* Builder-defined extension (no upstream semantics): refractive indices outside / inside the grid
  * for ORC_FLAG_FRESNEL -- specular reflection at launch, Fresnel reflection or escape at the six outer faces. */
 void orc_set_indices(orc_state *o, double n1, double n2);
+/* EXTENSION: per-voxel albedo / hgg / refractive index, rhokap's layout; NULL = the scalar (tamc_set_optics_grids) */
+void orc_set_grids(orc_state *o, const double *albedo, const double *hgg, const double *n);
 void orc_set_spot(orc_state *o, double spot_diameter);   /* sourceph.f90:23, default 250d-4 */
 /* Gaussian beam built on rang() (sourceph.f90:73-101: Marsaglia polar method over ranu, :52-70; dead code
  * upstream, so the launch that uses it is builder-defined): xp = rang(0, sigma), yp = rang(0, sigma), each

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libtamc.so does not export {n}"
     assert sorted(binding.EXPORTS) == names          # the Python binding covers the whole ABI
-    assert tamc.lib().tamc_version() == 104
+    assert tamc.lib().tamc_version() == 105
 
 
 def test_record_and_stats_layout_match_header():

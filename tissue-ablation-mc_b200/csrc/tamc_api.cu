@@ -139,6 +139,7 @@ static DevGrid make_grid(const tamc_context *c)
     g.sc.two_g = 2. * g.hgg;
     g.sc.inv_two_g = (g.hgg != 0.) ? 1. / (2. * g.hgg) : 0.;
     g.rhokap = c->d_rhokap; g.jmean = c->d_jmean; g.faces = c->d_faces;
+    g.albedo_g = c->d_albedo_g; g.hgg_g = c->d_hgg_g; g.n_g = c->d_n_g;
     return g;
 }
 
@@ -246,6 +247,7 @@ extern "C" int tamc_finalize(tamc_handle h)
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_flush);
+    cudaFree(h->d_albedo_g); cudaFree(h->d_hgg_g); cudaFree(h->d_n_g); cudaFree(h->colws.optc);
     cudaFree(h->colws.stops); cudaFree(h->colws.rkT); cudaFree(h->colws.dense); cudaFree(h->colws.vox);
     if (h->colws.s_side) { cudaStreamSynchronize(h->colws.s_side); cudaStreamDestroy(h->colws.s_side); }
     if (h->colws.h_bound) cudaFreeHost(h->colws.h_bound);
@@ -340,6 +342,40 @@ extern "C" int tamc_set_optics(tamc_handle h, const double *rhokap, double albed
     }
     h->albedo = albedo; h->hgg = hgg; h->n1 = n1; h->n2 = n2; h->flags = flags;
     h->optics_set = true;
+    return TAMC_OK;
+}
+
+// EXTENSION (no upstream counterpart: opt_prop.f90:5 holds scalars): per-voxel albedo / hgg / refractive index.
+extern "C" int tamc_set_optics_grids(tamc_handle h, const double *albedo, const double *hgg, const double *n)
+{
+    if (int rc = check(h)) return rc;
+    const double *src[3] = {albedo, hgg, n};
+    double **dst[3] = {&h->d_albedo_g, &h->d_hgg_g, &h->d_n_g};
+    const char *what[3] = {"albedo must be in [0,1]", "hgg must be in (-1,1)", "refractive index must be positive"};
+    for (int i = 0; i < 3; ++i) {
+        if (!src[i]) continue;
+        // the halo is never read; the interior has to be a valid optical property
+        for (int k = 1; k <= h->nzg; ++k)
+            for (int j = 1; j <= h->nyg; ++j) {
+                const double *row = src[i] + (size_t)(h->nxg + 2) * ((size_t)j + (size_t)(h->nyg + 2) * (size_t)k);
+                for (int ii = 1; ii <= h->nxg; ++ii) {
+                    const double v = row[ii];
+                    const bool ok = i == 0 ? (v >= 0. && v <= 1.) : (i == 1 ? (v > -1. && v < 1.) : (v > 0. && v < 1e300));
+                    if (!ok) return fail(TAMC_EINVAL, std::string("tamc_set_optics_grids: ") + what[i]);
+                }
+            }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 3; ++i) {
+        if (!src[i]) {
+            cudaFree(*dst[i]);
+            *dst[i] = nullptr;
+            continue;
+        }
+        if (!*dst[i]) CU(cudaMalloc(dst[i], h->n_rhokap * sizeof(double)));
+        CU(cudaMemcpyAsync(*dst[i], src[i], h->n_rhokap * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
     return TAMC_OK;
 }
 

@@ -26,6 +26,7 @@ struct tamc_context {
 
     size_t n_rhokap = 0, n_jmean = 0;
     double *d_rhokap = nullptr, *d_jmean = nullptr, *d_faces = nullptr, *d_flush = nullptr;
+    double *d_albedo_g = nullptr, *d_hgg_g = nullptr, *d_n_g = nullptr;   // tamc_set_optics_grids: per-voxel optics, null = scalar
     size_t flush_elems = 0;
     unsigned long long *d_cnt = nullptr;
     cudaStream_t stream = nullptr;

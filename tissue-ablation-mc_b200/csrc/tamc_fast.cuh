@@ -304,6 +304,44 @@ __device__ __forceinline__ int voxel_step_fast(const DevGrid &g, const double *x
 // u1 -> stokes.f90:24/:48, u2 -> :32/:64, tau = -log(u3) -> the next tauint1 draw (inttau2.f90:36).
 template <bool kSetDir = true>
 __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2);
+template <bool kSetDir = true>
+__device__ __forceinline__ void scatter_dir(FastPhoton &p, double u1, double u2, double hgg, const ScatterConsts &sc);
+
+// The constants of the Henyey-Greenstein draw for one value of g (per-voxel hgg: formed per event; otherwise DevGrid::sc)
+__device__ __forceinline__ ScatterConsts make_scatter_consts(double hgg)
+{
+    ScatterConsts sc;
+    const double g2 = hgg * hgg;
+    sc.one_m_g2 = 1. - g2;
+    sc.one_p_g2 = 1. + g2;
+    sc.one_m_g = 1. - hgg;
+    sc.two_g = 2. * hgg;
+    sc.inv_two_g = (hgg != 0.) ? 1. / (2. * hgg) : 0.;
+    return sc;
+}
+
+// albedo and Henyey-Greenstein constants of an interaction in the voxel with halo-layout index v
+__device__ __forceinline__ void voxel_optics(const DevGrid &g, long long v, double &albedo, double &hgg, ScatterConsts &sc)
+{
+    albedo = g.albedo_g ? __ldg(g.albedo_g + v) : g.albedo;
+    hgg = g.hgg;
+    sc = g.sc;
+    if (g.hgg_g) {
+        hgg = __ldg(g.hgg_g + v);
+        sc = make_scatter_consts(hgg);
+    }
+}
+
+__device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double tau, double hgg,
+                                             const ScatterConsts &sc)
+{
+    p.taurun = 0.;
+    p.tau = tau;
+    p.xcur = (p.xcur - g.xmax) + g.xmax;
+    p.ycur = (p.ycur - g.ymax) + g.ymax;
+    p.zcur = (p.zcur - g.zmax) + g.zmax;
+    scatter_dir<true>(p, u1, u2, hgg, sc);
+}
 
 __device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, double u1, double u2, double tau)
 {
@@ -321,8 +359,13 @@ __device__ __forceinline__ void scatter_fast(const DevGrid &g, FastPhoton &p, do
 template <bool kSetDir>
 __device__ __forceinline__ void scatter_dir(const DevGrid &g, FastPhoton &p, double u1, double u2)
 {
-    const ScatterConsts &sc = g.sc;
-    if (g.hgg == 0.0) {                                   // isotropic, stokes.f90:23-38
+    scatter_dir<kSetDir>(p, u1, u2, g.hgg, g.sc);
+}
+
+template <bool kSetDir>
+__device__ __forceinline__ void scatter_dir(FastPhoton &p, double u1, double u2, double hgg, const ScatterConsts &sc)
+{
+    if (hgg == 0.0) {                                     // isotropic, stokes.f90:23-38
         const double cost = 2. * u1 - 1.;
         const double s2 = 1. - cost * cost;
         p.sint = (s2 <= 0.) ? 0. : sqrt(s2);
@@ -373,8 +416,10 @@ __device__ __forceinline__ bool fresnel_reflect_fast(const DevGrid &g, const dou
 {
     const int a = ((unsigned)(p.celli - 1) >= (unsigned)g.nxg) ? 0 : (((unsigned)(p.cellj - 1) >= (unsigned)g.nyg) ? 1 : 2);
     const double na = a == 0 ? p.nxp : (a == 1 ? p.nyp : p.nzp);
-    if (!(boundary_draw(key, id_lo, id_hi, nb) < fresnel_reflectance(g.n2, g.n1, fabs(na)))) return false;
     const int back = (na > 0.) ? -1 : 1;             // undo the index step of the crossing
+    double n_in = g.n2;
+    if (g.n_g) n_in = __ldg(g.n_g + (p.ridx + back * (a == 0 ? 1 : (a == 1 ? g.sx : (int)g.sxy))));   // the voxel being left
+    if (!(boundary_draw(key, id_lo, id_hi, nb) < fresnel_reflectance(n_in, g.n1, fabs(na)))) return false;
     if (a == 0) {
         p.xcur = (na > 0.) ? xf[g.nxg] - g.delta : xf[0] + g.delta;
         p.celli += back; p.ridx += back; p.jidx += back;
@@ -420,6 +465,15 @@ __device__ __forceinline__ int boundary_fast(const DevGrid &g, const double *xf,
     if ((g.flags & TAMC_PERIODIC) && periodic_wrap_fast(g, p)) return 2;
     if ((g.flags & TAMC_FRESNEL) && fresnel_reflect_fast(g, xf, yf, zf, p, key, id_lo, id_hi, nb)) return 1;
     return 0;
+}
+
+// TAMC_FRESNEL: probability of the specular reflection at launch, ((n1-n2)/(n1+n2))^2 with the launch voxel's index
+__device__ __forceinline__ double specular_r0sq(const DevGrid &g, int ridx)
+{
+    if (!g.n_g) return g.r0sq;
+    const double n_in = __ldg(g.n_g + ridx);
+    const double r = (g.n1 - n_in) / (g.n1 + n_in);
+    return r * r;
 }
 
 __device__ __forceinline__ int exit_face_fast(const FastPhoton &p, const DevGrid &g)

@@ -77,6 +77,21 @@ __global__ void __launch_bounds__(256) k_rk_compact(const DevGrid g, double *__r
     }
 }
 
+// per-voxel albedo / hgg (tamc_set_optics_grids) in the tally's own index, for the flight kernel's event phase
+__global__ void __launch_bounds__(256) k_optics_compact(const DevGrid g, double *__restrict__ albc, double *__restrict__ hggc)
+{
+    const long long nvox = (long long)g.nxg * g.nyg * g.nzg;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += stride) {
+        const int ci = (int)(i % g.nxg);
+        const long long r = i / g.nxg;
+        const int cj = (int)(r % g.nyg), ck = (int)(r / g.nyg);
+        const long long v = (ci + 1) + (long long)g.sx * (cj + 1) + g.sxy * (ck + 1);
+        if (albc) albc[i] = __ldg(g.albedo_g + v);
+        if (hggc) hggc[i] = __ldg(g.hgg_g + v);
+    }
+}
+
 // jmean(i,j,k) = vox[idx].y
 __global__ void __launch_bounds__(256) k_vox_unpack(const DevGrid g, const double2 *__restrict__ vox)
 {
@@ -89,11 +104,10 @@ __global__ void __launch_bounds__(256) k_vox_unpack(const DevGrid g, const doubl
 // (the event phase shares that sincos with the launch): stokes.f90:40-148 as a rotation of the direction vector,
 // exactly scatter_dir() of tamc_fast.cuh.  u1 -> stokes.f90:24 / :48.  (si, ci) = sin / cos of ri1 = TWOPI*u2
 // (isotropic: of phi = TWOPI*u2, stokes.f90:32).
-__device__ __forceinline__ void scatter_rotate(const DevGrid &g, double &nzp, double &sint, double &cosp, double &sinp,
+__device__ __forceinline__ void scatter_rotate(double hgg, const ScatterConsts &sc, double &nzp, double &sint, double &cosp, double &sinp,
                                                double u1, double si, double ci)
 {
-    const ScatterConsts &sc = g.sc;
-    if (g.hgg == 0.0) {                                   // isotropic, stokes.f90:23-38
+    if (hgg == 0.0) {                                     // isotropic, stokes.f90:23-38
         const double cost = 2. * u1 - 1.;
         const double s2 = 1. - cost * cost;
         sint = (s2 <= 0.) ? 0. : sqrt(s2);
@@ -235,10 +249,12 @@ __device__ __forceinline__ void walk_step(double &tx, double &ty, double &tz, do
         : "memory");
 }
 
-template <int kBlock, int kMinCtas, bool kInter>
+template <int kBlock, int kMinCtas, bool kInter, bool kGrids = false>
 __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const DevGrid g, double *__restrict__ vox, long long n,
                                                                    uint64_t first_id, int chunk, int walk_min,
-                                                                   unsigned long long *__restrict__ cnt)
+                                                                   unsigned long long *__restrict__ cnt,
+                                                                   const double *__restrict__ albc = nullptr,
+                                                                   const double *__restrict__ hggc = nullptr)
 {
     extern __shared__ double s_faces[];
     const double *xf, *yf, *zf;
@@ -332,7 +348,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
             // azimuth: launch phi = TWOPI*u (sourceph.f90:34); scattering ri1 = TWOPI*u, beyond PI the reference works with
             // ri3 = TWOPI - ri1 (stokes.f90:66-68; with the truncated constants not exactly -ri1 mod 2 pi: same ri3 here)
             const double ri1 = kTWOPI * unit_fast(r.z);
-            const bool upper = !fresh && g.hgg != 0.0 && ri1 > kPI;
+            // kGrids: albedo / hgg of the voxel the interaction happens in (tamc_set_optics_grids), else the scalars
+            double albedo = g.albedo, hgg = g.hgg;
+            ScatterConsts sc = g.sc;
+            if (kGrids && !fresh) {
+                if (albc) albedo = __ldg(albc + idx);
+                if (hggc) { hgg = __ldg(hggc + idx); sc = make_scatter_consts(hgg); }
+            }
+            const bool upper = !fresh && hgg != 0.0 && ri1 > kPI;
             double si, co;
             fm::sincospi_0_2((upper ? kTWOPI - ri1 : ri1) * kInvPi, &si, &co);
             si = upper ? -si : si;
@@ -360,8 +383,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
                 const double ex = tx < kFar ? (tx - tend) * fabs(sint * cosp) : dtx;
                 const double ey = ty < kFar ? (ty - tend) * fabs(sint * sinp) : dty;
                 const double ez = tz < kFar ? (tz - tend) * fabs(nzp) : dtz;
-                if (unit_fast(r.x) < g.albedo) {                        // draw < albedo ? stokes : absorbed
-                    scatter_rotate(g, nzp, sint, cosp, sinp, unit_fast(r.y), si, co);
+                if (unit_fast(r.x) < albedo) {                          // draw < albedo ? stokes : absorbed
+                    scatter_rotate(hgg, sc, nzp, sint, cosp, sinp, unit_fast(r.y), si, co);
                     ++ns;
                     // ---- start of the next flight: wall_dist (inttau2.f90:75-121) from the in-voxel distances
                     const double nxp = sint * cosp, nyp = sint * sinp;

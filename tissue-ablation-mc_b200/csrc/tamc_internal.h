@@ -72,6 +72,8 @@ struct ColumnWorkspace {
     // flight kernel (tamc_flight.cuh): the interleaved {rhokap, jmean} voxel records, rebuilt per MC call
     double2 *vox = nullptr;
     size_t vox_elems = 0;
+    double *optc = nullptr;          // compact copies of the per-voxel albedo | hgg grids (tamc_set_optics_grids)
+    size_t optc_elems = 0;
 };
 
 // shipped regime: the columns every deposit lies in, and the copy between them and a dense buffer

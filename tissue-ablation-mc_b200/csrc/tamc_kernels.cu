@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
         tally.begin();
         int steps = 0, nscatt = 0, fate = 0, ndraws = 4, nb = 0;
         bool specular = false;
-        if (fresnel && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < g.r0sq) {
+        if (fresnel && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < specular_r0sq(g, p.ridx)) {
             specular = true;                                      // reflected at the top surface before entering
             fate = 6;
             ndraws = 3;
@@ -88,8 +88,11 @@ __global__ void __launch_bounds__(256) k_transport_simple(const DevGrid g, long 
             }
             if (!scatter_on) break;                               // mcpolar.f90:166-169 stub
             const uint4 w = philox_block(g, rng);
-            if (unit_fast(w.x) < g.albedo) {
-                scatter_fast(g, p, unit_fast(w.y), unit_fast(w.z), fm::neglog_u32(w.w));
+            double albedo, hgg;
+            ScatterConsts sc;
+            voxel_optics(g, p.ridx, albedo, hgg, sc);             // scalars, or the voxel's own (tamc_set_optics_grids)
+            if (unit_fast(w.x) < albedo) {
+                scatter_fast(g, p, unit_fast(w.y), unit_fast(w.z), fm::neglog_u32(w.w), hgg, sc);
                 ++nscatt;
                 ndraws += 4;
             } else {
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(256, kMinCtas) k_transport_persistent(const De
                 nscatt = 0;
                 nb = 0;
                 mode = LANE_WALK;
-                if (fresnel && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < g.r0sq) {
+                if (fresnel && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < specular_r0sq(g, p.ridx)) {
                     c.note(CNT_SPECULAR);                 // reflected at the top surface: never enters
                     c.death(6, 0, 0, false);
                     mode = LANE_IDLE;
@@ -830,7 +833,11 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
     // the thread-per-packet kernels and the `ext` build of the pool kernel only; the stub-regime and persistent kernels
     // stay as they are.  Periodic boundaries alone change nothing in the stub regime (straight-down flights).
     const bool scat = (g.flags & TAMC_SCATTER) != 0, gauss = g.gauss_sigma > 0.;
-    const bool simple_ext = scat ? (!pool && (gauss || (g.flags & TAMC_PERIODIC))) : (gauss || (g.flags & TAMC_FRESNEL));
+    // per-voxel albedo / hgg (tamc_set_optics_grids) live in the exact, thread-per-packet and flight kernels only
+    const bool vox_optics = scat && (g.albedo_g || g.hgg_g);
+    const bool flight_ok = pool && ws && cfg.flight != 0 && !((g.flags & (TAMC_FRESNEL | TAMC_PERIODIC)) != 0 || gauss);
+    const bool simple_ext = (scat ? (!pool && (gauss || (g.flags & TAMC_PERIODIC))) : (gauss || (g.flags & TAMC_FRESNEL))) ||
+                            (vox_optics && cfg.variant != 2 && !flight_ok);
     if (form) *form = cfg.variant == 2 ? FORM_EXACT : ((d_rec || cfg.variant == 0 || simple_ext) ? FORM_SIMPLE : (pool ? FORM_POOL : FORM_PERSISTENT));
     if (cfg.variant == 2) {
         if (d_rec) {
@@ -849,7 +856,7 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
         if (merge) return launch_sized(k_transport_simple<MergeTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
         return launch_sized(k_transport_simple<DirectTally32, false>, cfg, smem, n, s, g, n, seed, first_id, d_cnt, none);
     }
-    if (pool) {
+    if (pool && !simple_ext) {
         const bool ext = (g.flags & (TAMC_FRESNEL | TAMC_PERIODIC)) != 0 || gauss;      // options only the `ext` pool build carries
         if (ws && cfg.flight != 0 && !ext) {
             // flight kernel (tamc_flight.cuh): interleaved voxel records built before, tally written back after
@@ -875,14 +882,29 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
             c2.block = 256;
             cudaError_t e;
             const int regs = cfg.flight_regs ? cfg.flight_regs : (inter ? 2 : 3);
-            if (inter) {
-                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
-                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
-                else e = launch_sized(k_transport_flight<256, 3, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+            if (g.albedo_g || g.hgg_g) {
+                // per-voxel albedo / hgg: compact copies in the tally's index beside the opacities, the kGrids build
+                if (ws->optc_elems < 2 * nvox) {
+                    cudaFree(ws->optc);
+                    ws->optc = nullptr;
+                    ws->optc_elems = 0;
+                    e = cudaMalloc(&ws->optc, 2 * nvox * sizeof(double));
+                    if (e != cudaSuccess) return e;
+                    ws->optc_elems = 2 * nvox;
+                }
+                double *albc = g.albedo_g ? ws->optc : nullptr, *hggc = g.hgg_g ? ws->optc + nvox : nullptr;
+                k_optics_compact<<<cfg.num_sms * 8, 256, 0, s>>>(g, albc, hggc);
+                if (launches) *launches += 1;
+                if (inter) e = launch_sized(k_transport_flight<256, 2, true, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)albc, (const double *)hggc);
+                else e = launch_sized(k_transport_flight<256, 2, false, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)albc, (const double *)hggc);
+            } else if (inter) {
+                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                else e = launch_sized(k_transport_flight<256, 3, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
             } else {
-                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
-                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
-                else e = launch_sized(k_transport_flight<256, 3, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt);
+                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                else e = launch_sized(k_transport_flight<256, 3, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
             }
             if (e != cudaSuccess) return e;
             if (inter) k_vox_unpack<<<cfg.num_sms * 8, 256, 0, s>>>(g, ws->vox);

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_pool(const DevGr
                 steps = g5.y;
                 if (kFresnel) nb = g4.w;
                 walking = true;
-                if (fresnel && (g.flags & TAMC_FRESNEL) && nb == 0 && boundary_draw(key, S.id.x, S.id.y, nb) < g.r0sq) {
+                if (fresnel && (g.flags & TAMC_FRESNEL) && nb == 0 && boundary_draw(key, S.id.x, S.id.y, nb) < specular_r0sq(g, p.ridx)) {
                     walking = false;                      // fresh packet reflected at the top surface: never enters
                     doa = true;
                 }

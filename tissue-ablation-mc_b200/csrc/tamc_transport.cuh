@@ -62,6 +62,9 @@ struct DevGrid {
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
     const double *faces;  // xface(1:nxg+1) | yface(1:nyg+1) | zface(1:nzg+1)
+    // EXTENSION (tamc_set_optics_grids; upstream's opt_prop.f90:5 holds scalars): optional per-voxel albedo / hgg /
+    // refractive index in rhokap's layout, read-only through L2 next to rhokap; null = the scalar above
+    const double *albedo_g, *hgg_g, *n_g;
     uint32_t rk[20];      // Philox round keys of this call's seed: key + r*(0x9E3779B9, 0xBB67AE85), r = 0..9 (production kernels)
 };
 
@@ -417,10 +420,10 @@ __device__ __forceinline__ int voxel_step(const DevGrid &g, const double *xf, co
 
 // stokes.f90:6-153: new direction after a scattering event (no polarisation state exists).
 // u1 feeds stokes.f90:24 / :48, u2 feeds :32 / :64.
-__device__ __forceinline__ void stokes(const DevGrid &g, Photon &p, double u1, double u2)
+__device__ __forceinline__ void stokes(const DevGrid &g, Photon &p, double u1, double u2, double hgg, double g2)
 {
     double sinp, cosp;
-    if (g.hgg == 0.0) {
+    if (hgg == 0.0) {
         p.cost = 2. * u1 - 1.;
         double s2 = 1. - p.cost * p.cost;
         p.sint = (s2 <= 0.) ? 0. : sqrt(s2);
@@ -432,8 +435,8 @@ __device__ __forceinline__ void stokes(const DevGrid &g, Photon &p, double u1, d
         return;
     }
     const double costp = p.cost, sintp = p.sint, phip = p.phi;
-    const double q = (1. - g.g2) / (1. - g.hgg + 2. * g.hgg * u1);
-    double bmu = ((1. + g.g2) - q * q) / (2. * g.hgg);
+    const double q = (1. - g2) / (1. - hgg + 2. * hgg * u1);
+    double bmu = ((1. + g2) - q * q) / (2. * hgg);
     double cosb2 = bmu * bmu;
     if (fabs(bmu) > 1.) {
         bmu = (bmu > 1.) ? 1. : -1.;
@@ -481,7 +484,13 @@ __device__ __forceinline__ bool fresnel_reflect_exact(const DevGrid &g, const do
     if (out != 1) return false;
     const int a = (p.celli == -1) ? 0 : ((p.cellj == -1) ? 1 : 2);
     const double na = a == 0 ? p.nxp : (a == 1 ? p.nyp : p.nzp);
-    if (!(boundary_draw(key, id_lo, id_hi, nb) < fresnel_reflectance(g.n2, g.n1, fabs(na)))) return false;
+    double n_in = g.n2;
+    if (g.n_g) {                                  // the voxel the packet is leaving (tamc_set_optics_grids)
+        const int li = a == 0 ? ((na > 0.) ? g.nxg : 1) : p.celli, lj = a == 1 ? ((na > 0.) ? g.nyg : 1) : p.cellj,
+                  lk = a == 2 ? ((na > 0.) ? g.nzg : 1) : p.cellk;
+        n_in = __ldg(g.n_g + ((long long)li + (long long)g.sx * lj + g.sxy * lk));
+    }
+    if (!(boundary_draw(key, id_lo, id_hi, nb) < fresnel_reflectance(n_in, g.n1, fabs(na)))) return false;
     double s, c;
     if (a == 0) {
         p.xcur = (na > 0.) ? xf[g.nxg] - g.delta : xf[0] + g.delta;
@@ -581,7 +590,12 @@ __device__ __forceinline__ void transport_packet(const DevGrid &g, const double 
     int nb = 0;
     bool specular = false;
     if constexpr (Rng::kHasBoundary) {
-        if ((g.flags & TAMC_FRESNEL) && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < g.r0sq) {
+        double r0sq = g.r0sq;
+        if ((g.flags & TAMC_FRESNEL) && g.n_g) {
+            const double n_in = __ldg(g.n_g + ((long long)p.celli + (long long)g.sx * p.cellj + g.sxy * p.cellk));
+            r0sq = ((g.n1 - n_in) / (g.n1 + n_in)) * ((g.n1 - n_in) / (g.n1 + n_in));
+        }
+        if ((g.flags & TAMC_FRESNEL) && boundary_draw(rng.key, rng.id_lo, rng.id_hi, nb) < r0sq) {
             specular = true;                                       // reflected at the top surface before entering
             fate = 6;
             ndraws = 3;                                            // the optical depth was never drawn
@@ -614,8 +628,14 @@ __device__ __forceinline__ void transport_packet(const DevGrid &g, const double 
         }
         if (!(g.flags & TAMC_SCATTER)) break;                      // stub: tflag = .true.; exit
         rng.block(u);
-        if (u[0] < g.albedo) {
-            stokes(g, p, u[1], u[2]);
+        double albedo = g.albedo, hgg = g.hgg, g2 = g.g2;
+        if (g.albedo_g || g.hgg_g) {                               // the voxel of the interaction (tamc_set_optics_grids)
+            const long long v = (long long)p.celli + (long long)g.sx * p.cellj + g.sxy * p.cellk;
+            if (g.albedo_g) albedo = __ldg(g.albedo_g + v);
+            if (g.hgg_g) { hgg = __ldg(g.hgg_g + v); g2 = hgg * hgg; }
+        }
+        if (u[0] < albedo) {
+            stokes(g, p, u[1], u[2], hgg, g2);
             ++nscatt;
             ndraws += 4;
             recentre(g, p);

@@ -72,6 +72,13 @@ module tamc_mod
             integer(c_int), value     :: flags
         end function tamc_set_optics
 
+        !  EXTENSION (no upstream counterpart): per-voxel albedo / hgg / refractive index, each an array shaped like rhokap
+        !  or c_null_ptr for the scalar -- hence type(c_ptr) arguments (c_loc of a TARGET array)
+        integer(c_int) function tamc_set_optics_grids(handle, albedo, hgg, n) bind(C, name="tamc_set_optics_grids")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: handle, albedo, hgg, n
+        end function tamc_set_optics_grids
+
         integer(c_int) function tamc_run(handle, nphotons, seed, jmean_global, stats) bind(C, name="tamc_run")
             import :: c_int, c_int64_t, c_double, c_ptr
             type(c_ptr), value           :: handle

@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
         "tamc_set_source_co2": (i, [p, d]),
         "tamc_set_source_gaussian": (i, [p, d]),
         "tamc_set_optics": (i, [p, p, d, d, d, d, i]),
+        "tamc_set_optics_grids": (i, [p, p, p, p]),
         "tamc_run": (i, [p, i64, i64, p, C.POINTER(Stats)]),
         "tamc_run_optics": (i, [p, p, d, d, d, d, i, i64, i64, p, C.POINTER(Stats)]),
         "tamc_run_async": (i, [p, i64, i64, i64]),
@@ -127,7 +128,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = [
-    "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_source_gaussian", "tamc_set_optics", "tamc_run", "tamc_run_optics", "tamc_run_async",
+    "tamc_init", "tamc_finalize", "tamc_set_source_co2", "tamc_set_source_gaussian", "tamc_set_optics", "tamc_set_optics_grids", "tamc_run", "tamc_run_optics", "tamc_run_async",
     "tamc_sync", "tamc_get_jmean", "tamc_get_stats", "tamc_seek", "tamc_run_replay", "tamc_run_records",
     "tamc_comm_unique_id", "tamc_comm_init", "tamc_stream", "tamc_jmean_device", "tamc_rhokap_device",
     "tamc_pin_host", "tamc_unpin_host", "tamc_set_option", "tamc_get_option", "tamc_roofline_probe", "tamc_selfcheck_launch", "tamc_trace_probe",
@@ -222,6 +223,20 @@ class MCTransport:
             self._keep = rk
             ptr = rk.ctypes.data
         _ck(self.L.tamc_set_optics(self.h, ptr, float(albedo), float(hgg), float(n1), float(n2), int(flags)))
+
+    def set_optics_grids(self, albedo=None, hgg=None, n=None):
+        """EXTENSION: per-voxel albedo / hgg / refractive index, each shaped like rhokap (halo included) or None = scalar."""
+        ptrs, keep = [], []
+        for a in (albedo, hgg, n):
+            if a is None:
+                ptrs.append(None)
+                continue
+            b = np.asfortranarray(np.asarray(a, dtype=np.float64))
+            if b.shape != self.rhokap_shape:
+                raise ValueError(f"optics grids must have shape {self.rhokap_shape} (halo included)")
+            keep.append(b)
+            ptrs.append(b.ctypes.data)
+        _ck(self.L.tamc_set_optics_grids(self.h, *ptrs))
 
     def set_option(self, name: str, value: int):
         _ck(self.L.tamc_set_option(self.h, name.encode(), int(value)))
