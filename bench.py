@@ -228,13 +228,19 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(name):
-    """DRAM bytes per launch of the transport kernel from the committed ncu --set full capture."""
+def ncu_traffic(name, voxel_steps_per_launch=None):
+    """DRAM bytes per launch of the transport kernel from the committed ncu --set full capture.  A capture taken at a
+    smaller packet count than the bench launch is scaled by voxel-steps (the traffic is per voxel visited)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(name)
+            v = json.load(f).get(name)
     except Exception:
         return None
+    if isinstance(v, dict):
+        if voxel_steps_per_launch:
+            return v["dram_bytes"] * voxel_steps_per_launch / v["voxel_steps"]
+        return v["dram_bytes"]
+    return v
 
 
 class Ctx:
@@ -391,7 +397,9 @@ def roofline_block(ctx, t, name, res, steps, per_rank):
     form = t.get_option("form")
     kernel_name = FORMS.get(form, "k_transport_persistent")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(name + ":" + kernel_name) or ncu_traffic(name), "peak_source": peak_src,
+                "traffic": ncu_traffic(name + ":" + kernel_name, res["local_voxel_steps"] / steps) or ncu_traffic(name),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of this kernel "
+                                "(profiles/ncu_traffic.json), scaled by voxel-steps to this launch", "peak_source": peak_src,
                 "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes_per_voxel_step": BYTES_PER_VOXEL_STEP,
                 "voxel_steps_per_launch": res["local_voxel_steps"] / steps,
                 "bound_ncu": "instruction issue / L1TEX (the grids' hot region is L2-resident, DRAM < 1 % busy): see profiles/",

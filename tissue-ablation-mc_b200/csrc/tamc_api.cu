@@ -972,6 +972,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "walk_min")) return &h->cfg.walk_min;
     if (!strcmp(name, "flight_regs")) return &h->cfg.flight_regs;
     if (!strcmp(name, "flight_inter")) return &h->cfg.flight_inter;
+    if (!strcmp(name, "flight_agg")) return &h->cfg.flight_agg;
     if (!strcmp(name, "launch32")) return &h->launch32;
     if (!strcmp(name, "io_early")) return &h->io_early;
     if (!strcmp(name, "gather_depth")) return &h->cfg.gather_depth;

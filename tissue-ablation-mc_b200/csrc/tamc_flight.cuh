@@ -166,12 +166,45 @@ __device__ __forceinline__ void prefetch_opacity(double &dst, const double2 *p, 
 // roles (walk_step<0>(ra), walk_step<1>(rb)) -- all lanes in flight cross exactly one face per step, so the roles are the
 // same for the whole warp.  Conditional fp64 updates are written as fma with a 1.0 / 0.0 factor (exact), which is one
 // instruction where a predicated fp64 add becomes an add and two selects.
-template <int kParity>
+// kAgg (north-star: "warp-aggregated (shuffle-reduced) atomics"): lanes of the warp that tally into the SAME voxel in
+// this step are found with match.any, their deposits summed through shuffles, and one lane issues the RED.  Measured
+// (profiles/README.md, round 2): no gain on the layered-skin grid -- the deposits of a step are spread over 20-30
+// different voxels per warp and the L2 atomic unit is not the bound -- so the default build issues one RED per lane.
+__device__ __forceinline__ void aggregated_red(double *addr, double v, bool pv)
+{
+    const unsigned act = __ballot_sync(0xffffffffu, pv);
+    if (!pv) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned grp = __match_any_sync(act, (unsigned long long)addr);
+    const int most = __reduce_max_sync(act, __popc(grp));
+    double sum = v;
+    for (int k = 1; k < most; ++k) {
+        // the k-th other member of this lane's group, or the lane itself (adds nothing) when the group is smaller
+        const unsigned others = grp & ~(1u << lane);
+        const unsigned src = __fns(others, 0, k);
+        const double o = __shfl_sync(act, v, src < 32u ? src : lane);
+        if (src < 32u) sum += o;
+    }
+    if ((unsigned)(__ffs(grp) - 1) == lane) atomicAdd(addr, sum);
+}
+
+template <int kParity, bool kAgg = false>
 __device__ __forceinline__ void walk_step(double &tx, double &ty, double &tz, double &tcur, double &tmin, double &taul, double &pend,
                                           double &rcur, int &idx, int &rx, int &ry, int &rz, int &ax, int &sn, int &rn,
                                           int &steps, int &mode, double dtx, double dty, double dtz, int sax, int say, int saz,
                                           const double *rkb, unsigned slot, double *jmb, int stride)
 {
+    if (kAgg) {
+        // the deposit of this step, formed as in the block below (which then skips its own RED), through the aggregated RED
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const bool pw = mode == FL_WALK;
+        double rc = rcur;
+        if (pw) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(slot) : "memory");
+        const double tc = (tmin - tcur) * rc;
+        const bool wall = pw && tc < taul;
+        const double v = pend + tc;
+        aggregated_red(jmb + (size_t)idx * (size_t)(stride >> 3), v, wall && v != 0.);
+    }
     asm volatile(
         "{\n\t"
         ".reg .pred pw, pwall, pnw, pev, pv, pz, py, px, pout, pin, pxy, pmz, pld;\n\t"
@@ -229,6 +262,7 @@ __device__ __forceinline__ void walk_step(double &tx, double &ty, double &tz, do
         "@pev mov.s32 %16, 1;\n\t"
         "add.f64 v, %6, tc;\n\t"
         "setp.neu.and.f64 pv, v, 0d0000000000000000, pwall;\n\t"
+        "setp.eq.and.s32 pv, %27, 0, pv;\n\t"
         "@pv red.global.add.f64 [ad], v;\n\t"
         "selp.b32 hw, 0x3ff00000, 0, pwall;\n\t"
         "mov.b64 fw, {zero, hw};\n\t"
@@ -245,11 +279,11 @@ __device__ __forceinline__ void walk_step(double &tx, double &ty, double &tz, do
         "}"
         : "+d"(tx), "+d"(ty), "+d"(tz), "+d"(tcur), "+d"(tmin), "+d"(taul), "+d"(pend), "+d"(rcur), "+r"(idx), "+r"(rx),
           "+r"(ry), "+r"(rz), "+r"(ax), "+r"(sn), "+r"(rn), "+r"(steps), "+r"(mode)
-        : "d"(dtx), "d"(dty), "d"(dtz), "r"(sax), "r"(say), "r"(saz), "l"(rkb), "r"(slot), "l"(jmb), "r"(stride)
+        : "d"(dtx), "d"(dty), "d"(dtz), "r"(sax), "r"(say), "r"(saz), "l"(rkb), "r"(slot), "l"(jmb), "r"(stride), "r"(kAgg ? 1 : 0)
         : "memory");
 }
 
-template <int kBlock, int kMinCtas, bool kInter, bool kGrids = false>
+template <int kBlock, int kMinCtas, bool kInter, bool kGrids = false, bool kAgg = false>
 __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const DevGrid g, double *__restrict__ vox, long long n,
                                                                    uint64_t first_id, int chunk, int walk_min,
                                                                    unsigned long long *__restrict__ cnt,
@@ -462,8 +496,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
                 const unsigned em = __ballot_sync(full, (mode != FL_WALK && mode != FL_DEAD) || (mode == FL_DEAD && !exhausted));
                 if (em) break;
             }
-            walk_step<0>(tx, ty, tz, tcur, tmin, taul, pend, rkc, idx, rx, ry, rz, ax, sn, rn, steps, mode, dtx, dty, dtz, sax, say, saz, rkb, slot0, jmb, 8 * ws);
-            walk_step<1>(tx, ty, tz, tcur, tmin, taul, pend, rkc, idx, rx, ry, rz, ax, sn, rn, steps, mode, dtx, dty, dtz, sax, say, saz, rkb, slot1, jmb, 8 * ws);
+            walk_step<0, kAgg>(tx, ty, tz, tcur, tmin, taul, pend, rkc, idx, rx, ry, rz, ax, sn, rn, steps, mode, dtx, dty, dtz, sax, say, saz, rkb, slot0, jmb, 8 * ws);
+            walk_step<1, kAgg>(tx, ty, tz, tcur, tmin, taul, pend, rkc, idx, rx, ry, rz, ax, sn, rn, steps, mode, dtx, dty, dtz, sax, say, saz, rkb, slot1, jmb, 8 * ws);
         }
         if (exhausted && __ballot_sync(full, mode != FL_DEAD) == 0u) break;
     }

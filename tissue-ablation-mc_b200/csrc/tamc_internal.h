@@ -36,6 +36,7 @@ struct LaunchCfg {
                         // Fresnel / periodic boundaries / the Gaussian beam are selected), 0 = off, 1 = on
     int walk_min;       // flight kernel: the walk phase hands over to the event phase once fewer lanes than this are in flight
     int flight_regs;    // flight kernel: 0 = auto, 2 / 3 / 4 = the 256-thread build for that many CTAs per SM
+    int flight_agg;     // flight kernel: 1 = the build with warp-aggregated REDs (match.any + shuffles); default 0 (measured: no gain)
     int flight_inter;   // flight kernel: interleaved {opacity, tally} voxel records; -1 = auto (grids beyond L2), 0 = off, 1 = on
 };
 

@@ -901,6 +901,8 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
                 if (regs == 2) e = launch_sized(k_transport_flight<256, 2, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
                 else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
                 else e = launch_sized(k_transport_flight<256, 3, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+            } else if (cfg.flight_agg > 0) {
+                e = launch_sized(k_transport_flight<256, 3, false, false, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
             } else {
                 if (regs == 2) e = launch_sized(k_transport_flight<256, 2, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
                 else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
