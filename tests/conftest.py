@@ -12,6 +12,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: a minute or more (full-size streamed replay); still part of -m gpu")
 
 
 @pytest.fixture(scope="session")

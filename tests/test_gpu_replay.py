@@ -129,6 +129,41 @@ def test_replay_full_scale_chunk_homog200():
     assert worst < 1e-9 and gerr < 1e-10
 
 
+@pytest.mark.slow
+def test_replay_full_scale_streamed_1e8_homog200():
+    """BASELINE config 2(i) as SURVEY 8(d) states it: the homogeneous 200^3 cube, 1e8 packets, 4e8 ran2 draws (3.2 GB)
+    generated sequentially by the oracle -- ONE rank's stream, continued from chunk to chunk -- and streamed through the C
+    ABI in chunks of 1e7 packets.  Per chunk: integer fields exact, floating fields within the north-star's 1e-6 (measured
+    ~1e-9), counters equal; at the end the sum of the ten device grids against the oracle's accumulated grid."""
+    import tamc
+
+    cfg = tamc.configs.CONFIGS["homog200"]
+    rk = cfg["rhokap"]()
+    o = make_oracle(cfg, rk)
+    o.seed_ran2(3)
+    t = make_transport(cfg, rk)
+    scale = {"xp": cfg["xmax"], "yp": cfg["ymax"], "zp": cfg["zmax"], "nxp": 1.0, "nyp": 1.0, "nzp": 1.0}
+    chunk, chunks = 10_000_000, 10
+    total = np.zeros((200, 200, 200), order="F")
+    steps = 0
+    worst = 0.0
+    for c in range(chunks):
+        out = o.run(chunk, records=True, draws_cap=4 * chunk)          # the ran2 state carries over: one sequential stream
+        rec, jm = t.run_replay(out["offsets"], out["draws"])
+        st = t.get_stats()
+        worst = max(worst, compare_records(rec, out["records"], scale=scale))
+        assert st["packets"] == chunk and st["voxel_steps"] == out["stats"]["voxel_steps"]
+        assert st["absorbed"] == out["stats"]["absorbed"] == chunk
+        total += jm
+        steps += st["voxel_steps"]
+        del out, rec
+    t.close()
+    assert worst < 1e-8
+    compare_grids(total, o.jmean, rtol=1e-9)                           # the oracle's tally accumulated over the ten chunks
+    assert abs(steps / 1e8 - 1 / (1 - np.exp(-680.0 * 0.12 / 200))) < 1e-3
+    assert abs(total.sum() / 1e8 - 1.0) < 5e-4                         # E[tau] = 1 per packet
+
+
 def test_replay_phantom400_subset():
     """BASELINE config 4 (400^3, albedo 0.999, ~750 voxel-steps and ~300 scatterings per packet): a small
     subset replayed on the full-size grid (grids of 0.5 GB each exceed L2)."""

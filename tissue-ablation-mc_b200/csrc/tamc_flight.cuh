@@ -116,11 +116,14 @@ __device__ __forceinline__ void scatter_rotate(double hgg, const ScatterConsts &
         nzp = cost;
         return;
     }
-    const double q = sc.one_m_g2 * __drcp_rn(sc.one_m_g + sc.two_g * u1);   // stokes.f90:48
+    // (1 - g + 2 g u lies in [1 - |g|, 1 + |g|], 1 - bmu^2 in (0, 1] once bmu = +-1 has left: normal numbers, so the
+    // range-restricted reciprocal / roots of tamc_math.cuh apply: ~1 ulp, a third of the library versions' instructions)
+    const double q = sc.one_m_g2 * fm::rcp_normal(sc.one_m_g + sc.two_g * u1);   // stokes.f90:48
     double bmu = (sc.one_p_g2 - q * q) * sc.inv_two_g;
     bmu = fmin(1., fmax(-1., bmu));
     if (bmu == 1. || bmu == -1.) return;                               // goto 100, stokes.f90:71-77
-    const double sinbt = sqrt(1. - bmu * bmu);
+    const double s2b = 1. - bmu * bmu;
+    const double sinbt = s2b > 1e-280 ? fm::sqrt_normal(s2b) : sqrt(s2b);
     const double costp = nzp, sintp = sint;
     const double nxp = sintp * cosp, nyp = sintp * sinp;
     const double a = sinbt * ci * costp, b = sinbt * si;
@@ -132,7 +135,7 @@ __device__ __forceinline__ void scatter_rotate(double hgg, const ScatterConsts &
     // reciprocal root gives it and the new azimuth
     const double h2 = ux * ux + uy * uy;
     if (h2 > 0.) {
-        const double ih = rsqrt(h2);
+        const double ih = h2 > 1e-280 ? fm::rsqrt_normal(h2) : rsqrt(h2);
         cosp = ux * ih;
         sinp = uy * ih;
         sint = h2 * ih;
@@ -437,7 +440,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
                     if (!(zx | zy | zzr)) {
                         // one division for the three reciprocals (set_direction, tamc_fast.cuh)
                         const double xy = nxp * nyp;
-                        const double rr = __drcp_rn(xy * nzp);
+                        const double xyz = xy * nzp;
+                        const double rr = fabs(xyz) > 1e-280 ? fm::rcp_normal(xyz) : __drcp_rn(xyz);
                         inz = fabs(xy * rr);
                         const double rzz = rr * nzp;
                         inx = fabs(nyp * rzz);
