@@ -319,7 +319,10 @@ def timed_steps(ctx, t, per_rank, steps, flush=True):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     red = ctx.reduce_max([dev_ms, sums["kernel_ms"], sums["allreduce_ms"], wall * 1e3])
     tot = ctx.reduce_sum([sums["voxel_steps"], sums["scatters"], sums["launches"]])
-    return {"dev_ms": red[0], "kernel_ms": red[1], "allreduce_ms": red[2], "wall_ms": red[3],
+    per_rank = [0.0] * ctx.world
+    per_rank[ctx.rank] = sums["kernel_ms"] / steps
+    per_rank = ctx.reduce_sum(per_rank)
+    return {"dev_ms": red[0], "kernel_ms": red[1], "allreduce_ms": red[2], "wall_ms": red[3], "kernel_ms_by_rank": per_rank,
             "voxel_steps": tot[0], "scatters": tot[1], "launches": int(tot[2]),
             "local_kernel_ms": sums["kernel_ms"], "local_voxel_steps": sums["voxel_steps"]}
 
@@ -438,7 +441,7 @@ def also_homog200(ctx, options, steps=10):
     out = {"workload": workload_desc("homog200", c, per * ctx.world) + " (weak: 1e8 per GPU)",
            "packets_per_s": per * ctx.world * steps / (r["dev_ms"] * 1e-3),
            "voxel_steps_per_s": r["voxel_steps"] / (r["dev_ms"] * 1e-3), "ms_per_step": r["dev_ms"] / steps,
-           "kernel_ms": r["kernel_ms"] / steps, "allreduce_ms": r["allreduce_ms"] / steps,
+           "kernel_ms": r["kernel_ms"] / steps, "kernel_ms_by_rank": r["kernel_ms_by_rank"], "allreduce_ms": r["allreduce_ms"] / steps,
            "kernel": FORMS.get(t.get_option("form")), "allreduce_planes_of_box": int(t.get_option("reduce_planes")),
            "e2e_packets_per_s": per * ctx.world * steps / secs, "e2e_ms_per_step": 1e3 * secs / steps,
            "e2e_ms_by_grid": {"uniform": 1e3 * statistics.mean(per_call[0::2]), "crater": 1e3 * statistics.mean(per_call[1::2])},
@@ -673,7 +676,8 @@ def run_ours(args, cfg, name):
             "voxel_steps_per_s": vsteps_per_s,
             "voxel_steps_per_packet": res["voxel_steps"] / (float(total) * args.steps),
             "scatters_per_packet": res["scatters"] / (float(total) * args.steps),
-            "breakdown_ms_per_step": {"kernel": res["kernel_ms"] / args.steps, "allreduce": res["allreduce_ms"] / args.steps,
+            "breakdown_ms_per_step": {"kernel": res["kernel_ms"] / args.steps, "kernel_by_rank": res["kernel_ms_by_rank"],
+                                      "allreduce": res["allreduce_ms"] / args.steps,
                                       "wall_incl_l2_flush": res["wall_ms"] / args.steps},
             "parity_check": parity,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
