@@ -467,8 +467,10 @@ def also_homog200(ctx, options, steps=10):
             t.roofline_probe(per, SEED)
             pms, psteps = t.roofline_probe(per, SEED)
             t.set_option("probe_form", -1)
-            out["frac_of_probe_column"] = vs_rate / (psteps / (pms * 1e-3))
+            out["ratio_to_unregrouped_column_probe"] = vs_rate / (psteps / (pms * 1e-3))
             out["probe_column_ms"] = pms
+            out["probe_note"] = ("k_probe_column issues the column form's address stream packet by packet WITHOUT the regrouped walk the "
+                                 "transport uses, so it is a reference point, not a ceiling: a ratio above 1 is the gain of regrouping")
         except Exception as e:
             out["probe_error"] = str(e)
     ctx.barrier()
