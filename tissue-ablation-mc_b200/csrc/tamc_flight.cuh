@@ -1,40 +1,46 @@
 // tamc_flight.cuh -- scatter-regime transport (TAMC_SCATTER), one packet per lane, flight by flight.
 //
 // Replaces the scatter loop the driver's shell implies (mcpolar.f90:165-169 around tauint1, inttau2.f90:7-72,
-// and stokes.f90:6-153) for the default production path.  Two changes against the work-queue
-// kernel (tamc_pool.cuh), both aimed at the instruction count -- that kernel is issue-bound with 40 warp
-// instructions per scattering event (profiles/r02a_skin200_pool_ncu_summary.txt):
+// and stokes.f90:6-153) for the default production path.  The work-queue kernel of round 1
+// (tamc_pool.cuh) was issue-bound with 40 warp instructions per scattering event, 40 % of them queue management
+// (profiles/r02a_skin200_pool_ncu_summary.txt).  What is different here (DESIGN.md 3b has the measurements):
 //
-// 1. The voxel walk of one flight (tauint1's loop, inttau2.f90:37-63) is a 3-D DDA on the RAY PARAMETER instead
-//    of on the position.  At the start of a flight the three distances to the next x / y / z face are formed
-//    exactly as wall_dist does (inttau2.f90:75-121, per-event reciprocals as in tamc_fast.cuh); after that a
-//    crossing of axis a only adds the constant dt_a = (w_a - delta) * |1/n_a| to that axis' entry.  This is the
-//    reference's geometry, not an approximation of it: update_pos (inttau2.f90:140-170) puts the crossed
-//    coordinate at `face +- delta`, i.e. delta INSIDE the next voxel, so the next wall on that axis is a full
-//    voxel edge minus delta away, while the other two coordinates advance by n * dcell and keep their
-//    distances.  (Faces are (i-1)*2*max/n, gridset.f90:23-31, so w_a is constant up to the rounding of the
-//    face table, ~1e-13 of an edge.)  A voxel-step is then: min of three, one subtraction, one product, one
-//    compare, one predicated add per axis -- no face look-ups, no position update, no division.
-//    The position is only needed where the flight ends (the scattering site): per axis it is
-//    `face +- delta + n_a * (t_end - t_cross_a)` if the axis was crossed in this flight (t_cross_a = t_a - dt_a)
-//    and `start + n_a * t_end` otherwise, followed by the centred round trip of inttau2.f90:65-67 / :24-26.
+// 1. The voxel walk of one flight (tauint1's loop, inttau2.f90:37-63) is a 3-D DDA on the RAY PARAMETER.  At the
+//    start of a flight the three distances to the next x / y / z face are formed as wall_dist does
+//    (inttau2.f90:75-121, per-event reciprocals as in tamc_fast.cuh); after that a crossing of axis a only adds the
+//    constant dt_a = (w_a - delta) * |1/n_a| to that axis' entry.  This is the reference's geometry, not an
+//    approximation of it: update_pos (inttau2.f90:140-170) puts the crossed coordinate at `face +- delta`, i.e.
+//    delta INSIDE the next voxel, so the next wall on that axis is a full voxel edge minus delta away, while the
+//    other two coordinates advance by n * dcell and keep their distances.  (Faces are (i-1)*2*max/n,
+//    gridset.f90:23-31, so w_a is constant up to the rounding of the face table, ~1e-13 of an edge.)  A voxel-step
+//    is then: min of three, one subtraction, one product, one compare, predicated updates -- no face look-ups, no
+//    position update, no division.
 //
-// 2. No shared-memory pool.  Every lane keeps its packet in registers and the warp alternates between an EVENT
+// 2. Between flights a packet is described RELATIVE TO ITS VOXEL: the voxel index, per axis the number of crossings
+//    left before the grid ends (r*), and per axis the distance e_a to the face ahead -- (t_a - t_end) * |n_a| at the
+//    end of a flight, `edge - e_a` when the new direction looks at the other face.  Absolute positions and the
+//    face tables are touched once per packet, at launch.  (The centred round trip of inttau2.f90:65-67 / :24-26
+//    is a rounding of the absolute position and has no counterpart here; the deviation is of the order of the
+//    production arithmetic's, DESIGN.md "Two arithmetics".)
+//
+// 3. No shared-memory pool.  Every lane keeps its packet in registers and the warp alternates between an EVENT
 //    phase (end of flight, albedo test + stokes rotation + next optical depth -- or, for a lane whose packet
 //    ended, the launch of a new one -- all sharing one Philox block, one log and one sincos) and a WALK phase
 //    that steps every walking lane until fewer than `walk_min` lanes are still in flight.  Flights are short
-//    (2.4 voxel-steps per scattering in the layered-skin grid), a step costs ~30 instructions and an event
-//    ~300, so letting the few long flights run on while the rest of the warp waits is cheaper than moving
-//    packets through queues (a scheduling model with geometric flight lengths puts the optimum at
-//    walk_min ~ 6-8 and 15.5 warp instructions per lane-event).
+//    (2.4 voxel-steps per scattering in the layered-skin grid), so letting the few long flights run on while the
+//    rest of the warp waits is cheaper than moving packets through queues.
 //
-// Memory layout: the kernel reads the opacity and tallies the deposit of a voxel from ONE 16-byte record,
-// vox[idx] = {rhokap(i,j,k), jmean(i,j,k)}, idx = (i-1) + nxg*((j-1) + nyg*(k-1)) -- k_vox_pack builds it from
-// the resident Fortran-layout grid before the transport and k_vox_unpack writes the tally back afterwards.  The
-// load of a voxel-step and its RED then hit the same 32-byte sector: half the sectors per visited voxel, which
-// is what matters once the grids exceed L2 (400^3).  The deposit of the partial step that ends a flight stays
-// in a register (`pend`): the packet is still in that voxel after the scattering, so it is added to the first
-// deposit of the next flight and both go out as one RED when the packet leaves the voxel (or is absorbed).
+// 4. The walk step is one block of predicated PTX (walk_step): state updated in place, nothing copied at a
+//    reconvergence point; the opacity of the voxel two crossings ahead is requested with cp.async into a per-lane
+//    shared-memory slot and picked up two steps later (cp.async.wait_group 1).
+//
+// Memory layout: while the grids fit L2 the kernel reads a compact copy of the opacities (k_rk_compact: no halo,
+// the tally's own index) and tallies into g.jmean -- separate arrays on purpose: under a narrow beam the REDs into
+// the few voxels below it queue up in their L2 slices, and loads of the same sectors would wait behind them
+// (measured: 2x).  Beyond L2 (400^3) one 16-byte record per voxel, vox[idx] = {rhokap, jmean} (k_vox_pack /
+// k_vox_unpack), halves the sectors per visited voxel.  The deposit of the partial step that ends a flight stays in
+// a register (`pend`): the packet is still in that voxel after the scattering, so it is added to the first deposit
+// of the next flight and both go out as one RED when the packet leaves the voxel (or is absorbed).
 //
 // Same Philox streams (one block per event, counter = (packet id, event index)) and the same production
 // arithmetic for the launch and the rotation as tamc_fast.cuh; tests/test_gpu_production.py checks the grid and
@@ -145,30 +151,24 @@ __device__ __forceinline__ void scatter_rotate(double hgg, const ScatterConsts &
     nzp = uz;
 }
 
-// Opacity prefetch of the walk: a predicated load whose destination IS the loop-carried register (written as PTX so the
-// compiler cannot load into a temporary and copy it at the loop's end, which would wait for the load right there).
-__device__ __forceinline__ void prefetch_opacity(double &dst, const double2 *p, bool pred)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(dst) : "l"(p), "r"((int)pred));
-}
-
 // One voxel-step (inttau2.f90:37-63) of every lane in flight, as straight-line predicated PTX: every state variable is
 // updated in place, so a lane that is not walking passes through untouched and nothing is copied at a reconvergence
 // point (a compiler-generated copy of a prefetched opacity waits for the load right there).
 //   taucell = (tmin - tcur) * rcur                      inttau2.f90:39-40
 //   wall    = walking && taucell < taul                 :42   (taurun + taucell < tau)
-//   wall:   RED(vox[idx].y, pend + taucell), pend = 0, taul -= taucell, tcur = tmin,           :43-46
+//   wall:   RED(tally[idx], pend + taucell), pend = 0, taul -= taucell, tcur = tmin,           :43-46
 //           t[ax] += dt[ax], r[ax] -= 1, idx += sn                                              :48 (update_pos: face +- delta)
 //           rn < 0 ? mode = EXITED + ax                                                         :57-61
 //           the crossing after this one: tmin = min3(t) (later axis wins ties, :116-118), ax, sn, rn
-//           rcur <- vox[idx + sn].x if that crossing stays inside     (the opacity two voxels ahead)
-//   else walking: mode = EVENT (+ kParity * 4: which of the two opacity registers holds this voxel's)   :50-55 -> event phase
-// Opacity registers: the packet alternates between two, the one of the voxel it is in (rcur) and the one of the voxel
-// behind the next face (the other one, loaded one step ago).  A step consumes rcur in its first instruction and reloads it
-// at its end with the opacity two voxels ahead, so every load has two full steps to arrive; the caller alternates the
-// roles (walk_step<0>(ra), walk_step<1>(rb)) -- all lanes in flight cross exactly one face per step, so the roles are the
-// same for the whole warp.  Conditional fp64 updates are written as fma with a 1.0 / 0.0 factor (exact), which is one
-// instruction where a predicated fp64 add becomes an add and two selects.
+//           slot <- opacity[idx + sn] (cp.async) if that crossing stays inside: the opacity two voxels ahead
+//   else walking: mode = EVENT                                                                  :50-55 -> event phase
+// Opacity pipeline: each lane owns two 8-byte slots of shared memory.  A step first waits for the copy issued two steps
+// ago (cp.async.wait_group 1: the one issued in the previous step may still be in flight), reads its slot -- the opacity
+// of the voxel the packet is in -- and at its end asks for the opacity two voxels ahead into the same slot; the caller
+// alternates the slots (walk_step<0>(slot0), walk_step<1>(slot1)).  All lanes in flight cross exactly one face per step,
+// so the parity is the same for the whole warp.  (A register prefetch cannot do this: ptxas puts both loads on one
+// scoreboard, and a wait for the older one waits for the newer one too.)  Conditional fp64 updates are written as fma
+// with a 1.0 / 0.0 factor (exact), which is one instruction where a predicated fp64 add becomes an add and two selects.
 // kAgg (north-star: "warp-aggregated (shuffle-reduced) atomics"): lanes of the warp that tally into the SAME voxel in
 // this step are found with match.any, their deposits summed through shuffles, and one lane issues the RED.  Measured
 // (profiles/README.md, round 2): no gain on the layered-skin grid -- the deposits of a step are spread over 20-30
