@@ -133,6 +133,9 @@ static DevGrid make_grid(const tamc_context *c)
         g.half_x = (ex < 0.125 && c->launch32) ? (float)(0.5 - ex) : -1.f;
         g.half_y = (ey < 0.125 && c->launch32) ? (float)(0.5 - ey) : -1.f;
     }
+    g.fwx = 2. * c->xmax / (double)c->nxg; g.fwy = 2. * c->ymax / (double)c->nyg; g.fwz = 2. * c->zmax / (double)c->nzg;
+    g.wx = g.fwx - c->delta; g.wy = g.fwy - c->delta; g.wz = g.fwz - c->delta;
+    g.ez0 = g.zcur0 - (double)(g.cellk0 - 1) * 2. * c->zmax / (double)c->nzg;      // zface(cellk0), gridset.f90:29-31
     g.sc.one_m_g2 = 1. - g.g2;                                         // stokes.f90:48
     g.sc.one_p_g2 = 1. + g.g2;
     g.sc.one_m_g = 1. - g.hgg;
@@ -973,6 +976,7 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "flight_regs")) return &h->cfg.flight_regs;
     if (!strcmp(name, "flight_inter")) return &h->cfg.flight_inter;
     if (!strcmp(name, "flight_agg")) return &h->cfg.flight_agg;
+    if (!strcmp(name, "flight_launch_min")) return &h->cfg.flight_launch_min;
     if (!strcmp(name, "launch32")) return &h->launch32;
     if (!strcmp(name, "io_early")) return &h->io_early;
     if (!strcmp(name, "gather_depth")) return &h->cfg.gather_depth;

@@ -36,7 +36,7 @@ struct tamc_context {
     int nranks = 1, rank = 0;
     int64_t cursor = 0;
 
-    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0., -1, 0, 0, -1, 8, 0, 0, -1};
+    tamc::LaunchCfg cfg{3, 0, 0, 148, 0, 20, -1, 3, -1, -1, -1, -1, 0., -1, 0, 0, -1, 8, 0, 0, 3, -1};
     tamc::ColumnWorkspace colws;
     int reduce = 1;
     int reduce_bound = 1;   // all-reduce only the planes k_column_bound proves reachable (column form; 0 = every plane of the box)

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
                                                                    uint64_t first_id, int chunk, int walk_min,
                                                                    unsigned long long *__restrict__ cnt,
                                                                    const double *__restrict__ albc = nullptr,
-                                                                   const double *__restrict__ hggc = nullptr)
+                                                                   const double *__restrict__ hggc = nullptr, int launch_min = 1)
 {
     extern __shared__ double s_faces[];
     const double *xf, *yf, *zf;
@@ -318,9 +318,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
     constexpr int ws = kInter ? 2 : 1;                    // doubles per voxel record
     const int nxy = g.nxg * g.nyg;
     // voxel edges; w* = the edge minus the snap: the distance to the next face on an axis right after crossing one (header)
-    const double fwx = 2. * g.xmax / (double)g.nxg, fwy = 2. * g.ymax / (double)g.nyg, fwz = 2. * g.zmax / (double)g.nzg;
-    const double wx = fwx - g.delta, wy = fwy - g.delta, wz = fwz - g.delta;
-    const double ez0 = g.zcur0 - zf[g.cellk0 - 1];        // launch: distance down to the bottom face of the launch voxel
+    const double fwx = g.fwx, fwy = g.fwy, fwz = g.fwz, wx = g.wx, wy = g.wy, wz = g.wz;
+    const double ez0 = g.ez0;                              // launch: distance down to the bottom face of the launch voxel
 
     // ---- the packet of this lane.  Position is held relative to the voxel: during a flight through (t*, dt*), between
     // flights as e* = distance to the face AHEAD on each axis (ahead = the side the stride sa* points to).
@@ -357,7 +356,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
         // (b) packet ids for the lanes without a packet
         const unsigned deadm = __ballot_sync(full, mode == FL_DEAD);
         bool fresh = false;
-        if (deadm && !exhausted) {
+        // launches are batched: the launch path (a second sincos, a root) runs for the whole warp whenever one lane is
+        // fresh, so lanes without a packet wait until `launch_min` of them can launch together -- unless nothing else is
+        // left to do in this warp
+        const bool launch_now = __popc(deadm) >= launch_min || __ballot_sync(full, mode != FL_DEAD) == 0u;
+        if (deadm && !exhausted && launch_now) {
             if (next >= end) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(cnt + CNT_WORK, (unsigned long long)chunk);
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
             } else {
                 // ---- end of the flight (inttau2.f90:50-55): where the packet stands in its voxel
                 pend += taul;                                           // dcell*rhokap = ((tau-taurun)/rhokap)*rhokap
-                const double tend = tcur + taul * __drcp_rn(rkc);       // inttau2.f90:51
+                const double tend = tcur + taul * ((rkc > 1e-280 && rkc < 1e280) ? fm::rcp_normal(rkc) : __drcp_rn(rkc));   // inttau2.f90:51
                 const double ex = tx < kFar ? (tx - tend) * fabs(sint * cosp) : dtx;
                 const double ey = ty < kFar ? (ty - tend) * fabs(sint * sinp) : dty;
                 const double ez = tz < kFar ? (tz - tend) * fabs(nzp) : dtz;
@@ -497,7 +500,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
             if (wm == 0u) break;
             if (__popc(wm) < walk_min) {
                 // hand over to the event phase only if it has something to do
-                const unsigned em = __ballot_sync(full, (mode != FL_WALK && mode != FL_DEAD) || (mode == FL_DEAD && !exhausted));
+                const unsigned dm = __ballot_sync(full, mode == FL_DEAD || mode >= FL_EXITED);
+                const unsigned em = __ballot_sync(full, mode == FL_EVENT) | ((!exhausted && __popc(dm) >= launch_min) ? dm : 0u);
                 if (em) break;
             }
             walk_step<0, kAgg>(tx, ty, tz, tcur, tmin, taul, pend, rkc, idx, rx, ry, rz, ax, sn, rn, steps, mode, dtx, dty, dtz, sax, say, saz, rkb, slot0, jmb, 8 * ws);

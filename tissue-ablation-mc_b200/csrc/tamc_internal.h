@@ -37,6 +37,8 @@ struct LaunchCfg {
     int walk_min;       // flight kernel: the walk phase hands over to the event phase once fewer lanes than this are in flight
     int flight_regs;    // flight kernel: 0 = auto, 2 / 3 / 4 = the 256-thread build for that many CTAs per SM
     int flight_agg;     // flight kernel: 1 = the build with warp-aggregated REDs (match.any + shuffles); default 0 (measured: no gain)
+    int flight_launch_min;  // flight kernel: lanes without a packet wait until this many can launch together (1 = at once;
+                        // default 3: measured 53.2 / 51.9 / 51.6 / 51.9 / 53.1 ms per 4e7 skin200 packets for 1 / 2 / 3 / 4 / 6)
     int flight_inter;   // flight kernel: interleaved {opacity, tally} voxel records; -1 = auto (grids beyond L2), 0 = off, 1 = on
 };
 

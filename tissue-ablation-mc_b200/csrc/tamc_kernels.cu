@@ -877,6 +877,7 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
             else k_rk_compact<<<cfg.num_sms * 8, 256, 0, s>>>(g, voxd);
             const int chunk = cfg.chunk > 0 ? cfg.chunk : 64;
             const int walk_min = cfg.walk_min < 1 ? 1 : (cfg.walk_min > 32 ? 32 : cfg.walk_min);
+            const int launch_min = cfg.flight_launch_min < 1 ? 1 : (cfg.flight_launch_min > 16 ? 16 : cfg.flight_launch_min);
             const size_t fsmem = ((smem + 7) & ~(size_t)7) + (size_t)(256 / 32) * CNT_N * sizeof(unsigned long long) + 2 * 256 * sizeof(double);
             LaunchCfg c2 = cfg;
             c2.block = 256;
@@ -895,18 +896,18 @@ cudaError_t launch_transport(const DevGrid &g_in, const LaunchCfg &cfg_in, long 
                 double *albc = g.albedo_g ? ws->optc : nullptr, *hggc = g.hgg_g ? ws->optc + nvox : nullptr;
                 k_optics_compact<<<cfg.num_sms * 8, 256, 0, s>>>(g, albc, hggc);
                 if (launches) *launches += 1;
-                if (inter) e = launch_sized(k_transport_flight<256, 2, true, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)albc, (const double *)hggc);
-                else e = launch_sized(k_transport_flight<256, 2, false, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)albc, (const double *)hggc);
+                if (inter) e = launch_sized(k_transport_flight<256, 2, true, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)albc, (const double *)hggc, launch_min);
+                else e = launch_sized(k_transport_flight<256, 2, false, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)albc, (const double *)hggc, launch_min);
             } else if (inter) {
-                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
-                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
-                else e = launch_sized(k_transport_flight<256, 3, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
+                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
+                else e = launch_sized(k_transport_flight<256, 3, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
             } else if (cfg.flight_agg > 0) {
-                e = launch_sized(k_transport_flight<256, 3, false, false, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                e = launch_sized(k_transport_flight<256, 3, false, false, true>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
             } else {
-                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
-                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
-                else e = launch_sized(k_transport_flight<256, 3, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr);
+                if (regs == 2) e = launch_sized(k_transport_flight<256, 2, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
+                else if (regs == 4) e = launch_sized(k_transport_flight<256, 4, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
+                else e = launch_sized(k_transport_flight<256, 3, false>, c2, fsmem, n, s, g, voxd, n, first_id, chunk, walk_min, d_cnt, (const double *)nullptr, (const double *)nullptr, launch_min);
             }
             if (e != cudaSuccess) return e;
             if (inter) k_vox_unpack<<<cfg.num_sms * 8, 256, 0, s>>>(g, ws->vox);

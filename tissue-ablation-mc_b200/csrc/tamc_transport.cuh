@@ -59,6 +59,9 @@ struct DevGrid {
     // half < 0 switches the fp32 pass off.
     float spot_r2_f, inv_dx_f, inv_dy_f, x0_f, y0_f, half_x, half_y;
     ScatterConsts sc;
+    // flight kernel (tamc_flight.cuh): voxel edges 2*max/n, the same minus delta, and the distance from the launch height
+    // down to the bottom face of the launch voxel -- formed once on the host so the kernel reads them from the parameter bank
+    double fwx, fwy, fwz, wx, wy, wz, ez0;
     const double *rhokap; // (0:nxg+1,0:nyg+1,0:nzg+1) column-major, as uploaded
     double *jmean;        // (nxg,nyg,nzg) column-major
     const double *faces;  // xface(1:nxg+1) | yface(1:nyg+1) | zface(1:nzg+1)
