@@ -300,8 +300,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
     unsigned long long *wc = reinterpret_cast<unsigned long long *>(s_faces + nfaces) + (threadIdx.x >> 5) * CNT_N;
     // two opacity slots per lane (walk_step): the asynchronous copies of the walk land here
     double *slots = reinterpret_cast<double *>(reinterpret_cast<unsigned long long *>(s_faces + nfaces) + (kBlock >> 5) * CNT_N);
-    const unsigned slot0 = (unsigned)__cvta_generic_to_shared(slots + threadIdx.x);
-    const unsigned slot1 = (unsigned)__cvta_generic_to_shared(slots + kBlock + threadIdx.x);
+    unsigned slot0 = (unsigned)__cvta_generic_to_shared(slots + threadIdx.x);
+    asm volatile("" : "+r"(slot0));
+    unsigned slot1 = (unsigned)__cvta_generic_to_shared(slots + kBlock + threadIdx.x);
+    asm volatile("" : "+r"(slot1));          // keep both addresses in registers: re-deriving them costs three instructions per step
 
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
