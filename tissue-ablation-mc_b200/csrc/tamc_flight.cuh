@@ -51,7 +51,14 @@
 
 namespace tamc {
 
-constexpr double kFar = 1e300;       // ray parameter of a face that is never reached (direction cosine 0)
+constexpr double kFar = 1e300;
+
+// |v| is a normal number far from both ends of the exponent range (2^-1007 .. 2^993): one integer compare on the high
+// word, no 64-bit immediate -- the guard in front of the range-restricted reciprocal / roots of tamc_math.cuh
+__device__ __forceinline__ bool mid_range(double v)
+{
+    return (unsigned)((__double2hiint(v) & 0x7fffffff) - 0x01000000) < 0x7d000000u;
+}       // ray parameter of a face that is never reached (direction cosine 0)
 
 // FL_EVENT + 4: the flight ended in a step that held its voxel's opacity in the second register (walk_step<1>);
 // FL_EXITED + axis: the packet left the grid through a face of that axis
@@ -129,7 +136,7 @@ __device__ __forceinline__ void scatter_rotate(double hgg, const ScatterConsts &
     bmu = fmin(1., fmax(-1., bmu));
     if (bmu == 1. || bmu == -1.) return;                               // goto 100, stokes.f90:71-77
     const double s2b = 1. - bmu * bmu;
-    const double sinbt = s2b > 1e-280 ? fm::sqrt_normal(s2b) : sqrt(s2b);
+    const double sinbt = mid_range(s2b) ? fm::sqrt_normal(s2b) : sqrt(s2b);
     const double costp = nzp, sintp = sint;
     const double nxp = sintp * cosp, nyp = sintp * sinp;
     const double a = sinbt * ci * costp, b = sinbt * si;
@@ -141,7 +148,7 @@ __device__ __forceinline__ void scatter_rotate(double hgg, const ScatterConsts &
     // reciprocal root gives it and the new azimuth
     const double h2 = ux * ux + uy * uy;
     if (h2 > 0.) {
-        const double ih = h2 > 1e-280 ? fm::rsqrt_normal(h2) : rsqrt(h2);
+        const double ih = mid_range(h2) ? fm::rsqrt_normal(h2) : rsqrt(h2);
         cosp = ux * ih;
         sinp = uy * ih;
         sint = h2 * ih;
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
             } else {
                 // ---- end of the flight (inttau2.f90:50-55): where the packet stands in its voxel
                 pend += taul;                                           // dcell*rhokap = ((tau-taurun)/rhokap)*rhokap
-                const double tend = tcur + taul * ((rkc > 1e-280 && rkc < 1e280) ? fm::rcp_normal(rkc) : __drcp_rn(rkc));   // inttau2.f90:51
+                const double tend = tcur + taul * (mid_range(rkc) ? fm::rcp_normal(rkc) : __drcp_rn(rkc));   // inttau2.f90:51
                 const double ex = tx < kFar ? (tx - tend) * fabs(sint * cosp) : dtx;
                 const double ey = ty < kFar ? (ty - tend) * fabs(sint * sinp) : dty;
                 const double ez = tz < kFar ? (tz - tend) * fabs(nzp) : dtz;
@@ -430,10 +437,9 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
                     ++ns;
                     // ---- start of the next flight: wall_dist (inttau2.f90:75-121) from the in-voxel distances
                     const double nxp = sint * cosp, nyp = sint * sinp;
-                    const bool zx = nxp == 0., zy = nyp == 0., zzr = nzp == 0.;
-                    // an axis whose cosine changed sign now looks at the opposite face
-                    const bool fx = !zx && ((nxp < 0.) != (sax < 0)), fy = !zy && ((nyp < 0.) != (say < 0)),
-                               fz = !zzr && ((nzp < 0.) != (saz < 0));
+                    // an axis whose cosine changed sign now looks at the opposite face (a cosine of exactly 0 keeps its face)
+                    const bool fx = (nxp < 0.) != (sax < 0) && nxp != 0., fy = (nyp < 0.) != (say < 0) && nyp != 0.,
+                               fz = (nzp < 0.) != (saz < 0) && nzp != 0.;
                     const double ax_ = fx ? fwx - ex : ex, ay_ = fy ? fwy - ey : ey, az_ = fz ? fwz - ez : ez;
                     rx = fx ? (g.nxg - 1) - rx : rx;
                     ry = fy ? (g.nyg - 1) - ry : ry;
@@ -441,24 +447,25 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) k_transport_flight(const Dev
                     sax = fx ? -sax : sax;
                     say = fy ? -say : say;
                     saz = fz ? -saz : saz;
-                    double inx, iny, inz;
-                    if (!(zx | zy | zzr)) {
-                        // one division for the three reciprocals (set_direction, tamc_fast.cuh)
-                        const double xy = nxp * nyp;
-                        const double xyz = xy * nzp;
-                        const double rr = fabs(xyz) > 1e-280 ? fm::rcp_normal(xyz) : __drcp_rn(xyz);
-                        inz = fabs(xy * rr);
+                    const double xy = nxp * nyp;
+                    const double xyz = xy * nzp;
+                    if (mid_range(xyz)) {
+                        // the common case, no cosine is 0: one reciprocal for the three (set_direction, tamc_fast.cuh)
+                        const double rr = fm::rcp_normal(xyz);
+                        const double inz = fabs(xy * rr);
                         const double rzz = rr * nzp;
-                        inx = fabs(nyp * rzz);
-                        iny = fabs(nxp * rzz);
+                        const double inx = fabs(nyp * rzz), iny = fabs(nxp * rzz);
+                        tx = ax_ * inx; dtx = wx * inx;
+                        ty = ay_ * iny; dty = wy * iny;
+                        tz = az_ * inz; dtz = wz * inz;
                     } else {
-                        inx = zx ? 0. : fabs(1. / nxp);
-                        iny = zy ? 0. : fabs(1. / nyp);
-                        inz = zzr ? 0. : fabs(1. / nzp);
+                        // a cosine of 0 (or a product of cosines beyond the range of the fast reciprocal): axis by axis
+                        const bool zx = nxp == 0., zy = nyp == 0., zzr = nzp == 0.;
+                        const double inx = zx ? 0. : fabs(1. / nxp), iny = zy ? 0. : fabs(1. / nyp), inz = zzr ? 0. : fabs(1. / nzp);
+                        tx = zx ? kFar : ax_ * inx; dtx = zx ? ax_ : wx * inx;
+                        ty = zy ? kFar : ay_ * iny; dty = zy ? ay_ : wy * iny;
+                        tz = zzr ? kFar : az_ * inz; dtz = zzr ? az_ : wz * inz;
                     }
-                    tx = zx ? kFar : ax_ * inx; dtx = zx ? ax_ : wx * inx;
-                    ty = zy ? kFar : ay_ * iny; dty = zy ? ay_ : wy * iny;
-                    tz = zzr ? kFar : az_ * inz; dtz = zzr ? az_ : wz * inz;
                 } else {
                     if (pend != 0.) atomicAdd(jmb + (size_t)idx * ws, pend);
                     acc_steps += (unsigned long long)steps;
