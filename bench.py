@@ -517,24 +517,28 @@ def also_coupled_calls(ctx, options, calls=1000):
     grids = list(tamc.configs.crater_sequence(80, 16))
     for g in grids:
         tamc.pin_host(g)
-    t = make_transport(ctx, c, grids[0], options)
-    jm = t.new_jmean()
-    tamc.pin_host(jm)
     per = 125_000
-    for i in range(20):
-        t.run_optics(grids[i % 16], c["albedo"], c["hgg"], per, SEED, flags=0, out=jm)
-    ctx.barrier()
-    lat, parts = [], {"h2d_ms": 0.0, "kernel_ms": 0.0, "allreduce_ms": 0.0, "d2h_ms": 0.0, "zero_ms": 0.0}
-    w0 = time.perf_counter()
-    for i in range(calls):
-        c0 = time.perf_counter()
-        _, st = t.run_optics(grids[i % 16], c["albedo"], c["hgg"], per, SEED, flags=0, out=jm)
-        lat.append(time.perf_counter() - c0)
-        for k in parts:
-            parts[k] += st[k] / calls
-    ctx.barrier()
-    wall = ctx.reduce_max([time.perf_counter() - w0])[0]
-    lat = np.array(lat) * 1e6
+    jm = np.zeros((80, 80, 80), dtype=np.float64, order="F")
+    tamc.pin_host(jm)
+
+    def sequence(t):
+        for i in range(20):
+            t.run_optics(grids[i % 16], c["albedo"], c["hgg"], per, SEED, flags=0, out=jm)
+        ctx.barrier()
+        lat, parts = [], {"h2d_ms": 0.0, "kernel_ms": 0.0, "allreduce_ms": 0.0, "d2h_ms": 0.0, "zero_ms": 0.0}
+        w0 = time.perf_counter()
+        for i in range(calls):
+            c0 = time.perf_counter()
+            _, st = t.run_optics(grids[i % 16], c["albedo"], c["hgg"], per, SEED, flags=0, out=jm)
+            lat.append(time.perf_counter() - c0)
+            for k in parts:
+                parts[k] += st[k] / calls
+        ctx.barrier()
+        wall = ctx.reduce_max([time.perf_counter() - w0])[0]
+        return np.array(lat) * 1e6, parts, wall
+
+    t = make_transport(ctx, c, grids[0], options)
+    lat, parts, wall = sequence(t)
     out = {"calls": calls, "packets_per_call": per * ctx.world, "ranks": ctx.world,
            "mean_us": float(lat.mean()), "p50_us": float(np.percentile(lat, 50)), "p95_us": float(np.percentile(lat, 95)),
            "max_us": float(lat.max()), "packets_per_s": per * ctx.world * calls / wall,
@@ -542,6 +546,13 @@ def also_coupled_calls(ctx, options, calls=1000):
            "what": "tamc_run_optics(host rhokap -> host jmeanGLOBAL) per call, 16 crater grids in rotation (a different grid every call), "
                    "4.4 MB up + 4.1 MB down per rank per call; breakdown = device events of the parts, the rest is launch + sync latency"}
     t.close()
+    if ctx.world > 1:
+        t2 = make_transport(ctx, c, grids[0], options, root_io=1)
+        lat2, parts2, wall2 = sequence(t2)
+        out["root_io"] = {"mean_us": float(lat2.mean()), "p50_us": float(np.percentile(lat2, 50)), "p95_us": float(np.percentile(lat2, 95)),
+                          "packets_per_s": per * ctx.world * calls / wall2, "breakdown_us": {k[:-3]: 1e3 * v for k, v in parts2.items()},
+                          "what": "the same sequence with only rank 0 moving host arrays (tamc_set_option root_io)"}
+        t2.close()
     for g in grids:
         tamc.unpin_host(g)
     tamc.unpin_host(jm)
