@@ -157,9 +157,10 @@ def _deep_grid(nx, ny, nz, kappa=30.0):
                                                   ((48, 48, 96), 1, 23, 1), ((48, 48, 96), 20, 12, 0)])
 def test_depth_limited_upload_reads_deeper_planes_from_the_callers_grid(dims, depth, tile, park):
     """Columns-first upload cut at `gather_depth` planes on a grid whose packets go far deeper (mean free path ~ 8 voxels,
-    some leave through the bottom face): the transport and the finish kernel fetch what was not copied from the caller's
-    page-locked array (untiled, tiled and regrouped column kernels).  Same packets, counters and grid as the plain path
-    and as the oracle on the same Philox stream."""
+    some leave through the bottom face): k_column_bound carries the deeper planes a packet can reach from the caller's
+    page-locked array into the resident grid, where the transport and the finish kernel fetch what was not copied
+    (untiled, tiled and regrouped column kernels; the handles are fresh, so a voxel that was not carried over would be
+    read as 0).  Same packets, counters and grid as the plain path and as the oracle on the same Philox stream."""
     import tamc
 
     nx, ny, nz = dims
@@ -208,7 +209,8 @@ def test_depth_limited_upload_reads_deeper_planes_from_the_callers_grid(dims, de
 def test_depth_limit_follows_the_previous_call():
     """Auto mode: the first tamc_run_optics copies every plane of the beam's columns, the next ones only down to the
     depth the previous call reached plus a margin; when the top 40 planes vanish between two calls (packets suddenly
-    40 voxels deeper than the copied planes) the result is still exact -- the deeper planes come from the caller's array."""
+    40 voxels deeper than the copied planes) the result is still exact -- the deeper planes come from the caller's array
+    (through the resident grid, k_column_bound)."""
     import tamc
 
     cfg = tamc.configs.CONFIGS["shipped80"]
@@ -237,5 +239,41 @@ def test_depth_limit_follows_the_previous_call():
     assert 8 <= forms[0][1] <= 40 and forms[2][1] >= forms[1][1] + 30       # the third call reached far deeper
     tamc.unpin_host(jm)
     tamc.unpin_host(jr)
+    t.close()
+    ref.close()
+
+
+def test_an_abrupt_change_of_tissue_does_not_fall_off_a_cliff():
+    """homog200, the opacity drops 16-fold between two tamc_run_optics calls, so nearly every packet of the
+    next call goes below the planes the depth-limited upload copied.  Measured before k_column_bound filled the resident
+    grid: 1 160 ms for that call against 7.9 ms with every plane copied (1e8 packets).  Same result, and the call now
+    costs about what the every-plane handle pays (generous factor: host clocks on a shared box)."""
+    import time
+    import tamc
+
+    c = tamc.configs.CONFIGS["homog200"]
+    n = 20_000_000
+    rk_a = _pinned(tamc, c["rhokap"]())
+    rk_b = _pinned(tamc, np.asfortranarray(rk_a / 16.0))
+    t = tamc.MCTransport(200, 200, 200, c["xmax"], c["ymax"], c["zmax"])
+    ref = tamc.MCTransport(200, 200, 200, c["xmax"], c["ymax"], c["zmax"])
+    ref.set_option("gather_depth", 0)
+    jm, jr = _pinned(tamc, t.new_jmean()), _pinned(tamc, ref.new_jmean())
+    took = []
+    for i, g in enumerate((rk_a, rk_a, rk_a, rk_b)):
+        t0 = time.perf_counter()
+        got, st = t.run_optics(g, 0.0, 0.9, n, SEED + i, out=jm)
+        t1 = time.perf_counter()
+        want, sr = ref.run_optics(g, 0.0, 0.9, n, SEED + i, out=jr)
+        t2 = time.perf_counter()
+        took.append((t1 - t0, t2 - t1, t.get_option("io_form")))
+        for key in ("packets", "voxel_steps", "absorbed", "exits"):
+            assert st[key] == sr[key], key
+        compare_grids(got, want, rtol=1e-11)
+    assert took[2][2] == 7 and took[3][2] == 7                       # both under a depth limit; the last one far too shallow
+    assert st["exits"][4] > 0                                        # packets reached the bottom face
+    assert took[3][0] < 3.0 * took[3][1] + 2e-3, took
+    for a in (rk_a, rk_b, jm, jr):
+        tamc.unpin_host(a)
     t.close()
     ref.close()

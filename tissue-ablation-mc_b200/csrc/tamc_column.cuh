@@ -516,8 +516,16 @@ __global__ void __launch_bounds__(32 * kFinishChunks) k_column_finish(const DevG
 // down from the launch plane with the kernel's own chords until the sum passes 23; *out receives the largest number of
 // planes (from the top face, one spare) over the columns, nzg when some column never gets there.  Every rank holds the
 // same grid and gets the same number: the all-reduce (mcpolar.f90:173) moves only those planes of the box.
+//
+// Depth-limited columns-first upload (ColGeom::kz_lo > 0): a column whose copied planes do not reach optical depth 23
+// goes on in the caller's page-locked grid `cg.deep`, and -- `fill` = the resident grid -- keeps what it reads there, in
+// whole four-plane groups (the unit load_group fetches) down to the group in which the column reaches 23.  That is every
+// voxel of the column a packet of this call can read: the transport kernels then take their rare deep reads from the
+// resident grid in HBM instead of one PCIe round trip per packet and group (measured, homog200 / 1e8 packets, opacity
+// dropping 16-fold between two calls: 1 160 ms for that call before).  The full-grid upload that follows
+// beside the transport writes the same values to the same addresses.  out == nullptr: only the fill is wanted.
 __global__ void __launch_bounds__(256) k_column_bound(const DevGrid g, const ColGeom cg, const double *__restrict__ rkT, int *__restrict__ acc_max,
-                                                      unsigned int *__restrict__ done, int *__restrict__ out)
+                                                      unsigned int *__restrict__ done, int *__restrict__ out, double *__restrict__ fill)
 {
     extern __shared__ double s_dz[];
     stage_column_steps(g, cg.nzp, s_dz);                               // ends with __syncthreads()
@@ -547,10 +555,24 @@ __global__ void __launch_bounds__(256) k_column_bound(const DevGrid g, const Col
             // (depth-limited upload and a column that needs more than the copied planes: go on in the caller's grid, so the
             // answer never depends on how much this rank happened to copy)
             const int dj = c / cg.tw, di = c - dj * cg.tw;
-            const double *q = cg.deep + ((long long)(cg.i0 + di) + (long long)cg.deep_sx * (cg.j0 + dj));
-            for (kz = cg.kz_lo - 1; kz >= 0; --kz) {
-                acc += s_dz[kz] * q[cg.deep_sxy * (kz + 1)];
-                if (acc >= 23.0) { planes = min(g.nzg, g.nzg - kz + 1); break; }
+            const long long at = (long long)(cg.i0 + di) + (long long)cg.deep_sx * (cg.j0 + dj);
+            const double *q = cg.deep + at;
+            double *w = fill ? fill + at : nullptr;                     // the resident grid has the caller's layout
+            for (int gb = cg.kz_lo - 4; gb >= 0 && !found; gb -= 4) {   // kz_lo is a multiple of 32
+                double r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = q[cg.deep_sxy * (gb + j + 1)];
+                if (w) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[cg.deep_sxy * (gb + j + 1)] = r[j];
+                }
+#pragma unroll
+                for (int j = 3; j >= 0; --j) {
+                    if (!found) {
+                        acc += s_dz[gb + j] * r[j];
+                        if (acc >= 23.0) { planes = min(g.nzg, g.nzg - (gb + j) + 1); found = true; }
+                    }
+                }
             }
         }
     }
@@ -564,7 +586,8 @@ __global__ void __launch_bounds__(256) k_column_bound(const DevGrid g, const Col
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
-        *out = atomicMax(acc_max, 0);
+        const int deepest = atomicMax(acc_max, 0);
+        if (out) *out = deepest;
         *acc_max = 0;
         *done = 0u;
         __threadfence_system();

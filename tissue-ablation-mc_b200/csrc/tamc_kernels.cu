@@ -704,7 +704,10 @@ bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n)
 // The depth bound of this call for the all-reduce (k_column_bound), handed to the host through one int in mapped
 // page-locked memory.  from_copy: walk the z-fastest copy the
 // gather just made (the resident grid may still be on its way over PCIe); otherwise walk the resident grid.
-static void enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *ws, cudaStream_t s, int *launches, bool from_copy)
+// fill / to_host: see k_column_bound (depth-limited upload: the deep planes a packet can read go into the resident grid).
+// Returns whether the kernel was enqueued.
+static bool enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *ws, cudaStream_t s, int *launches, bool from_copy,
+                          double *fill = nullptr, bool to_host = true)
 {
     if (!ws->h_bound) {
         if (cudaHostAlloc((void **)&ws->h_bound, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
@@ -718,8 +721,8 @@ static void enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *
             ws->h_bound = nullptr;
         }
     }
-    if (!ws->h_bound) return;
-    *ws->h_bound = 0;
+    if (!ws->h_bound) return false;
+    if (to_host) *ws->h_bound = 0;
     // On the transport's own stream, AHEAD of the transport (10-15 us): the host waits for this answer before it can
     // enqueue the reduction, and a kernel on a side stream does not get onto the SMs while the transport's one-CTA-per-SM
     // launch holds them -- measured (TAMC_TRACE): the host then sat in that wait until the transport had finished, and
@@ -728,13 +731,17 @@ static void enqueue_bound(const DevGrid &g, const ColGeom &cg, ColumnWorkspace *
     const int cols = cg.tw * cg.th;
     if (from_copy)
         k_column_bound<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, (const double *)ws->rkT, ws->bound_scratch,
-                                                                                      reinterpret_cast<unsigned int *>(ws->bound_scratch + 1), ws->d_bound);
+                                                                                      reinterpret_cast<unsigned int *>(ws->bound_scratch + 1),
+                                                                                      to_host ? ws->d_bound : nullptr, fill);
     else
         k_column_bound_resident<<<(cols + 255) / 256, 256, sizeof(double) * (size_t)cg.nzp, sb>>>(g, cg, ws->bound_scratch,
                                                                                                reinterpret_cast<unsigned int *>(ws->bound_scratch + 1), ws->d_bound);
-    cudaEventRecord(ws->ev_bound, sb);
-    ws->bound_pending = true;
+    if (to_host) {
+        cudaEventRecord(ws->ev_bound, sb);
+        ws->bound_pending = true;
+    }
     if (launches) *launches += 1;
+    return true;
 }
 
 // Column form of the shipped regime (tamc_column.cuh): gather the beam's columns, transport, add the full-crossing term.
@@ -751,14 +758,18 @@ static cudaError_t launch_column(const DevGrid &g, const LaunchCfg &cfg, long lo
     ws->last_kz_lo = cg.kz_lo;
     if (launches && gather) *launches += 1;
     ws->bound_pending = false;
-    if (cfg.want_bound && gather) enqueue_bound(g, cg, ws, s, launches, true);
-    else if (cfg.want_bound) enqueue_bound(g, cg, ws, s, launches, false);
+    const bool deep = cg.kz_lo > 0;          // depth-limited columns-first upload: the builds that can read below the copied planes
+    if (gather && (cfg.want_bound || deep)) {
+        // depth-limited: the same walk also copies the deeper planes a packet of this call can reach into the resident grid,
+        // and the kernels below take their deep reads from there (not from the caller's array over PCIe)
+        double *fill = deep ? const_cast<double *>(g.rhokap) : nullptr;
+        if (enqueue_bound(g, cg, ws, s, launches, true, fill, cfg.want_bound) && deep) cg.deep = g.rhokap;
+    } else if (cfg.want_bound) enqueue_bound(g, cg, ws, s, launches, false);
     const size_t smem = sizeof(double) * (size_t)cg.nzp;
     LaunchCfg c2 = cfg;
     c2.block = 256;
     cudaError_t e;
     const int ta = gather ? plan.ta : 0, tb = gather ? plan.tb : 0;
-    const bool deep = cg.kz_lo > 0;          // depth-limited columns-first upload: the builds that can read the caller's grid
     if (ta + tb > 0) {
         const size_t tsmem = smem + (size_t)cg.tw * cg.th * (8 * (size_t)ta + 4 * (size_t)tb);
         const long long want = (n + 1023) / 1024;

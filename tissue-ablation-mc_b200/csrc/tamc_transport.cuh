@@ -77,8 +77,10 @@ struct ColGeom {
     int tw, th;        // its extent
     int nzp;           // column length of the z-fastest opacity copy: nzg rounded up to a multiple of 4
     // Columns-first upload over PCIe with a depth limit (tamc_run_optics, LaunchCfg::gather_depth): only planes kz = k-1
-    // >= kz_lo (a multiple of 32) were copied into the z-fastest / box copies; the rare packet that goes deeper reads the
-    // caller's page-locked grid `deep` itself (reference layout, strides deep_sx / deep_sxy).  kz_lo = 0: everything copied.
+    // >= kz_lo (a multiple of 32) were copied into the z-fastest / box copies; the rare packet that goes deeper reads
+    // `deep` (reference layout, strides deep_sx / deep_sxy): the caller's page-locked grid for k_column_bound, which copies
+    // the planes such a packet can reach into the resident grid, and that resident grid for the kernels after it.
+    // kz_lo = 0: everything copied.
     int kz_lo;
     int deep_sx;
     long long deep_sxy;
