@@ -45,3 +45,22 @@ t.set_option("reduce_bound", 2)
 t.run_async(20000, 5, 0)
 print("resident bound planes", t.get_option("reduce_planes"), "form", t.get_option("form"))
 t.close()
+# depth-limited columns-first upload on a grid whose packets go far below the copied planes: k_column_bound fills the
+# resident grid from the caller's page-locked array (untiled and regrouped column kernels)
+nx, ny, nz = 48, 40, 96
+ii, jj, kk = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), indexing="ij")
+rk = np.zeros((nx + 2, ny + 2, nz + 2), order="F")
+rk[1:-1, 1:-1, 1:-1] = 100.0 * (1.0 + 0.25 * ((ii + 2 * jj + 3 * kk) % 4))
+tamc.pin_host(rk)
+for tile, park in ((0, -1), (12, 1)):
+    t = tamc.MCTransport(nx, ny, nz, 0.03, 0.03, 0.06)
+    for k, v in (("column", 1), ("column_tile", tile), ("column_park", park), ("gather_depth", 5)):
+        t.set_option(k, v)
+    jm = t.new_jmean()
+    tamc.pin_host(jm)
+    _, st = t.run_optics(rk, 0.0, 0.9, 4 * npk, 5, out=jm)
+    print("deep fill: io_form", t.get_option("io_form"), "form", t.get_option("form"), "bottom exits", st["exits"][4], "depth_hint", t.get_option("depth_hint"))
+    assert t.get_option("io_form") == 7
+    tamc.unpin_host(jm)
+    t.close()
+tamc.unpin_host(rk)
