@@ -277,6 +277,9 @@ class Ctx:
         return t.tolist()
 
 
+PEER_VARIANT = os.environ.get("TAMC_BENCH_PEER", "0") != "0"      # also.homog200 at N > 1: time the peer-memory box reduce as well
+
+
 def make_transport(ctx, cfg, rk, options, root_io=0):
     import tamc
     from tamc import dist as tdist
@@ -459,6 +462,23 @@ def also_homog200(ctx, options, steps=10):
         out["e2e_root_io_form"] = int(t2.get_option("io_form"))
         t2.close()
         log("also.homog200: root_io e2e timed")
+    if ctx.world > 1 and PEER_VARIANT:
+        # the same device-resident steps with the box summed out of peer memory by the library's own kernel
+        # ("peer_reduce", tamc_peer.cuh) instead of by ncclAllReduce
+        try:
+            t3 = make_transport(ctx, c, rk, list(options) + ["peer_reduce=1"])
+            for _ in range(3):
+                t3.run_async(per, SEED); t3.sync()
+            r3 = timed_steps(ctx, t3, per, steps)
+            out["peer_reduce"] = {"ms_per_step": r3["dev_ms"] / steps, "packets_per_s": per * ctx.world * steps / (r3["dev_ms"] * 1e-3),
+                                  "kernel_ms": r3["kernel_ms"] / steps, "kernel_ms_by_rank": r3["kernel_ms_by_rank"],
+                                  "allreduce_ms": r3["allreduce_ms"] / steps, "peer_state": int(t3.get_option("peer_state")),
+                                  "what": "tamc_set_option(peer_reduce, 1): pack + k_peer_box_reduce (every rank sums the ranks' boxes out of "
+                                          "peer memory over NVLink, rank order) + unpack; peer_state 1 = in use, -1 = fell back to NCCL"}
+            t3.close()
+        except Exception as e:
+            out["peer_reduce"] = {"error": str(e)}
+        log("also.homog200: peer_reduce steps timed")
     if ctx.rank == 0:
         try:
             vs_rate = r["local_voxel_steps"] / steps / (r["local_kernel_ms"] / steps * 1e-3)

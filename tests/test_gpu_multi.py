@@ -120,8 +120,9 @@ def test_coupled_loop_two_ranks_equals_one_rank_with_all_packets(tmp_path):
     t.close()
 
 
-def _stub_worker(rank, world, port, out):
+def _stub_worker(rank, world, port, out, peer=0):
     import sys
+    import time
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "tissue-ablation-mc_b200")]
@@ -137,6 +138,7 @@ def _stub_worker(rank, world, port, out):
     cfg = tamc.configs.CONFIGS["shipped80"]
     t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=rank)
     t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
+    t.set_option("peer_reduce", peer)                 # the box all-reduce out of peer memory instead of by NCCL (tamc_peer.cuh)
     t.comm_init(world, rank, tdist.broadcast_unique_id(tamc.comm_unique_id, dist))
     grids = []
     for column, box, bound in ((0, 0, 1), (0, -1, 1), (1, -1, 1), (1, 1, 1), (2, 0, 1), (1, -1, 0)):
@@ -167,15 +169,29 @@ def _stub_worker(rank, world, port, out):
     assert int(both[0]) in (5, 7, 8) and int(both[1]) in (1, 4), [int(b) for b in both]
     assert t.get_option("reduce_planes") == 24
     grids.append(mixed.copy())
+    if peer:
+        # many calls in a row (the two buffer halves alternate), the ranks arriving at different times
+        first = None
+        for i in range(24):
+            if i % 5 == rank:
+                time.sleep(0.02)
+            t.seek(0)
+            jm, st = t.run(60000, 7)
+            first = jm.copy() if first is None else first
+            assert np.allclose(jm, first, rtol=1e-12, atol=0), i
+        with open(f"{out}.{rank}.state", "w") as f:
+            f.write(str(t.get_option("peer_state")))
     np.save(f"{out}.{rank}.npy", np.stack(grids))
     dist.barrier()
     t.close()
     dist.destroy_process_group()
 
 
-def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
+@pytest.mark.parametrize("peer", [0, 1])
+def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path, peer):
     """Shipped (stub) regime on two ranks: reducing only the columns under the beam equals reducing the whole grid, for
-    the step-by-step kernel and for the column form, and equals one GPU running all the ids."""
+    the step-by-step kernel and for the column form, and equals one GPU running all the ids.  peer = 1: the box is summed
+    out of the other rank's buffer by k_peer_box_reduce ("peer_reduce") instead of by ncclAllReduce."""
     import torch
 
     import tamc
@@ -186,9 +202,10 @@ def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
     import torch.multiprocessing as mp
 
     out = str(tmp_path / "stub")
-    mp.spawn(_stub_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_stub_worker, args=(2, _free_port(), out, peer), nprocs=2, join=True)
     a, b = np.load(out + ".0.npy"), np.load(out + ".1.npy")
     assert np.array_equal(a, b)
+    states = [int(open(f"{out}.{r}.state").read()) for r in range(2)] if peer else []
     cfg = tamc.configs.CONFIGS["shipped80"]
     t = tamc.MCTransport(80, 80, 80, cfg["xmax"], cfg["ymax"], cfg["zmax"], device=0)
     t.set_optics(cfg["rhokap"](), cfg["albedo"], cfg["hgg"], flags=0)
@@ -203,3 +220,6 @@ def test_shipped_regime_box_allreduce_and_column_form_two_ranks(tmp_path):
     t.run_async(5_400_000, 7, 0)
     compare_grids(a[-1], t.get_jmean(), rtol=1e-10)     # ranks of different packet counts / kernel forms
     t.close()
+    if peer and states != [1, 1]:
+        assert states == [-1, -1], states                # the ranks agree on the fallback
+        pytest.skip("CUDA IPC between the two processes is not available here: the box went through ncclAllReduce")

@@ -242,11 +242,35 @@ extern "C" int tamc_init(int device, int nxg, int nyg, int nzg, double xmax, dou
     return TAMC_OK;
 }
 
+// "peer_reduce": give the buffers back.  The other ranks read this rank's buffer in their own k_peer_box_reduce, which may
+// still be running when this rank's stream has drained: wait (bounded) until each of them has flagged the last call done.
+static void peer_release(tamc_handle h)
+{
+    if (h->peer_state == 1 && h->peer_base) {
+        unsigned long long flags[tamc::kPeerCounter];
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            if (cudaMemcpy(flags, h->peer_base, sizeof(flags), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+            bool done = true;
+            for (int r = 0; r < h->nranks; ++r)
+                if (r != h->rank && flags[tamc::kPeerDone + r] < h->peer_call) done = false;
+            if (done || std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) break;
+        }
+    }
+    for (int r = 0; r < tamc::kPeerMaxRanks; ++r)
+        if (h->peer_open[r]) { cudaIpcCloseMemHandle(h->peer_open[r]); h->peer_open[r] = nullptr; }
+    if (h->peer_base) { cudaFree(h->peer_base); h->peer_base = nullptr; }
+    if (h->h_peer_err) { cudaFreeHost(h->h_peer_err); h->h_peer_err = nullptr; h->d_peer_err = nullptr; }
+    h->peer_state = 0;
+    cudaGetLastError();
+}
+
 extern "C" int tamc_finalize(tamc_handle h)
 {
     if (!h) return TAMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    peer_release(h);
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     tamc_heat_release_(h);
     cudaFree(h->d_rhokap); cudaFree(h->d_jmean); cudaFree(h->d_faces); cudaFree(h->d_flush);
@@ -414,7 +438,7 @@ extern "C" int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *i
     if (nranks > 1) {
         const double fp[16] = {(double)h->nxg, (double)h->nyg, (double)h->nzg, h->xmax, h->ymax, h->zmax, h->delta, h->spot,
                                h->gauss_sigma, (double)h->reduce, (double)h->box_reduce, (double)h->reduce_bound,
-                               (double)TAMC_VERSION, (double)h->root_io, 0., 0.};
+                               (double)TAMC_VERSION, (double)h->root_io, (double)h->peer_reduce, 0.};
         double *d_fp = nullptr;
         CU(cudaMalloc(&d_fp, 32 * sizeof(double)));
         double both[32];
@@ -437,6 +461,79 @@ extern "C" int tamc_comm_init(tamc_handle h, int nranks, int rank, const void *i
 // ------------------------------------------------------------------------------------------------
 // the hot path
 // ------------------------------------------------------------------------------------------------
+// "peer_reduce": one-time set-up of the buffers the ranks read from each other (tamc_peer.cuh).  Collective: every rank
+// reaches it in the same call (the option is part of tamc_comm_init's fingerprint, the element count is the same on
+// every rank).  Any rank that cannot export or map a buffer -- ranks in one process, no peer access, another node -- and
+// all ranks agree to stay with ncclAllReduce (peer_state = -1).
+static int peer_setup(tamc_handle h, size_t elems_needed)
+{
+    h->peer_state = -1;
+    const int nr = h->nranks;
+    if (nr > tamc::kPeerMaxRanks) return TAMC_OK;
+    NcclApi *n = nccl_api();
+    int mine_ok = 1;
+    const size_t elems = (elems_needed + 1) & ~(size_t)1;
+    const size_t bytes = tamc::kPeerFlagBytes + 2 * elems * sizeof(double);
+    cudaIpcMemHandle_t hm;
+    memset(&hm, 0, sizeof(hm));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle table below carries 16 words per rank");
+    if (cudaMalloc(&h->peer_base, bytes) != cudaSuccess) { cudaGetLastError(); h->peer_base = nullptr; mine_ok = 0; }
+    if (mine_ok && cudaMemsetAsync(h->peer_base, 0, tamc::kPeerFlagBytes, h->stream) != cudaSuccess) { cudaGetLastError(); mine_ok = 0; }
+    if (mine_ok && cudaIpcGetMemHandle(&hm, h->peer_base) != cudaSuccess) { cudaGetLastError(); mine_ok = 0; }
+    if (mine_ok && !h->h_peer_err) {
+        if (cudaHostAlloc((void **)&h->h_peer_err, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void **)&h->d_peer_err, h->h_peer_err, 0) != cudaSuccess) {
+            cudaGetLastError();
+            mine_ok = 0;
+        } else
+            *h->h_peer_err = 0u;
+    }
+    // every rank's handle (16 words) + its "fine so far": an all-reduce(sum) of a table that is zero outside the own row
+    constexpr int W = 17;
+    int table[tamc::kPeerMaxRanks * W];
+    memset(table, 0, sizeof(table));
+    memcpy(&table[h->rank * W], &hm, sizeof(hm));
+    table[h->rank * W + 16] = mine_ok;
+    int *d_tab = nullptr;
+    CU(cudaMalloc(&d_tab, sizeof(table)));
+    CU(cudaMemcpyAsync(d_tab, table, sizeof(table), cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = n->AllReduce(d_tab, d_tab, tamc::kPeerMaxRanks * W, ncclInt, ncclSum, h->comm, h->stream);
+    cudaError_t e = cudaMemcpyAsync(table, d_tab, sizeof(table), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (r != ncclSuccess || e != cudaSuccess) { cudaFree(d_tab); return fail(TAMC_ENCCL, "peer_reduce: exchanging the buffer handles failed"); }
+    int all_ok = 1;
+    for (int q = 0; q < nr; ++q) all_ok &= table[q * W + 16] == 1;
+    if (all_ok) {
+        for (int q = 0; q < nr && all_ok; ++q) {
+            if (q == h->rank) continue;
+            cudaIpcMemHandle_t hq;
+            memcpy(&hq, &table[q * W], sizeof(hq));
+            if (cudaIpcOpenMemHandle(&h->peer_open[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                h->peer_open[q] = nullptr;
+                all_ok = 0;
+            }
+        }
+    }
+    // ... and whether every rank could map every other rank's buffer
+    int agreed = all_ok;
+    CU(cudaMemcpyAsync(d_tab, &agreed, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    r = n->AllReduce(d_tab, d_tab, 1, ncclInt, ncclMin, h->comm, h->stream);
+    e = cudaMemcpyAsync(&agreed, d_tab, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_tab);
+    if (r != ncclSuccess || e != cudaSuccess) return fail(TAMC_ENCCL, "peer_reduce: agreeing on the buffer mappings failed");
+    if (agreed != 1) {
+        peer_release(h);
+        h->peer_state = -1;
+        return TAMC_OK;
+    }
+    h->peer_elems = elems;
+    h->peer_call = 0;
+    h->peer_state = 1;
+    return TAMC_OK;
+}
+
 static int enqueue_reduce(tamc_handle h)
 {
     h->timed_reduce = false;
@@ -476,8 +573,26 @@ static int enqueue_reduce(tamc_handle h)
                 CU(cudaMalloc(&h->colws.dense, cnt * sizeof(double)));
                 h->colws.dense_elems = cnt;
             }
-            CU(launch_box_copy(g, cg, h->colws.dense, false, h->num_sms, h->stream, kz0));
-            NC(nccl_api()->AllReduce(h->colws.dense, h->colws.dense, cnt, ncclDouble, ncclSum, h->comm, h->stream));
+            // "peer_reduce": the few MB of the box summed straight out of the other ranks' buffers (tamc_peer.cuh) -- no NCCL
+            // kernel between two transport kernels; buffers sized once for every plane of the box
+            if (h->peer_reduce && h->peer_state == 0) {
+                if (int rc = peer_setup(h, (size_t)cg.tw * cg.th * (size_t)h->nzg)) return rc;
+            }
+            if (h->peer_reduce && h->peer_state == 1 && cnt <= h->peer_elems) {
+                const unsigned long long call = ++h->peer_call;
+                const size_t half = (size_t)(call & 1ull) * h->peer_elems;
+                tamc::PeerSet ps{};
+                for (int q = 0; q < h->nranks; ++q) {
+                    char *base = (char *)(q == h->rank ? h->peer_base : h->peer_open[q]);
+                    ps.flags[q] = reinterpret_cast<unsigned long long *>(base);
+                    ps.buf[q] = reinterpret_cast<const double *>(base + tamc::kPeerFlagBytes) + half;
+                }
+                CU(launch_box_copy(g, cg, const_cast<double *>(ps.buf[h->rank]), false, h->num_sms, h->stream, kz0));
+                CU(launch_peer_box_reduce(ps, h->colws.dense, cnt, h->nranks, h->rank, call, h->d_peer_err, h->num_sms, h->stream));
+            } else {
+                CU(launch_box_copy(g, cg, h->colws.dense, false, h->num_sms, h->stream, kz0));
+                NC(nccl_api()->AllReduce(h->colws.dense, h->colws.dense, cnt, ncclDouble, ncclSum, h->comm, h->stream));
+            }
             CU(launch_box_copy(g, cg, h->colws.dense, true, h->num_sms, h->stream, kz0));
         } else {
             NC(nccl_api()->AllReduce(h->d_jmean, h->d_jmean, h->n_jmean, ncclDouble, ncclSum, h->comm, h->stream));
@@ -578,6 +693,10 @@ extern "C" int tamc_get_stats(tamc_handle h, tamc_stats *st)
     if (h->timed_h2d && (h->io_form & 2)) st->kernel_ms -= st->h2d_ms;     // k_column_gather over PCIe sits inside K0..K1
     if (h->timed_d2h) { CU(cudaEventElapsedTime(&ms, h->ev[EV_D0], h->ev[EV_D1])); st->d2h_ms = ms; }
     st->gpu_launches = h->last_launches;
+    if (h->h_peer_err && *(volatile unsigned int *)h->h_peer_err) {
+        *h->h_peer_err = 0u;
+        return fail(TAMC_ENCCL, "peer_reduce: another rank's box did not arrive within 20 s; the tally of this call is not reduced");
+    }
     if (cnt[CNT_ERRORS])
         return fail(TAMC_EINVAL, "transport: " + std::to_string(cnt[CNT_ERRORS]) + " packet(s) exceeded the voxel-step cap");
     return TAMC_OK;
@@ -989,6 +1108,8 @@ static int *option_slot(tamc_handle h, const char *name)
     if (!strcmp(name, "form")) return &h->form;
     if (!strcmp(name, "box_io")) return &h->box_io;
     if (!strcmp(name, "root_io")) return &h->root_io;
+    if (!strcmp(name, "peer_reduce")) return &h->peer_reduce;
+    if (!strcmp(name, "peer_state")) return &h->peer_state;
     if (!strcmp(name, "io_form")) return &h->io_form;
     return nullptr;
 }
@@ -1006,6 +1127,9 @@ extern "C" int tamc_set_option(tamc_handle h, const char *name, int64_t value)
     if (slot == &h->cfg.block && (value < 0 || value > 256 || value % 32)) return fail(TAMC_EINVAL, "block must be 0 (auto) or a multiple of 32 up to 256");
     if (slot == &h->cfg.variant && (value < 0 || value > 3)) return fail(TAMC_EINVAL, "variant must be 0..3");
     if (slot == &h->root_io && (value < 0 || value > 1)) return fail(TAMC_EINVAL, "root_io must be 0 or 1");
+    if (slot == &h->peer_state) return fail(TAMC_EINVAL, "peer_state is read-only: 1 = the box all-reduce runs out of peer memory, -1 = not available here (NCCL)");
+    if (slot == &h->peer_reduce && (value < 0 || value > 1)) return fail(TAMC_EINVAL, "peer_reduce must be 0 or 1");
+    if (slot == &h->peer_reduce && h->comm) return fail(TAMC_ESTATE, "peer_reduce shapes the collectives of every call: set it on every rank before tamc_comm_init");
     if (slot == &h->root_io && h->comm) return fail(TAMC_ESTATE, "root_io shapes the collectives of every call: set it on every rank before tamc_comm_init");
     if (slot == &h->cfg.flight && (value < -1 || value > 1)) return fail(TAMC_EINVAL, "flight must be -1 (auto), 0 or 1");
     if (slot == &h->cfg.walk_min && (value < 1 || value > 32)) return fail(TAMC_EINVAL, "walk_min must be in [1,32]");

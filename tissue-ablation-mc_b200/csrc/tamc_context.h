@@ -53,6 +53,14 @@ struct tamc_context {
     int root_io = 0;        // several ranks: 1 = only rank 0's host arrays are read / written (broadcast + root download); set before tamc_comm_init
     bool resident_behind = false;   // root_io: ranks > 0 hold only the beam's columns of the last uploaded grid (sync_resident, tamc_api.cu)
     int *d_path = nullptr;  // root_io: the copy path rank 0 chose for this call, broadcast to the other ranks
+    // "peer_reduce": the box all-reduce of the stub regime summed out of peer memory instead of by NCCL (tamc_peer.cuh)
+    int peer_reduce = 0;        // 0 = NCCL, 1 = own kernel; set on every rank before tamc_comm_init
+    int peer_state = 0;         // 0 = not set up yet, 1 = ready, -1 = unavailable on this node / in this process layout (NCCL is used)
+    void *peer_base = nullptr;  // own allocation: flag words + two buffer halves; exported to the other ranks
+    void *peer_open[16] = {};   // the other ranks' allocations (cudaIpcOpenMemHandle)
+    size_t peer_elems = 0;      // doubles per buffer half (even)
+    unsigned long long peer_call = 0;       // calls reduced this way so far (the flag value of the next one is peer_call + 1)
+    unsigned int *h_peer_err = nullptr, *d_peer_err = nullptr;   // mapped host word: a peer's flag did not arrive in time
     int io_form = 0;        // read-only: bit0 = the last tamc_run downloaded zero fill + beam columns, bit1 = the last
                             // tamc_run_optics uploaded the beam columns ahead of the grid, bit2 = ... and only down to the
                             // depth the previous call's packets reached (+ margin)

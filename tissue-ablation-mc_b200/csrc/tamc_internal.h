@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "tamc_transport.cuh"
+#include "tamc_peer.cuh"
 
 namespace tamc {
 
@@ -86,6 +87,9 @@ bool beam_box(const DevGrid &g, ColGeom &cg);
 bool column_gather_selected(const DevGrid &g, const LaunchCfg &cfg, long long n);
 cudaError_t launch_box_copy(const DevGrid &g, const ColGeom &cg, double *dense, bool unpack, int num_sms, cudaStream_t s, int kz0 = 0);
 cudaError_t launch_box_mirror(const DevGrid &g, const ColGeom &cg, double *dst, int num_sms, cudaStream_t s);
+// "peer_reduce" (tamc_peer.cuh): out[i] = sum over the ranks of their packed boxes, read from peer memory; *err = mapped host word
+cudaError_t launch_peer_box_reduce(const PeerSet &ps, double *out, size_t cnt, int nranks, int rank, unsigned long long call,
+                                   unsigned int *err, int num_sms, cudaStream_t s);
 
 // production transport (Philox).  d_rec may be null; when non-null the thread-per-packet kernel is used.
 // ws may be null (no column form).

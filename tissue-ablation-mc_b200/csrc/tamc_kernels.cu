@@ -605,6 +605,21 @@ cudaError_t launch_box_mirror(const DevGrid &g, const ColGeom &cg, double *dst, 
     return cudaGetLastError();
 }
 
+cudaError_t launch_peer_box_reduce(const PeerSet &ps, double *out, size_t cnt, int nranks, int rank, unsigned long long call,
+                                   unsigned int *err, int num_sms, cudaStream_t s)
+{
+    // a few MB: enough CTAs to keep (nranks - 1) NVLink reads per thread in flight on every SM, no more (each CTA polls the flags)
+    const size_t pairs = (cnt + 1) >> 1;
+    size_t want = (pairs + 255) / 256;
+    const int grid = (int)(want < (size_t)num_sms * 4 ? (want ? want : 1) : (size_t)num_sms * 4);
+    const unsigned long long timeout_ns = 20ull * 1000000000ull;      // a rank that never arrives: give up, report, do not hang the GPU
+    if (nranks == 2) k_peer_box_reduce<2><<<grid, 256, 0, s>>>(ps, out, cnt, nranks, rank, call, timeout_ns, err);
+    else if (nranks == 4) k_peer_box_reduce<4><<<grid, 256, 0, s>>>(ps, out, cnt, nranks, rank, call, timeout_ns, err);
+    else if (nranks == 8) k_peer_box_reduce<8><<<grid, 256, 0, s>>>(ps, out, cnt, nranks, rank, call, timeout_ns, err);
+    else k_peer_box_reduce<0><<<grid, 256, 0, s>>>(ps, out, cnt, nranks, rank, call, timeout_ns, err);
+    return cudaGetLastError();
+}
+
 // the workspace of the column form (+ the z-fastest copy of the opacities under the box)
 static cudaError_t column_setup(const DevGrid &g, ColumnWorkspace *ws, bool gather, cudaStream_t s, ColGeom &cg, int gather_planes = 0)
 {
