@@ -196,17 +196,36 @@ double *tamc_rhokap_device(tamc_handle h); /* device opacity grid with halo */
 /* Page-lock a caller-owned host array once so uploads/downloads run at PCIe speed. */
 int tamc_pin_host(void *ptr, uint64_t bytes);
 int tamc_unpin_host(void *ptr);
-/* Tuning knobs: "variant" (0 thread-per-packet, 1 persistent warps, 2 exact arithmetic, 3 = default:
- * work-queue regrouping when scattering; in the shipped stub regime the column form for large calls,
- * persistent warps otherwise), "block" (0 = auto), "ctas_per_sm", "chunk", "scatter_min", "merge",
- * "min_ctas", "tile" / "column" (-1 = auto, 0 = off, > 0 = force), "column_tile" (shared-memory
- * tiles of the column form: -1 = auto, 0 = off, 10*ta + tb = ta planes of deposits and tb planes of
- * stop counts), "column_park" (regrouped column walk of a tiled call: -1 = auto from the previous call's
- * voxel-steps per packet -- off in a process that holds a communicator, where it measured slower --, 0 = off, 1 = on), "launch32" (column form: fp32 first pass of the launch voxel, 1 = on), "reduce" (0 = skip the all-reduce), "reduce_bound" (column form: all-reduce only the planes of the box that a packet of the call can reach -- the optical depth of a packet is at most 33 ln 2, so every rank derives the same bound from its copy of the grid; 1 = on, 0 = every plane, 2 = compute it even without a communicator; read-only "reduce_planes" = the planes the last all-reduce moved), "box_reduce" / "box_io" (-1 = auto, 0 = move the
- * whole grid), "probe_form" (tamc_roofline_probe: -1 = the form the transport would take, 0 =
- * per-voxel-step address stream, 1 = column-form address stream).  Read-only: "form" = the kernel the
- * last MC call ran (0 thread-per-packet, 1 persistent, 2 exact, 3 pool, 4 tile, 5 column, 6 column on
- * the resident grid, 7 column with shared-memory tiles, 8 the same with the regrouped walk), "io_form" (see tamc_run_optics). */
+/* Tuning knobs (every default is the measured best; profiles/README.md):
+ *   "variant"       0 thread-per-packet, 1 persistent warps, 2 exact arithmetic, 3 = default: with the scatter loop the
+ *                   flight kernel (or the work-queue kernel, "flight" = 0); in the shipped stub regime the column form
+ *                   for large calls, persistent warps otherwise
+ *   "block" (0 = auto), "ctas_per_sm", "chunk", "scatter_min", "merge", "min_ctas"
+ *   "flight"        scatter loop: -1 = auto (flight kernel unless Fresnel / periodic boundaries / the Gaussian beam are
+ *                   selected), 0 = work-queue kernel, 1 = flight kernel; "walk_min" (1..32, default 8), "flight_regs"
+ *                   (0 = auto, 2 / 3 / 4 CTAs per SM), "flight_launch_min" (default 3), "flight_inter" (interleaved
+ *                   {opacity, tally} records: -1 = auto, beyond L2 only), "flight_agg" (1 = warp-aggregated REDs; slower)
+ *   "tile" / "column"   stub regime: -1 = auto, 0 = off, > 0 = force; "column_tile" (shared-memory tiles of the column
+ *                   form: -1 = auto, 0 = off, 10*ta + tb = ta planes of deposits and tb planes of stop counts);
+ *                   "column_park" (regrouped column walk of a tiled call: -1 = auto from the previous call's voxel-steps
+ *                   per packet, 0 = off, 1 = on); "launch32" (fp32 first pass of the launch voxel, 1 = on)
+ *   "gather_depth"  tamc_run_optics, columns-first upload: planes below the top face copied ahead of the transport
+ *                   (-1 = auto from the previous call, 0 = all); deeper planes a packet can reach follow through
+ *                   k_column_bound, so the result never depends on it; "io_early"; "box_io" (-1 = auto, 0 = plain copies)
+ *   "reduce" (0 = skip the all-reduce), "box_reduce" (-1 = auto, 0 = all-reduce the whole grid), "reduce_bound" (all-reduce
+ *                   only the planes of the box that a packet of the call can reach -- the optical depth of a packet is at
+ *                   most 33 ln 2, so every rank derives the same bound from its copy of the grid; 1 = on, 0 = every
+ *                   plane, 2 = compute it even without a communicator)
+ *   "root_io"       several ranks: 1 = only rank 0's host arrays are read / written; before tamc_comm_init
+ *   "peer_reduce"   several ranks on one node: 1 = the stub regime's box all-reduce is summed straight out of the other
+ *                   ranks' buffers (CUDA IPC, NVLink) by the library's own kernel instead of ncclAllReduce; falls back to
+ *                   NCCL (every rank alike) where the buffers cannot be mapped; before tamc_comm_init; default 0
+ *   "probe_form"    tamc_roofline_probe: -1 = the form the transport would take, 0 = per-voxel-step address stream, 1 =
+ *                   column-form address stream
+ * Read-only: "form" = the kernel the last MC call ran (0 thread-per-packet, 1 persistent, 2 exact, 3 work-queue pool,
+ * 4 tile, 5 column, 6 column on the resident grid, 7 column with shared-memory tiles, 8 the same with the regrouped walk,
+ * 9 flight kernel), "io_form" (see tamc_run_optics), "reduce_planes" (planes of the box the last all-reduce moved),
+ * "depth_hint", "peer_state" (1 = peer_reduce in use, -1 = not available here). */
 int tamc_set_option(tamc_handle h, const char *name, int64_t value);
 int64_t tamc_get_option(tamc_handle h, const char *name);
 /* Access-pattern-only kernel: the tally/grid address stream of `nphotons` straight-down packets
