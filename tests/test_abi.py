@@ -70,3 +70,18 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".f90", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not pat.search(text), (dirpath, f)
+
+
+def test_every_option_name_is_documented_in_the_header():
+    """tamc_set_option / tamc_get_option take names: each one the library knows (option_slot, tamc_api.cu) is described in
+    include/tamc.h, the only interface document a binding author reads."""
+    import re
+
+    src = open(os.path.join(ROOT, "tissue-ablation-mc_b200", "csrc", "tamc_api.cu")).read()
+    body = src[src.index("static int *option_slot("):]
+    body = body[:body.index("\n}\n")]
+    names = re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', body)
+    assert len(names) >= 30
+    header = open(os.path.join(ROOT, "include", "tamc.h")).read()
+    missing = [n for n in names if f'"{n}"' not in header]
+    assert not missing, missing
