@@ -149,7 +149,9 @@ int tamc_run(tamc_handle h, int64_t nphotons, int64_t seed, double *jmean_global
  * kernels plus a pitched copy of those columns, and the opacities of those columns are uploaded ahead
  * of the full grid, which follows on a second stream.  From the second such call on, the columns go up only down to the
  * depth the previous call's packets reached plus a margin ("gather_depth": -1 auto, 0 = every plane, n = n planes; the
- * rare packet that goes deeper reads the caller's array directly), and the download skips the rows that hold only zeros.
+ * deeper planes a packet of the call can still reach -- optical depth at most 33 ln 2 -- are fetched ahead of the
+ * transport by the depth-bound kernel, so the result never depends on the limit), and the download skips the rows that
+ * hold only zeros.
  * Options "box_io" (-1 auto, 0 = plain copies in sequence) and read-only "io_form" (bit0: columns-only download, bit1:
  * columns-first upload, bit2: depth-limited), "io_early" (bit0 / bit1: start the full-grid upload / the zero fill beside the
  * column gather instead of behind it; measured slower, default 0) and "depth_hint" (planes from the top face to the deepest stop of the last
