@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
 ``--impl reference`` legs of bench.py.  The product (libtamc.so, the ``tamc`` package) never
-imports this module.  PARITY UNPINNED BY THE REFERENCE -- see tamc_oracle.h.
+imports this module.  Parity: pinned to outputs of the reference's own source text run by oracle/f90interp.py, not to a
+compiled reference -- see tamc_oracle.h.
 """
 from __future__ import annotations
 
@@ -104,6 +105,12 @@ def _bind(path: str) -> C.CDLL:
     for f in ("orc_ran2_idum", "orc_ran2_idum2", "orc_ran2_iy"):
         getattr(lib, f).restype = i
         getattr(lib, f).argtypes = [p]
+    lib.orc_rang.restype = d
+    lib.orc_rang.argtypes = [p, d, d]
+    lib.orc_repeat_bounds.restype = i
+    lib.orc_repeat_bounds.argtypes = [C.POINTER(i), C.POINTER(i), C.POINTER(d), C.POINTER(d), d, d, i, i, d]
+    lib.orc_stokes_chain.restype = None
+    lib.orc_stokes_chain.argtypes = [p, i, C.c_void_p]
     lib.orc_find.restype = i
     lib.orc_find.argtypes = [d, C.POINTER(d), i]
     lib.orc_philox4x32_10.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
@@ -248,6 +255,21 @@ class Oracle:
 
     def ran2(self) -> float:
         return self.lib.orc_ran2(self.h)
+
+    def rang(self, avg: float, sigma: float) -> float:
+        return self.lib.orc_rang(self.h, avg, sigma)
+
+    def repeat_bounds(self, cella, cellb, acur, bcur, amax, bmax, nag, nbg, delta):
+        """inttau2.f90:242-279 -> (status, cella, cellb, acur, bcur); status -1 = the Fortran's error stop."""
+        ca, cb, xa, xb = C.c_int(cella), C.c_int(cellb), C.c_double(acur), C.c_double(bcur)
+        rc = self.lib.orc_repeat_bounds(C.byref(ca), C.byref(cb), C.byref(xa), C.byref(xb), amax, bmax, nag, nbg, delta)
+        return rc, ca.value, cb.value, xa.value, xb.value
+
+    def stokes_chain(self, nsteps: int) -> np.ndarray:
+        """sourcephCO2 once, then stokes nsteps times (ran2 stream); rows of nxp nyp nzp cost sint cosp sinp phi."""
+        out = np.zeros((int(nsteps), 8), dtype=np.float64)
+        self.lib.orc_stokes_chain(self.h, int(nsteps), out.ctypes.data)
+        return out
 
     def ran2_state(self):
         return (self.lib.orc_ran2_idum(self.h), self.lib.orc_ran2_idum2(self.h), self.lib.orc_ran2_iy(self.h))

@@ -6,8 +6,9 @@ transliteration shows up as a mismatch against the other.  Python floats are IEE
 ``math`` calls the same libm as the C oracle, so the two must agree bit for bit.
 
 Follows /root/reference/src: ran2.f:1-33, sourceph.f90:7-49, inttau2.f90:7-239, stokes.f90:6-153,
-gridset.f90:23-31, mcpolar.f90:97-98,112,151-170.  PARITY UNPINNED BY THE REFERENCE (no upstream
-golden vectors; no Fortran compiler here).
+gridset.f90:23-31, mcpolar.f90:97-98,112,151-170.  No upstream golden vectors and no Fortran compiler here: pinned to
+what the reference's own source text computes when oracle/f90interp.py executes it (tests/test_oracle_reference_vectors.py),
+not to a compiled reference.
 
 Run as a script to regenerate tests/golden/oracle_kat.json.
 """

@@ -1,8 +1,9 @@
 /*
  * tamc_oracle.c -- plain-C fp64 restatement of the reference's photon Monte-Carlo hot path.
  *
- * TEST INFRASTRUCTURE ONLY (see tamc_oracle.h).  PARITY UNPINNED BY THE REFERENCE: no golden
- * vectors exist upstream and the Fortran cannot be built here; pinned instead by the KATs in
+ * TEST INFRASTRUCTURE ONLY (see tamc_oracle.h).  PARITY NOT PINNED BY A COMPILED REFERENCE: no golden
+ * vectors exist upstream and the Fortran cannot be built here; pinned instead, bit for bit, by outputs of the
+ * reference's own source text executed by oracle/f90interp.py (tests/golden/reference_interp.json.gz), by the KATs in
  * tests/golden/ and by oracle/pyref.py.
  *
  * Conventions that matter for trace-replay parity:
@@ -717,6 +718,25 @@ static void stokes(orc_state *o)
 }
 
 /* ------------------------------------------------------------------ the photon loop */
+
+double orc_rang(orc_state *o, double avg, double sigma) { return rang(o, avg, sigma); }
+int orc_repeat_bounds(int *cella, int *cellb, double *acur, double *bcur, double amax, double bmax, int nag, int nbg,
+                      double delta)
+{
+    return repeat_bounds(cella, cellb, acur, bcur, amax, bmax, nag, nbg, delta);
+}
+
+void orc_stokes_chain(orc_state *o, int nsteps, double *out)
+{
+    int xcell, ycell, zcell;
+    sourcephCO2(o, o->xmax, o->ymax, o->zmax, &xcell, &ycell, &zcell);
+    for (int s = 0; s < nsteps; ++s) {
+        stokes(o);
+        double *q = out + 8 * (size_t)s;
+        q[0] = o->nxp; q[1] = o->nyp; q[2] = o->nzp; q[3] = o->cost;
+        q[4] = o->sint; q[5] = o->cosp; q[6] = o->sinp; q[7] = o->phi;
+    }
+}
 
 static int exit_face(const orc_state *o, int xcell, int ycell, int zcell)
 {

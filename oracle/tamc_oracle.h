@@ -6,15 +6,20 @@
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it, and only as the checker / CPU baseline.
  *
- * PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, golden
- * vectors or fixtures, and it cannot be compiled here (Fortran + mpi_f08, no
- * Fortran front-end or MPI in the image).  This file is a plain-C, fp64,
- * statement-by-statement restatement of the Fortran sources (every function
- * cites the file:line it follows; -freal-4-real-8 promotion semantics from
- * src/Makefile:3).  What pins it instead: the hand-evaluated ran2 / first-packet
- * known answers of SURVEY.md section 8(c), an independent Python transliteration
- * (oracle/pyref.py), the analytic invariants of the shipped regime and, for the
- * scatter loop, Chandrasekhar's semi-infinite-slab reflectance (tests/test_oracle_*.py).
+ * PARITY: NOT PINNED BY A COMPILED REFERENCE -- the reference ships no tests, golden vectors or fixtures, and it cannot be
+ * compiled here (Fortran + mpi_f08, no Fortran front-end or MPI in the image).  This file is a plain-C, fp64,
+ * statement-by-statement restatement of the Fortran sources (every function cites the file:line it follows;
+ * -freal-4-real-8 promotion semantics from src/Makefile:3, no FMA contraction).  What pins it:
+ *   - outputs of the reference's OWN SOURCE TEXT (ran2.f, sourceph.f90, inttau2.f90, stokes.f90, gridset.f90, ch_opt.f90,
+ *     statement ranges of mcpolar.f90) executed by a Fortran-subset interpreter (oracle/f90interp.py, itself tested on
+ *     known-answer snippets); the vectors are committed with the script that made them
+ *     (tests/golden/make_reference_vectors.py -> reference_interp.json.gz) and this oracle reproduces them bit for bit:
+ *     2 100 packets of the shipped loop on three ranks, 700 stokes steps, 210 packets of the scatter loop, every voxel of
+ *     jmean, the generator state (tests/test_oracle_reference_vectors.py).  An interpreter written for the purpose is not
+ *     gfortran: its assumptions are listed in its header;
+ *   - the hand-evaluated ran2 / first-packet known answers of SURVEY.md section 8(c) and the Numerical Recipes sequence,
+ *     an independent Python transliteration (oracle/pyref.py), the analytic invariants of the shipped regime and, for the
+ *     scatter loop, Chandrasekhar's semi-infinite-slab reflectance and van de Hulst's slab (tests/test_oracle_*.py).
  */
 #ifndef TAMC_ORACLE_H
 #define TAMC_ORACLE_H
@@ -102,6 +107,14 @@ int orc_ran2_idum(const orc_state *o);
 int orc_ran2_idum2(const orc_state *o);
 int orc_ran2_iy(const orc_state *o);
 int orc_find(double val, const double *a, int n);
+/* sourcephCO2 once (sourceph.f90:7-49), then stokes (stokes.f90:6-153) nsteps times on the ran2 stream;
+ * out[8*s .. 8*s+7] = nxp nyp nzp cost sint cosp sinp phi after step s. */
+void orc_stokes_chain(orc_state *o, int nsteps, double *out);
+/* rang (sourceph.f90:73-101) on the ran2 stream; repeat_bounds (inttau2.f90:242-279): returns 0, or -1 where the
+ * Fortran stops with 'Error in Repeat_bounds...'.  Both are dead code upstream; the oracle's options call them. */
+double orc_rang(orc_state *o, double avg, double sigma);
+int orc_repeat_bounds(int *cella, int *cellb, double *acur, double *bcur, double amax, double bmax, int nag, int nbg,
+                      double delta);
 void orc_philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                        uint32_t out[4]);
 

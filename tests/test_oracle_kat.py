@@ -1,6 +1,7 @@
 """The C oracle against the committed known answers (tests/golden/oracle_kat.json, produced by the
 independent Python transliteration oracle/pyref.py) and against SURVEY.md 8(c)'s hand-evaluated values.
-Parity is unpinned by the reference itself: it ships no vectors and cannot be compiled here."""
+The reference ships no vectors and cannot be compiled here; tests/test_oracle_reference_vectors.py holds the stronger
+pin (outputs of the reference's own source text run by oracle/f90interp.py)."""
 import numpy as np
 import pytest
 
