@@ -71,6 +71,8 @@ class Cell:
             self.v = float(x)
         elif t == "i":
             self.v = int(x) if not isinstance(x, float) else int(math.trunc(x))
+        elif t == "c":
+            self.v = str(x)
         else:
             self.v = bool(x)
 
@@ -105,8 +107,63 @@ class FArray:
             x = math.trunc(x)
         self.a[self._ix(idx)] = x
 
+    def view(self, lb):
+        """The same storage under other lower bounds (an explicit-shape dummy associated with this array)."""
+        v = FArray.__new__(FArray)
+        v.t, v.a, v.lb = self.t, self.a, tuple(lb)
+        return v
+
+    def _np_index(self, idx):
+        """Subscripts with sections -> a numpy index (scalars drop their dimension, as in Fortran)."""
+        out = []
+        for k, (i, lo, n) in enumerate(zip(idx, self.lb, self.a.shape)):
+            if isinstance(i, Sec):
+                a = 0 if i.lo is None else i.lo - lo
+                b = n if i.hi is None else i.hi - lo + 1
+                if a < 0 or b > n:
+                    raise FortranError(f"section {i.lo}:{i.hi} of dimension {k + 1} outside [{lo}, {lo + n - 1}]")
+                out.append(slice(a, b))
+            else:
+                j = i - lo
+                if j < 0 or j >= n:
+                    raise FortranError(f"subscript {i} of dimension {k + 1} outside [{lo}, {lo + n - 1}]")
+                out.append(j)
+        return tuple(out)
+
+    def section(self, idx):
+        if len(idx) != self.a.ndim:
+            raise FortranError("rank mismatch in an array section")
+        part = self.a[self._np_index(idx)]
+        r = FArray.__new__(FArray)
+        r.t, r.a, r.lb = self.t, np.array(part, copy=True), (1,) * part.ndim
+        return r
+
+    def put_section(self, idx, x):
+        if len(idx) != self.a.ndim:
+            raise FortranError("rank mismatch in an array section")
+        self.a[self._np_index(idx)] = x.a if isinstance(x, FArray) else x
+
+    @staticmethod
+    def _wrap(a, like):
+        r = FArray.__new__(FArray)
+        r.t, r.a, r.lb = "r", np.asarray(a, dtype=np.float64), (1,) * np.ndim(a)
+        return r
+
+    # whole-array arithmetic (elementwise, binary64), e.g. mcpolar.f90:174  jmeanGLOBAL = jmeanGLOBAL * (scalar)
+    def __mul__(self, o): return FArray._wrap(self.a * (o.a if isinstance(o, FArray) else o), self)
+    def __rmul__(self, o): return FArray._wrap(o * self.a, self)
+    def __add__(self, o): return FArray._wrap(self.a + (o.a if isinstance(o, FArray) else o), self)
+    def __radd__(self, o): return FArray._wrap(o + self.a, self)
+    def __sub__(self, o): return FArray._wrap(self.a - (o.a if isinstance(o, FArray) else o), self)
+    def __rsub__(self, o): return FArray._wrap(o - self.a, self)
+    def __truediv__(self, o): return FArray._wrap(self.a / (o.a if isinstance(o, FArray) else o), self)
+    def __rtruediv__(self, o): return FArray._wrap(o / self.a, self)
+    def __neg__(self): return FArray._wrap(-self.a, self)
+
     def fill(self, x):
         if isinstance(x, FArray):
+            if x.a.shape != self.a.shape:
+                raise FortranError(f"array assignment of shape {x.a.shape} to shape {self.a.shape}")
             self.a[...] = x.a
         elif isinstance(x, list):
             if len(x) != self.a.size:
@@ -114,6 +171,14 @@ class FArray:
             self.a.reshape(-1, order="F")[...] = x
         else:
             self.a[...] = x
+
+
+class Sec:
+    """A subscript triplet lo:hi (stride 1); None = the bound of the dimension."""
+    __slots__ = ("lo", "hi")
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
 
 
 class ElemRef:
@@ -325,6 +390,7 @@ INTRINSICS = {
     "tan": math.tan, "acos": math.acos, "asin": math.asin, "atan": math.atan, "abs": abs,
     "min": _maxmin(min), "max": _maxmin(max), "int": lambda x: int(math.trunc(x)), "nint": lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5)),
     "floor": lambda x: int(math.floor(x)), "real": float, "dble": float, "mod": _fmod, "sign": _sign,
+    "trim": lambda c: c.rstrip(),
 }
 
 
@@ -421,6 +487,8 @@ class _Parser:
             else:
                 def div(f, a=left, b=right):
                     x, y = a(f), b(f)
+                    if isinstance(x, FArray) or isinstance(y, FArray):
+                        return x / y
                     if isinstance(x, int) and isinstance(y, int) and not isinstance(x, bool):
                         return _idiv(x, y)
                     return x / y if y != 0 else (math.copysign(math.inf, x) * math.copysign(1.0, y) if x != 0 else math.nan)
@@ -457,6 +525,10 @@ class _Parser:
         """An actual argument / subscript: returns (kind, payload, value closure); kind var | elem | expr."""
         start = self.i
         k, v = self.peek()
+        if v == ":":                                          # a section  :hi  or  :
+            self.take()
+            hi = None if self.peek()[1] in (",", ")") else self.parse_expr()
+            return ("sec", None, (lambda f, hi=hi: Sec(None, None if hi is None else int(hi(f)))))
         if k == "name":
             # a bare name, or name(subscripts), followed directly by , or ) : may be passed by reference
             j = self.i + 1
@@ -480,6 +552,10 @@ class _Parser:
                     return ("elem", (v, subs), self._call_or_index(v, subs))
         self.i = start
         e = self.parse_expr()
+        if self.peek()[1] == ":":                             # a section  lo:hi  or  lo:
+            self.take()
+            hi = None if self.peek()[1] in (",", ")") else self.parse_expr()
+            return ("sec", None, (lambda f, lo=e, hi=hi: Sec(int(lo(f)), None if hi is None else int(hi(f)))))
         return ("expr", None, e)
 
     def _name_value(self, name):
@@ -498,11 +574,15 @@ class _Parser:
     def _call_or_index(self, name, args):
         interp = self.interp
         vals = [a[2] for a in args]
+        has_sec = any(a[0] == "sec" for a in args)
 
         def run(f):
             x = f.get(name)
             if isinstance(x, FArray):
-                return x.get(tuple(v(f) for v in vals))
+                idx = tuple(v(f) for v in vals)
+                if has_sec:
+                    return x.section(idx)
+                return x.get(idx)
             if name == "size":
                 arr = vals[0](f)
                 return int(arr.a.size) if len(vals) == 1 else int(arr.a.shape[vals[1](f) - 1])
@@ -567,7 +647,9 @@ class Interpreter:
     def __init__(self):
         self.modules = {}
         self.procs = {}
-        self.counts = {}
+        self._blocks = {}
+        self.alias = {}              # a procedure pointer bound by the harness: name -> procedure name
+        self.skipped_calls = set()   # CALLs compiled to nothing besides mpi_* (e.g. checkallocate)
 
     # -- loading ---------------------------------------------------------------------------------------------------
     def load(self, path, fixed=None):
@@ -597,11 +679,12 @@ class Interpreter:
 
     @staticmethod
     def _proc_header(s):
-        m = re.match(r"^(?:(integer|real|logical|double\s+precision)\s+)?(subroutine|function)\s+(\w+)\s*(?:\(([^)]*)\))?$", s)
+        m = re.match(r"^((?:(?:elemental|pure|recursive)\s+)*)(?:(integer|real|logical|double\s+precision)\s+)?(subroutine|function)\s+(\w+)"
+                     r"\s*(?:\(([^)]*)\))?\s*(?:result\s*\(\s*(\w+)\s*\))?$", s)
         if not m:
             return None
-        args = [a.strip() for a in (m.group(4) or "").split(",") if a.strip()]
-        return m.group(3), m.group(2), args, m.group(1)
+        args = [a.strip() for a in (m.group(5) or "").split(",") if a.strip()]
+        return m.group(4), m.group(3), args, m.group(2), m.group(6), "elemental" in m.group(1)
 
     def _load_module(self, lines, i, name, file):
         mod = Module(name)
@@ -624,14 +707,14 @@ class Interpreter:
             m = re.match(r"^use\s+(\w+)", s)
             if m:
                 mod.uses.append(s)
-            elif s in ("implicit none", "save", "private", "public"):
+            elif s in ("implicit none", "save") or re.match(r"^(private|public|procedure)\b", s):
                 pass
             else:
                 self._declare(s, mod.vars, frame_for_eval=mod.vars, module=mod, where=f"{file}:{no}")
             i += 1
 
     def _load_proc(self, lines, i, hdr, file, host):
-        name, kind, args, rtype = hdr
+        name, kind, args, rtype, rname, elemental = hdr
         body = []
         i += 1
         while True:
@@ -641,10 +724,12 @@ class Interpreter:
             body.append((no, lab, s))
             i += 1
         self.procs[name] = Procedure(name, kind, args, body, file, host, rtype)
+        self.procs[name].result_name = rname or name
+        self.procs[name].elemental = elemental
         return i + 1
 
     def has_procedure(self, name):
-        return name in self.procs
+        return name in self.procs or name in self.alias
 
     # -- declarations ----------------------------------------------------------------------------------------------
     def _eval(self, text, frame):
@@ -695,11 +780,9 @@ class Interpreter:
         if not m:
             return False
         tname, _kind, attrs, dcolon, rest = m.groups()
-        if tname == "character":
-            return True
         if not dcolon and not rest:
             return False
-        t = {"integer": "i", "real": "r", "logical": "l"}.get(tname, "r")
+        t = {"integer": "i", "real": "r", "logical": "l", "character": "c"}.get(tname, "r")
         attrs = attrs.lower()
         is_param = "parameter" in attrs
         is_alloc = "allocatable" in attrs
@@ -718,8 +801,16 @@ class Interpreter:
             nm, dims = mm.group(1), mm.group(2) or (dim_attr.group(1) if dim_attr else None)
             if nm in self.procs and nm not in dummies and dims is None and (proc is None or nm != proc.name):
                 continue                                     # `real :: ran2` -- the type of an external function
-            if nm in dummies or (proc is not None and proc.kind == "function" and nm == proc.name):
-                continue                                     # bound to the actual argument / the function result
+            if proc is not None and proc.kind == "function" and nm == proc.result_name:
+                continue                                     # the function result
+            if nm in dummies:
+                if dims is not None and isinstance(scope.get(nm), FArray):
+                    specs = [d.strip() for d in _split_top(dims)]
+                    if all(d != ":" for d in specs):
+                        lbs = [int(self._eval(d.split(":")[0], frame_for_eval)) if ":" in d else 1 for d in specs]
+                        if len(lbs) == scope[nm].a.ndim and tuple(lbs) != scope[nm].lb:
+                            scope[nm] = scope[nm].view(lbs)
+                continue                                     # bound to the actual argument
             if dims is not None:
                 specs = [d.strip() for d in _split_top(dims)]
                 if is_alloc or any(d == ":" for d in specs):
@@ -858,6 +949,8 @@ class Interpreter:
                 raise _Goto(label)
             return go, pos + 1
         m = re.match(r"^call\s+(\w+)\s*(?:\((.*)\))?$", s)
+        if m and (m.group(1).startswith("mpi_") or m.group(1) in self.skipped_calls):
+            return (lambda f: None), pos + 1
         if m:
             name = m.group(1)
             args = []
@@ -970,7 +1063,13 @@ class Interpreter:
             if m:
                 name = m.group(1)
                 p = _Parser(tokenize(m.group(2) + ")"), self, s)
-                subs = [a[2] for a in p.parse_args()]
+                parsed = p.parse_args()
+                subs = [a[2] for a in parsed]
+                if any(a[0] == "sec" for a in parsed):
+                    def set_sec(f):
+                        v = val(f)
+                        f[name].put_section(tuple(x(f) for x in subs), v)
+                    return set_sec, pos + 1
 
                 def set_elem(f):
                     v = val(f)
@@ -1070,14 +1169,23 @@ class Interpreter:
         proc.static = None
 
     def call(self, name, actuals, want_result=False):
+        name = self.alias.get(name, name)
         proc = self.procs.get(name)
         if proc is None:
             raise FortranError(f"no procedure {name!r} is loaded")
         if proc.compiled is None:
             self._prepare(proc)
-        proc.calls += 1
         if len(actuals) != len(proc.args):
             raise FortranError(f"{name}: {len(actuals)} arguments for {len(proc.args)} dummies")
+        if proc.elemental and any(isinstance(a, FArray) for a in actuals):
+            # an elemental function referenced with array arguments: element by element, in array element order
+            shape = next(a.a.shape for a in actuals if isinstance(a, FArray))
+            out = FArray("r", shape)
+            for idx in np.ndindex(*shape):
+                scal = [Cell(a.t, (float if a.t == "r" else int)(a.a[idx])) if isinstance(a, FArray) else a for a in actuals]
+                out.a[idx] = self.call(name, scal, want_result=True)
+            return out
+        proc.calls += 1
         f = {}
         if proc.host is not None:
             for u in proc.host.uses:
@@ -1089,8 +1197,9 @@ class Interpreter:
             f[d] = a
         result = None
         if proc.kind == "function":
-            result = Cell({"integer": "i", "real": "r", "logical": "l"}.get(proc.result_type or "", None) or proc.types.get(name, "r"))
-            f[name] = result
+            result = Cell({"integer": "i", "real": "r", "logical": "l"}.get(proc.result_type or "", None) or
+                          proc.types.get(proc.result_name, "r"))
+            f[proc.result_name] = result
         # specification part, in source order (an F77 PARAMETER may sit between two type statements and size an array of
         # the second).  Locals are fresh and undefined at every call; SAVE'd / DATA-initialised ones are created at the
         # first call and persist.
@@ -1136,11 +1245,15 @@ class Interpreter:
     # -- statement ranges of a main program -------------------------------------------------------------------------------
     def run_block(self, path, first_line, last_line, frame):
         """Executes the statements of source lines first_line..last_line of a free-form file in `frame` (name -> Cell / FArray)."""
-        text = open(path).read().splitlines()
-        chunk = "\n".join(text[first_line - 1:last_line])
-        stmts = logical_lines(chunk, False)
-        stmts = [(no + first_line - 1, lab, s) for no, lab, s in stmts]
-        block, _ = self._compile_block(stmts, 0, (), {"where": path})
+        key = (path, first_line, last_line)
+        block = self._blocks.get(key)
+        if block is None:
+            text = open(path).read().splitlines()
+            chunk = "\n".join(text[first_line - 1:last_line])
+            stmts = logical_lines(chunk, False)
+            stmts = [(no + first_line - 1, lab, s) for no, lab, s in stmts]
+            block, _ = self._compile_block(stmts, 0, (), {"where": path})
+            self._blocks[key] = block
         self._execute(block, frame)
 
 

@@ -11,8 +11,11 @@
  *   3dFD.f90:424-466            Arrhenius
  *   mcpolar.f90:123-140,174     temperature boundary set-up, total_time override, jmean scaling
  *
- * TEST INFRASTRUCTURE ONLY, like tamc_oracle.c.  PARITY UNPINNED BY THE REFERENCE (no upstream
- * vectors, no Fortran compiler here).  Variable names follow the Fortran; every `real` is a double
+ * TEST INFRASTRUCTURE ONLY, like tamc_oracle.c.  No upstream vectors and no Fortran compiler here: pinned, bit for bit,
+ * to what the reference's own text computes for one rank when oracle/f90interp.py executes it (the time loop of
+ * heat_sim_3D, Arrhenius, setupThermalCoeff, initThermalCoeff's arithmetic, the getPwr functions, thermalConst_mod.f90,
+ * the driver lines of mcpolar.f90; tests/golden/reference_interp_heat.json.gz, tests/test_oracle_reference_heat.py) --
+ * not to a compiled reference.  Variable names follow the Fortran; every `real` is a double
  * (-freal-4-real-8).  Quirks kept: dx,dy,dz use numpoints+2 while volumeVoxel uses nxg (:249-251,
  * :287); the negative-temperature check looks at the INPUT temp (:179); pulsesDone starts at 0
  * (uninitialised upstream); the "six neighbours ablated" rule reads neighbours in sweep order, i.e.
@@ -47,6 +50,9 @@ typedef struct {
 static const double airHeatCap = 1.006e3, lw = 2256.e3;
 static const double waterContentInit = .75, proteinContent = 1. - .75;
 
+/* (thermalConst_mod.f90:20-23 stops the program when T < 0 -- the explicit scheme has diverged in an air voxel; the oracle
+ * goes on with whatever exp() returns, and tests/test_oracle_reference_heat.py checks that condition at the iteration where
+ * the reference's own text stops) */
 static double airThermalCond(double T)
 {
     const double a = -0.188521, b = 0.000367259, c = 0.212453;

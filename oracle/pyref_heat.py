@@ -4,7 +4,9 @@ TEST INFRASTRUCTURE ONLY.  Written separately from oracle/heat_oracle.c (dict-of
 index triples instead of flat buffers, one function per Fortran routine) so that a slip in one transliteration
 shows up as a mismatch against the other; both use IEEE doubles and the same libm, so they must agree bit
 for bit.  Follows /root/reference/src: thermalConst_mod.f90:1-88, 3dFD.f90:21-230 (numproc = 1), :233-309,
-:312-361, :365-421, :424-466, mcpolar.f90:65-71,123-140,174.  PARITY UNPINNED BY THE REFERENCE.
+:312-361, :365-421, :424-466, mcpolar.f90:65-71,123-140,174.  Not pinned by a compiled reference; oracle/heat_oracle.c, which
+this file must equal bit for bit, reproduces what oracle/f90interp.py computes from the reference's own text
+(tests/test_oracle_reference_heat.py).
 """
 from __future__ import annotations
 

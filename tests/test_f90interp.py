@@ -238,3 +238,84 @@ def test_tokens_that_look_alike():
     assert kinds("250d-4") == ["250d-4"]
     ll = logical_lines("a = 1 &\n  + 2 ! c\n100 continue\nb = 'x!y'")
     assert [(lab, s) for _, lab, s in ll] == [(None, "a = 1 + 2"), ("100", "continue"), (None, "b = 'x!y'")]
+
+
+SRC2 = """
+module props
+   implicit none
+   real, parameter :: w0 = .75
+   real :: scale
+   real, allocatable :: field(:,:,:)
+   character(len=16) :: mode
+   procedure(pa), pointer :: pick => null()
+   private
+   public :: scale, field
+contains
+   elemental real function clip(x, hi)
+      real, intent(IN) :: x, hi
+      clip = max(min(w0 - w0 * (x / scale), hi), 0.0)
+   end function clip
+
+   real function pa() result (val)
+      val = 2.d0 * scale
+   end function pa
+
+   real function pb() result (val)
+      if (scale > 1.) then
+         val = -1.
+         return
+      end if
+      val = scale
+   end function pb
+
+   subroutine shifted(t, np)
+      integer, intent(IN)    :: np
+      real,    intent(INOUT) :: t(0:np+1, 0:np+1)
+      t(0, np+1) = 7.
+      t(np+1, 0) = t(np+1, 0) + 1.
+   end subroutine shifted
+end module props
+"""
+
+
+def test_sections_array_arithmetic_elemental_result_clause_strings_and_dummy_bounds():
+    x = Interpreter()
+    x.load_text(SRC2)
+    assert x.procs["clip"].elemental and x.procs["pa"].result_name == "val" and x.var("props", "mode").t == "c"
+    g = x.allocate("props", "field", (4, 4, 3), (0, 0, 1))
+    f = {"field": g, "scale": x.var("props", "scale"), "mode": x.var("props", "mode"), "n": Cell("i", 2), "q": FArray("r", (2, 2)),
+         "w": FArray("r", (2, 2)), "flag": Cell("l")}
+    src = "\n".join([
+        "scale = 4.",
+        "field = 1.5",                         # whole array
+        "field(n+1,:,:) = 2.",                 # a plane
+        "field(1:n,1:n,2) = 9.",               # a box of one plane
+        "field(:,:,3) = field(:,:,1) * (scale/8.) + 1.",   # section on both sides, array arithmetic
+        "q = field(1:n,1:n,2)",
+        "w = clip(q, .5)",                     # elemental over an array
+        "mode = 'gaussian'",
+        "flag = trim(mode) == \"gaussian\"",
+    ])
+    import tempfile, os
+    with tempfile.NamedTemporaryFile("w", suffix=".f90", delete=False) as t:
+        t.write(src)
+    try:
+        x.run_block(t.name, 1, 9, f)
+    finally:
+        os.unlink(t.name)
+    a = g.a                                  # stored 0-based: a[i, j, k-1]
+    assert a[3, 0, 0] == 2.0 and a[0, 0, 0] == 1.5 and a[1, 1, 1] == 9.0 and a[0, 1, 1] == 1.5 and a[3, 2, 1] == 2.0
+    assert a[3, 1, 2] == 2.0 * 0.5 + 1 and a[0, 0, 2] == 1.5 * 0.5 + 1
+    assert (f["q"].a == 9.0).all()
+    assert (f["w"].a == max(min(0.75 - 0.75 * (9.0 / 4.0), 0.5), 0.0)).all() and f["flag"].v is True
+    # result clause, RETURN with the result set, a procedure pointer bound by the harness
+    assert x.call("pa", [], want_result=True) == 8.0 and x.call("pb", [], want_result=True) == -1.0
+    x.alias["pick"] = "pb"
+    x.var("props", "scale").set(0.25)
+    assert x.call("pick", [], want_result=True) == 0.25
+    # an explicit-shape dummy with its own lower bounds over the caller's storage
+    t2 = FArray("r", (4, 4))                 # bounds 1:4 in the caller
+    x.call("shifted", [t2, Cell("i", 2)])
+    assert t2.a[0, 3] == 7.0 and t2.a[3, 0] == 1.0
+    with pytest.raises(FortranError, match="shape"):
+        f["q"].fill(g)
