@@ -19,8 +19,9 @@ What the harness does instead of the reference (each place cites the line it sta
   * the grid size: constants.f90:12's nxg = nyg = nzg = 80 are compile-time parameters; the harness sets them to a small n
     before anything is allocated (the reference's user edits that line to change the grid);
   * Heat's module variable pulsesDone is never initialised upstream (3dFD.f90:12, first use :203): static storage, 0;
-  * the tally jmean of every MC call is synthetic (seeded, sparse, the same numbers the test feeds the oracle): this
-    file pins the heat step, tests/golden/make_reference_vectors.py pins the transport.
+  * in the `cases` the tally jmean of every MC call is synthetic (seeded, sparse, the same numbers the test feeds the
+    oracle); in `coupled` it is the reference's own photon loop (mcpolar.f90:151-170 with ran2.f, sourceph.f90, inttau2.f90)
+    on the opacity the previous property update left behind -- the whole `do while(time <= total_time)` iteration.
 """
 import gzip
 import json
@@ -64,10 +65,11 @@ def synthetic_jmean(rng, n):
 
 
 class Machine:
-    def __init__(self, n, xmax, ymax, zmax, pulsetype, power, energy, total_time, loops, rep_rate, pulses, ablate, nphotons):
+    def __init__(self, n, xmax, ymax, zmax, pulsetype, power, energy, total_time, loops, rep_rate, pulses, ablate, nphotons,
+                 extra_files=()):
         it = self.it = Interpreter()
         it.skipped_calls.add("checkallocate")
-        for f in FILES:
+        for f in FILES + tuple(extra_files):
             it.load(os.path.join(REF, f))
         for k in ("nxg", "nyg", "nzg"):
             it.var("constants", k).set(n)                       # constants.f90:12 (see the header)
@@ -177,6 +179,57 @@ class Machine:
         return out
 
 
+TRANSPORT_FILES = ("ran2.f", "sourceph.f90", "inttau2.f90")
+
+
+def run_coupled_case(n, npackets, pulsetype, power, energy, loops, iterations, ablate=150.0, rank=0, extents=(0.03, 0.03, 0.06)):
+    """mcpolar.f90:148-186 as it stands: the photon loop (:151-170, the reference's ran2 stream running on from call to call)
+    on the opacity the last property update left behind, the tally scaled (:174) into the heat step, Arrhenius, the property
+    update -- every iteration, until the reference stops."""
+    m = Machine(n, *extents, pulsetype, power, energy, 2.0, loops, 1e7, 1, ablate, npackets,
+                extra_files=TRANSPORT_FILES)
+    it, fr = m.it, m.fr
+    for k, t in (("iseed", "i"), ("delta", "r"), ("nscatt", "r"), ("tflag", "l"), ("xcell", "i"), ("ycell", "i"), ("zcell", "i"), ("j", "i")):
+        fr[k] = Cell(t)
+    for k, v in it.modules["photon_vars"].vars.items():
+        fr[k] = v
+    fr["id"].set(rank)
+    it.run_block(MC, 97, 98, fr)                                  # seed rule
+    it.run_block(MC, 112, 113, fr)                                # delta
+    ran2, wall = it.procs["ran2"], it.procs["wall_dist"]
+    h = lambda k: it.var("heat", k).v
+    case = {"n": n, "extents": list(extents), "pulsetype": pulsetype, "power": power, "energyPerPixel": energy, "loops": loops,
+            "ablateTemp": ablate, "nphotons": npackets, "rank": rank, "init": m.snapshot(), "steps": []}
+    for i in range(iterations):
+        if not fr["time"].v <= fr["total_time"].v:               # :148
+            break
+        mc = None
+        try:
+            if fr["laser_flag"].v:                                # :149
+                d0, s0 = ran2.calls, wall.calls
+                it.run_block(MC, 151, 170, fr)                    # do j = 1, nphotons ... end do
+                mc = {"draws": ran2.calls - d0, "voxel_steps": wall.calls - s0, "iseed": fr["iseed"].v,
+                      "jmean_sum": hexf(exact_sum(fr["jmean"].a)), "jmean_nonzero": int((fr["jmean"].a != 0).sum())}
+                fr["jmeanglobal"].a[...] = fr["jmean"].a          # :173  MPI_allREDUCE, one rank
+                it.run_block(MC, 174, 174, fr)
+            m.heat_sim_3d()                                       # :178
+            it.run_block(MC, 180, 185, fr)
+        except Exception as e:
+            if "ERROR STOP" not in str(e):
+                raise
+            case["error_stop"] = {"iteration": i, "where": str(e).split(" at ")[-1].replace(REF + "/", "")}
+            break
+        snap = m.snapshot()
+        rk = fr["rhokap"].a
+        case["steps"].append({"mc": mc, "digest": snap if i % 9 == 0 else None, "temp_max": hexf(fr["temp"].a.max()),
+                              "temp_sum": hexf(exact_sum(fr["temp"].a)), "ablated": int((rk[1:-1, 1:-1, 1:-1] == 0).sum()),
+                              "q_sum": hexf(exact_sum(it.var("heat", "q").a)), "rhokap_sum": hexf(exact_sum(rk)),
+                              "tissue_sum": hexf(exact_sum(fr["tissue"].a)), "time": snap["time"], "laser_flag": snap["laser_flag"]})
+    case["last"] = m.snapshot() if "error_stop" not in case else None
+    print("coupled", pulsetype, n, "iterations", len(case["steps"]), case.get("error_stop"), flush=True)
+    return case
+
+
 def run_case(n, pulsetype, power, energy, loops, iterations, seed, ablate=150.0, total_time=2.0, rep_rate=1e7, pulses=1,
              nphotons=1000, extents=(0.03, 0.03, 0.06)):
     m = Machine(n, *extents, pulsetype, power, energy, total_time, loops, rep_rate, pulses, ablate, nphotons)
@@ -228,6 +281,7 @@ def main():
                     # three short pulses with pauses, no boiling: the laser on / off bookkeeping of 3dFD.f90:199-214
                     run_case(6, "tophat", 70.0, 40.0, 1, 70, 11, ablate=150.0, nphotons=5000000, rep_rate=0.1, pulses=3,
                              extents=(0.03, 0.03, 0.03))]
+    out["coupled"] = [run_coupled_case(8, 150, "tophat", 8.0, 400.0, 1, 40)]
     print("cases done", round(time.time() - t0, 1), flush=True)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_interp_heat.json.gz")
     with gzip.GzipFile(path, "wb", compresslevel=9, mtime=0) as g:

@@ -104,3 +104,46 @@ def test_coupled_iterations_bit_for_bit(ref, which):
     else:
         _check_snapshot(h, c["final"], "final")
         assert lasers == {0, 1} and int(h.scalar("pulsesDone")) >= 2      # pulses ended and started again
+
+
+def test_whole_coupled_iteration_bit_for_bit(ref):
+    """mcpolar.f90:148-186 as the reference's text runs it for one rank: the photon loop (ran2 stream running on from call to
+    call) on the opacity the previous property update left behind -> the scaled tally -> heat step -> Arrhenius -> property
+    update, 28 iterations through boiling and ablation until the reference stops.  The two C oracles, coupled the same way."""
+    c = ref["coupled"][0]
+    n, npk = c["n"], c["nphotons"]
+    h = orc.HeatOracle(n, *c["extents"])
+    h.init(power=c["power"], energyPerPixel=c["energyPerPixel"], loops=c["loops"], pulsetype=c["pulsetype"])
+    _check_snapshot(h, c["init"], "init")
+    o = orc.Oracle(n, n, n, *c["extents"])
+    o.init_opt1()                                                   # albedo 0, hgg 0.9 (ch_opt.f90:15-23)
+    o.seed_ran2(c["rank"])
+    jglobal = np.zeros((n, n, n), order="F")
+    assert len(c["steps"]) >= 25
+    for i, step in enumerate(c["steps"]):
+        assert h.scalar("time") <= h.scalar("total_time")
+        if h.scalar("laser_flag"):
+            o.set_rhokap(h.array("rhokap"))                         # the property update rewrote iarray's rhokap in place
+            o.zero_jmean()                                          # :185 of the previous iteration
+            st = o.run(npk)["stats"]
+            mc = step["mc"]
+            assert (st["draws"], st["voxel_steps"]) == (mc["draws"], mc["voxel_steps"]), (i, st, mc)
+            assert o.ran2_state()[0] == mc["iseed"] and hexf(exact_sum(o.jmean)) == mc["jmean_sum"], i
+            assert int((o.jmean != 0).sum()) == mc["jmean_nonzero"]
+            jglobal[...] = o.jmean
+            h.scale_jmean(jglobal, float(npk))
+        else:
+            assert step["mc"] is None
+        h.sim_3d(jglobal, i)
+        h.arrhenius()
+        h.setup_thermal_coeff(c["ablateTemp"])
+        rk = h.array("rhokap")
+        got = {"temp_max": hexf(h.array("temp").max()), "temp_sum": hexf(exact_sum(h.array("temp"))),
+               "ablated": int((rk[1:-1, 1:-1, 1:-1] == 0).sum()), "q_sum": hexf(exact_sum(h.array("Q"))),
+               "rhokap_sum": hexf(exact_sum(rk)), "tissue_sum": hexf(exact_sum(h.array("tissue"))),
+               "time": hexf(h.scalar("time")), "laser_flag": int(h.scalar("laser_flag"))}
+        for k, v in got.items():
+            assert v == step[k], (i, k, v, step[k])
+        if step["digest"] is not None:
+            _check_snapshot(h, step["digest"], i)
+    assert got["ablated"] > 0 and exact_sum(h.array("Q")) > 0 and c["error_stop"]["iteration"] == len(c["steps"])
