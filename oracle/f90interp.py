@@ -867,8 +867,7 @@ class Interpreter:
         mod = self.modules.get(m.group(1))
         if mod is None:
             raise FortranError(f"module {m.group(1)!r} is not loaded")
-        for u in mod.uses:
-            pass                                              # (no module of the interpreted set re-exports another)
+        # (no module of the interpreted set re-exports what it uses, so `use` does not chain)
         if m.group(2):
             for item in m.group(2).split(","):
                 item = item.strip()
@@ -1166,7 +1165,6 @@ class Interpreter:
                      if re.match(r"^use\s", s) or re.match(r"^(parameter\s*\(|save\b|data\s)", s) or
                      (_DECL.match(s) and ("::" in s or not re.match(r"^\w+\s*(\(|=)", s)))]
         proc.types = self._dummy_types(proc)
-        proc.static = None
 
     def call(self, name, actuals, want_result=False):
         name = self.alias.get(name, name)
@@ -1255,21 +1253,3 @@ class Interpreter:
             block, _ = self._compile_block(stmts, 0, (), {"where": path})
             self._blocks[key] = block
         self._execute(block, frame)
-
-
-class _Chain(dict):
-    """Name lookup for declaration expressions: the entities declared so far, then the enclosing frame."""
-
-    def __init__(self, first, second):
-        super().__init__()
-        self.first, self.second = first, second
-
-    def __getitem__(self, k):
-        if k in self.first:
-            return self.first[k]
-        return self.second[k]
-
-    def get(self, k, default=None):
-        if k in self.first:
-            return self.first[k]
-        return self.second.get(k, default)
