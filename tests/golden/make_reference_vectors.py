@@ -100,7 +100,13 @@ def shipped(rank, npackets):
         d0, s0 = ran2.calls, wall.calls
         it.run_block(mc, 153, 169, fr)                                     # tflag = F; sourcephCO2; tauint1; the stub
         rows.append(packet_row(it, fr, ran2.calls - d0, wall.calls - s0))
+    faces = {k: [hexf(x) for x in it.var("iarray", k).a] for k in ("xface", "yface", "zface")}
+    rk = it.var("iarray", "rhokap").a
+    optics = {k: hexf(it.var("opt_prop", k).v) for k in ("hgg", "g2", "mua", "mus", "kappa", "albedo", "mu_water", "mu_protein")}
     return {"rank": rank, "seed": seed0, "delta": hexf(fr["delta"].v), "kappa": hexf(it.var("opt_prop", "kappa").v),
+            "faces": faces, "optics": optics,
+            "rhokap_interior": sorted({hexf(x) for x in rk[1:-1, 1:-1, 1:-1].ravel()}),
+            "rhokap_halo_sum": hexf(float(rk.sum() - rk[1:-1, 1:-1, 1:-1].sum())),
             "grid": n, "extents": [0.03, 0.03, 0.06], "first_draws": first_draws, "packets": rows,
             "jmean": sparse(it.var("iarray", "jmean").a), "iseed_after": fr["iseed"].v}
 

@@ -150,3 +150,27 @@ def test_dead_code_the_options_are_built_on(ref):
         assert rc == c["status"], c
         if rc == 0:
             assert [ca, cb, bits(xa), bits(xb)] == c["out"], (c, ca, cb, xa, xb)
+
+
+def test_set_up_routines_and_their_host_side_mirror(ref):
+    """gridset.f90 (faces, rhokap with its zero halo), ch_opt.f90 init_opt1 and mcpolar.f90:112 (delta) as the reference's text
+    computes them, against the C oracle and against the host-side mirror the binding and the driver shim use (tamc.mcgrid)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tissue-ablation-mc_b200"))
+    from tamc import mcgrid
+
+    v = ref["shipped"][0]
+    n = v["grid"]
+    o = orc.Oracle(n[0], n[1], n[2], *v["extents"])
+    xf, yf, zf, rk = mcgrid.gridset(*v["extents"], *n)
+    of = o.faces()
+    for name, mine, theirs in (("xface", xf, of[0]), ("yface", yf, of[1]), ("zface", zf, of[2])):
+        assert [bits(x) for x in mine] == v["faces"][name], name
+        assert [bits(x) for x in theirs] == v["faces"][name], name
+    opt = mcgrid.init_opt1()
+    for k, h in v["optics"].items():
+        assert bits(opt[k]) == h, k
+    assert bits(mcgrid.delta_for(v["extents"][2], n[2])) == v["delta"]
+    assert v["rhokap_interior"] == [v["kappa"]] and unhex(v["rhokap_halo_sum"]) == 0.0
+    assert sorted({bits(x) for x in rk[1:-1, 1:-1, 1:-1].ravel()}) == [v["kappa"]] and rk.sum() == rk[1:-1, 1:-1, 1:-1].sum()
