@@ -111,6 +111,26 @@ def shipped(rank, npackets):
             "jmean": sparse(it.var("iarray", "jmean").a), "iseed_after": fr["iseed"].v}
 
 
+def crater(rank, npackets):
+    """The shipped loop on an opacity with holes -- test INPUT, written where 3dFD.f90:334-353 writes it: a transparent shaft
+    under the beam axis (packets cross every voxel of their column and leave through the bottom face: find() = -1, tflag set
+    by tauint1), a shallow crater beside it, a water-depleted rim."""
+    it, fr, n = machine(0.03, 0.03, 0.06, rank)
+    rk = it.var("iarray", "rhokap").a                      # stored 0-based with the halo: rk[i, j, k] = rhokap(i, j, k)
+    rk[39:43, 39:43, 1:n[2] + 1] = 0.0                     # shaft: i, j = 39..42, every k
+    rk[43:47, 36:47, n[2] - 5:n[2] + 1] = 0.0              # crater six voxels deep
+    rk[47:49, 36:47, 1:n[2] + 1] = 0.5 * 510.0 + 170.0     # rim: w * mu_water + mu_protein (3dFD.f90:343)
+    ran2, wall = it.procs["ran2"], it.procs["wall_dist"]
+    mc = os.path.join(REF, "mcpolar.f90")
+    rows = []
+    for _ in range(npackets):
+        d0, s0 = ran2.calls, wall.calls
+        it.run_block(mc, 153, 169, fr)
+        rows.append(packet_row(it, fr, ran2.calls - d0, wall.calls - s0))
+    return {"rank": rank, "grid": n, "extents": [0.03, 0.03, 0.06], "packets": rows, "jmean": sparse(it.var("iarray", "jmean").a),
+            "iseed_after": fr["iseed"].v, "left_through_the_bottom": sum(1 for r in rows if r[8] == -1)}
+
+
 def stokes_chain(hgg, nsteps, rank=0):
     """stokes.f90 applied again and again to the direction sourcephCO2 leaves behind."""
     it, fr, n = machine(0.03, 0.03, 0.06, rank)
@@ -185,6 +205,7 @@ def main():
            "row": "xp yp zp nxp nyp nzp (binary64 hex) xcell ycell zcell tflag draws voxel_steps [scatterings absorbed]"}
     out["shipped"] = [shipped(0, 1500), shipped(1, 300), shipped(7, 300)]
     print("shipped done", round(time.time() - t0, 1), flush=True)
+    out["crater"] = crater(2, 400)
     out["stokes"] = [stokes_chain(0.9, 400), stokes_chain(0.0, 100), stokes_chain(0.5, 200, rank=3)]
     print("stokes done", round(time.time() - t0, 1), flush=True)
     out["dead_code"] = dead_code()

@@ -174,3 +174,26 @@ def test_set_up_routines_and_their_host_side_mirror(ref):
     assert bits(mcgrid.delta_for(v["extents"][2], n[2])) == v["delta"]
     assert v["rhokap_interior"] == [v["kappa"]] and unhex(v["rhokap_halo_sum"]) == 0.0
     assert sorted({bits(x) for x in rk[1:-1, 1:-1, 1:-1].ravel()}) == [v["kappa"]] and rk.sum() == rk[1:-1, 1:-1, 1:-1].sum()
+
+
+def test_shipped_loop_on_an_opacity_with_holes(ref):
+    """A transparent shaft (packets leave through the bottom face: find() = -1, tauint1 sets tflag), a shallow crater and a
+    water-depleted rim under the beam: the reference's text against both oracles."""
+    v = ref["crater"]
+    n = v["grid"]
+    rk = np.zeros((n[0] + 2, n[1] + 2, n[2] + 2), order="F")
+    rk[1:-1, 1:-1, 1:-1] = 680.0
+    rk[39:43, 39:43, 1:n[2] + 1] = 0.0
+    rk[43:47, 36:47, n[2] - 5:n[2] + 1] = 0.0
+    rk[47:49, 36:47, 1:n[2] + 1] = 0.5 * 510.0 + 170.0
+    o = orc.Oracle(n[0], n[1], n[2], *v["extents"])
+    o.set_rhokap(rk)
+    o.set_optics(0.0, 0.9)
+    o.seed_ran2(v["rank"])
+    out = o.run(len(v["packets"]), records=True)
+    _check_packets(v["packets"], out["records"])
+    assert v["left_through_the_bottom"] >= 5 and out["stats"]["exits"][4] == v["left_through_the_bottom"]
+    assert np.array_equal(o.jmean, _dense(v["jmean"], n)) and o.ran2_state()[0] == v["iseed_after"]
+    tally, pk = pyref.photon_loop(len(v["packets"]), n[0], n[1], n[2], *v["extents"], lambda i, j, k: float(rk[i, j, k]),
+                                  pyref.Ran2(v["rank"]))
+    _check_pyref(v["packets"], pk, tally, v["jmean"])
